@@ -1,0 +1,880 @@
+// vgs_b200.cu — host pipeline + C ABI (include/vgs_b200.h) of the VGS/SVGS hot path on sm_100a.
+// No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/vgs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "vgs_kernels.cuh"
+
+using namespace vgs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+struct vgs_context {
+  int mode = 0, device = 0, leaf_order = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+
+  // input
+  const float* d_xyz = nullptr;
+  int stride = 3;
+  int64_t n = 0;
+  DBuf xyz_own;
+  const int32_t* d_labels = nullptr;
+  int32_t max_label = 0;
+  DBuf labels_own;
+
+  // octree
+  float voxel_size = 0;
+  Box box{};
+  int depth = 0;
+  int64_t n_finite = 0;
+  EpochTable ep{};
+  bool voxelized = false;
+  int64_t n_voxels = 0;   // octree leaves (VGS units; SVGS: getVoxelNum only)
+
+  // units
+  int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
+  int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
+  bool have_units = false, have_features = false, have_adj = false, have_segments = false;
+  int64_t n_used = 0, n_adj = 0, n_pairs = 0, max_n = 0, n_singles = 0, n_attached = 0, closest_rounds = 0;
+  int last_voxels_min = std::numeric_limits<int>::min();
+  bool have_cluster_stats = false;
+  int64_t n_clusters_all = 0, n_clusters_exp = 0;
+  int points_min = 0;
+  float graph_size = 0;
+
+  // device buffers
+  DBuf keysA, keysB, valsA, valsB, hist, tiles, flags, scan, small;
+  DBuf ustart, ukey, pos_unit, rec, key3, center, plainm, tk, tv, stencil;
+  DBuf adj_cnt, adj_off, adj_idx, class_count, class_list;
+  DBuf conn0_cnt, conn0_idx, conn1_cnt, conn1_idx, attach, parent, root, csize, cminpt, labels_out, tmp;
+  uint64_t* d_keys = nullptr;   // sorted keys (points to keysA or keysB)
+  uint32_t* d_perm = nullptr;   // sorted point indices
+  uint64_t hmask = 0;
+
+  vgs_timings tm{};
+  cudaEvent_t ev[16] = {};
+
+  vgs_status fail(vgs_status s, const std::string& m) { err = m; return s; }
+  vgs_status fail_cuda(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at vgs_b200.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+    err = buf;
+    return VGS_ERR_CUDA;
+  }
+};
+
+#define CK(x)                                                                 \
+  do {                                                                        \
+    cudaError_t e_ = (x);                                                     \
+    if (e_ != cudaSuccess) return h->fail_cuda(e_, #x, __LINE__);             \
+  } while (0)
+#define LAUNCH(kernel, grid, block, smem, ...)                                \
+  do {                                                                        \
+    kernel<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__);              \
+    h->launches++;                                                            \
+    CK(cudaGetLastError());                                                   \
+  } while (0)
+
+namespace {
+
+// exclusive scan of n u32 (in -> out, may alias); total (u64) read back to the host if total != null
+vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* total_host) {
+  int64_t nt = cdiv(n, SC_TILE);
+  if (nt < 1) nt = 1;
+  CK(h->tiles.reserve((size_t)(nt + 1) * 4 + 16));
+  CK(h->small.reserve(4096));
+  unsigned long long* d_total = h->small.as<unsigned long long>() + 8;
+  LAUNCH(k_scan_reduce, (unsigned)nt, SC_THREADS, 0, in, n, h->tiles.as<uint32_t>());
+  LAUNCH(k_scan_tiles, 1, 1024, 0, h->tiles.as<uint32_t>(), nt, d_total);
+  LAUNCH(k_scan_down, (unsigned)nt, SC_THREADS, 0, in, out, n, h->tiles.as<uint32_t>());
+  if (total_host) {
+    CK(cudaMemcpyAsync(total_host, d_total, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return VGS_OK;
+}
+
+// stable LSD radix sort of (key,val) over the low nbits bits; result pointers returned
+vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out) {
+  uint64_t* ka = h->keysA.as<uint64_t>(); uint64_t* kb = h->keysB.as<uint64_t>();
+  uint32_t* va = h->valsA.as<uint32_t>(); uint32_t* vb = h->valsB.as<uint32_t>();
+  int64_t nblk = cdiv(n, RS_TILE);
+  if (nblk < 1) nblk = 1;
+  CK(h->hist.reserve((size_t)nblk * 256 * 4));
+  for (int shift = 0; shift < nbits; shift += 8) {
+    LAUNCH(k_rs_hist, (unsigned)nblk, RS_THREADS, 0, ka, n, shift, h->hist.as<uint32_t>(), nblk);
+    vgs_status s = scan_u32(h, h->hist.as<uint32_t>(), h->hist.as<uint32_t>(), nblk * 256, nullptr);
+    if (s) return s;
+    LAUNCH(k_rs_scatter, (unsigned)nblk, RS_THREADS, 0, ka, va, kb, vb, n, shift, h->hist.as<uint32_t>(), nblk);
+    std::swap(ka, kb); std::swap(va, vb);
+  }
+  *keys_out = ka; *vals_out = va;
+  return VGS_OK;
+}
+
+// sorted keys -> unit table.  n_valid = number of sorted positions with key < sentinel.
+vgs_status build_units(vgs_handle h, const uint64_t* keys, int64_t n_valid, int64_t* n_units) {
+  if (n_valid <= 0) { *n_units = 0; return VGS_OK; }
+  CK(h->flags.reserve((size_t)n_valid * 4));
+  CK(h->scan.reserve((size_t)n_valid * 4));
+  CK(h->pos_unit.reserve((size_t)n_valid * 4));
+  LAUNCH(k_head_flags, (unsigned)cdiv(n_valid, 256), 256, 0, keys, n_valid, h->flags.as<uint32_t>());
+  unsigned long long total = 0;
+  vgs_status s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid, &total);
+  if (s) return s;
+  *n_units = (int64_t)total;
+  CK(h->ustart.reserve((size_t)(total + 1) * 4));
+  CK(h->ukey.reserve((size_t)(total + 1) * 8));
+  LAUNCH(k_head_write, (unsigned)cdiv(n_valid, 256), 256, 0, keys, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid,
+         h->ustart.as<uint32_t>(), h->ukey.as<uint64_t>(), h->pos_unit.as<uint32_t>());
+  uint32_t endv = (uint32_t)n_valid;
+  CK(cudaMemcpyAsync(h->ustart.as<uint32_t>() + total, &endv, 4, cudaMemcpyHostToDevice, h->stream));
+  return VGS_OK;
+}
+
+// ---- PCL dynamic bounding box on the host side of stage 0 (octree_pointcloud.hpp
+//      adoptBoundingBoxToPoint / getKeyBitSize); the device only finds the next violating point ----
+struct OctState {
+  double mn[3], mx[3], res;
+  unsigned depth = 0;
+  bool defined = false;
+  struct Ev { unsigned lowered, depth_old; };
+  std::vector<Ev> events;
+  void adopt(const float p[3]) {
+    const float eps = std::numeric_limits<float>::epsilon();
+    while (true) {
+      bool up[3], any = false;
+      for (int a = 0; a < 3; a++) {
+        bool lo = p[a] < mn[a];
+        up[a] = p[a] >= mx[a];
+        any = any || lo || up[a];
+      }
+      if (!any && defined) break;
+      if (defined) {
+        double side = (double)(1 << depth) * res;
+        unsigned lowered = 0;
+        for (int a = 0; a < 3; a++) if (!up[a]) { mn[a] -= side; lowered |= 1u << a; }
+        events.push_back(Ev{lowered, depth});
+        depth++;
+        side = (double)(1 << depth) * res - eps;
+        for (int a = 0; a < 3; a++) mx[a] = mn[a] + side;
+        if (depth > 30) break;
+      } else {
+        for (int a = 0; a < 3; a++) { mn[a] = p[a] - res / 2; mx[a] = p[a] + res / 2; }
+        unsigned mk = 2;
+        for (int a = 0; a < 3; a++) mk = std::max(mk, (unsigned)((mx[a] - mn[a]) / res));
+        depth = (unsigned)std::ceil(std::log((double)mk) / std::log(2.0) - eps);
+        double side = (double)(1 << depth) * res - eps;
+        for (int a = 0; a < 3; a++) {
+          double over = (side - (mx[a] - mn[a])) / 2.0;
+          mn[a] -= over; mx[a] += over;
+        }
+        defined = true;
+      }
+    }
+  }
+};
+
+vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* found) {
+  unsigned long long* d_found = h->small.as<unsigned long long>();
+  Box b;
+  for (int a = 0; a < 3; a++) { b.mn[a] = st.mn[a]; b.mx[a] = st.mx[a]; }
+  int64_t window = 1 << 18;
+  int64_t s = cursor;
+  *found = h->n;
+  while (s < h->n) {
+    int64_t e = std::min(h->n, s + window);
+    unsigned long long init = ~0ull;
+    CK(cudaMemcpyAsync(d_found, &init, 8, cudaMemcpyHostToDevice, h->stream));
+    int64_t blocks = std::min<int64_t>(cdiv(e - s, 256), 148 * 8);
+    LAUNCH(k_find_outside, (unsigned)blocks, 256, 0, h->d_xyz, h->stride, s, e, b, st.defined ? 1 : 0, d_found, nullptr);
+    unsigned long long r = 0;
+    CK(cudaMemcpyAsync(&r, d_found, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (r != ~0ull) { *found = (int64_t)r; return VGS_OK; }
+    s = e;
+    window *= 8;
+  }
+  return VGS_OK;
+}
+
+struct StageTimer {
+  vgs_handle h; float* slot; cudaEvent_t a, b;
+  StageTimer(vgs_handle h_, float* slot_, int idx) : h(h_), slot(slot_) {
+    a = h->ev[idx * 2]; b = h->ev[idx * 2 + 1];
+    cudaEventRecord(a, h->stream);
+  }
+  void stop() {
+    cudaEventRecord(b, h->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    *slot = ms;
+  }
+};
+
+std::vector<int4> make_stencil(float voxel_size_f, float graph_size_f) {
+  // integer lattice offsets whose ideal centre distance could pass the float test dist2 < (float)(r*r)
+  double res = (double)voxel_size_f, r = (double)graph_size_f;
+  int rho = (int)std::ceil(r / res) + 1;
+  double lim = r * r * (1.0 + 1e-4) + 1e-9;
+  std::vector<int4> st;
+  for (int dx = -rho; dx <= rho; dx++)
+    for (int dy = -rho; dy <= rho; dy++)
+      for (int dz = -rho; dz <= rho; dz++) {
+        double d2 = res * res * (double)(dx * dx + dy * dy + dz * dz);
+        if (d2 < lim) st.push_back(make_int4(dx, dy, dz, 0));
+      }
+  return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+vgs_status vgs_device_count(int* n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (n) *n = (e == cudaSuccess) ? c : 0;
+  return (e == cudaSuccess && c > 0) ? VGS_OK : VGS_ERR_NO_DEVICE;
+}
+
+vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
+  if (!out || !cfg) { g_create_error = "vgs_create: null argument"; return VGS_ERR_INVALID; }
+  *out = nullptr;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess || c <= 0) {
+    g_create_error = std::string("vgs_create: no CUDA device (") + cudaGetErrorString(e) + "); libvgs_b200 has no CPU path";
+    return VGS_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= c) { g_create_error = "vgs_create: bad device ordinal"; return VGS_ERR_INVALID; }
+  if (cfg->mode != VGS_MODE_VGS && cfg->mode != VGS_MODE_SVGS) { g_create_error = "vgs_create: bad mode"; return VGS_ERR_INVALID; }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return VGS_ERR_CUDA; }
+  vgs_handle h = new vgs_context();
+  h->mode = cfg->mode; h->device = cfg->device; h->leaf_order = cfg->leaf_order;
+  if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
+  else {
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return VGS_ERR_CUDA; }
+    h->own_stream = true;
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  // opt in to large dynamic shared memory for the local-graph kernel
+  cudaFuncSetAttribute(k_local_graph<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_local_graph<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_local_graph<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_local_graph<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_adjacency, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(e);
+    delete h;
+    return VGS_ERR_CUDA;
+  }
+  *out = h;
+  return VGS_OK;
+}
+
+void vgs_destroy(vgs_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DBuf* all[] = {&h->xyz_own, &h->labels_own, &h->keysA, &h->keysB, &h->valsA, &h->valsB, &h->hist, &h->tiles, &h->flags, &h->scan,
+                 &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
+                 &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
+                 &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
+                 &h->labels_out, &h->tmp};
+  for (DBuf* b : all) b->release();
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* vgs_last_error(vgs_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_bytes, int on_device) {
+  if (!h) return VGS_ERR_INVALID;
+  if (!xyz || n <= 0 || (stride_bytes != 12 && stride_bytes != 16)) return h->fail(VGS_ERR_INVALID, "vgs_set_points: bad argument");
+  if (n >= (1ll << 31)) return h->fail(VGS_ERR_LIMIT, "vgs_set_points: n must be < 2^31 per handle (point indices are int, VS.h:163)");
+  CK(cudaSetDevice(h->device));
+  h->n = n; h->stride = stride_bytes / 4;
+  h->voxelized = h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  h->d_labels = nullptr;
+  h->tm = vgs_timings{};
+  if (on_device) { h->d_xyz = xyz; }
+  else {
+    StageTimer t(h, &h->tm.h2d_ms, 0);
+    CK(h->xyz_own.reserve((size_t)n * stride_bytes));
+    CK(cudaMemcpyAsync(h->xyz_own.p, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->d_xyz = h->xyz_own.as<float>();
+    t.stop();
+  }
+  return VGS_OK;
+}
+
+vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* labels, int32_t max_label, int on_device) {
+  if (!h) return VGS_ERR_INVALID;
+  if (h->mode != VGS_MODE_SVGS) return h->fail(VGS_ERR_STATE, "vgs_set_supervoxel_labels: handle is not in SVGS mode");
+  if (!labels || h->n <= 0) return h->fail(VGS_ERR_STATE, "vgs_set_supervoxel_labels: call vgs_set_points first");
+  CK(cudaSetDevice(h->device));
+  if (on_device) h->d_labels = labels;
+  else {
+    CK(h->labels_own.reserve((size_t)h->n * 4));
+    CK(cudaMemcpyAsync(h->labels_own.p, labels, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+    h->d_labels = h->labels_own.as<int32_t>();
+  }
+  h->max_label = max_label;
+  h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  return VGS_OK;
+}
+
+vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
+  if (!h) return VGS_ERR_INVALID;
+  if (!h->d_xyz) return h->fail(VGS_ERR_STATE, "vgs_voxelize: call vgs_set_points first");
+  if (!(voxel_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: voxel_size must be > 0");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  h->voxel_size = voxel_size;
+  h->voxelized = false;
+  if (h->mode == VGS_MODE_VGS) h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  CK(h->small.reserve(4096));
+
+  // ---- stage 0: PCL dynamic bounding box (origin) ----
+  OctState st;
+  st.res = (double)voxel_size;
+  EpochTable& ep = h->ep;
+  ep.n = 0;
+  std::vector<OctState::Ev> ev_at_epoch_end;
+  std::vector<size_t> events_before;  // #growth events before each epoch started
+  {
+    StageTimer t(h, &h->tm.origin_ms, 1);
+    int64_t cursor = 0;
+    while (true) {
+      int64_t idx;
+      vgs_status s = find_next(h, cursor, st, &idx);
+      if (s) return s;
+      if (idx >= n) break;
+      float p[3];
+      CK(cudaMemcpyAsync(p, h->d_xyz + idx * h->stride, 12, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      st.adopt(p);
+      if (st.depth > 21) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: octree depth > 21 bits per axis (extent / voxel_size too large)");
+      if (ep.n >= MAX_EPOCHS) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: too many bounding-box growth epochs");
+      ep.viol[ep.n] = idx;
+      for (int a = 0; a < 3; a++) ep.mn[ep.n][a] = st.mn[a];
+      events_before.push_back(st.events.size());
+      ep.n++;
+      cursor = idx + 1;
+    }
+    if (!st.defined) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: no finite point in the cloud");
+    // shifts: growth events after an epoch move its keys by 1<<depth_old on lowered axes
+    for (int e = 0; e < ep.n; e++) {
+      for (int a = 0; a < 3; a++) ep.shift[e][a] = 0;
+      for (size_t k = events_before[e]; k < st.events.size(); k++)
+        for (int a = 0; a < 3; a++)
+          if ((st.events[k].lowered >> a) & 1u) ep.shift[e][a] += 1u << st.events[k].depth_old;
+    }
+    t.stop();
+  }
+  for (int a = 0; a < 3; a++) { h->box.mn[a] = st.mn[a]; h->box.mx[a] = st.mx[a]; }
+  h->depth = (int)st.depth;
+
+  // ---- stage 1: keys, sort, voxel table ----
+  {
+    StageTimer t(h, &h->tm.voxelize_ms, 2);
+    CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
+    CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
+    LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, ep, st.res, h->depth,
+           h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr);
+    uint64_t* ks; uint32_t* vs;
+    vgs_status s = radix_sort(h, n, 3 * h->depth + 1, &ks, &vs);
+    if (s) return s;
+    // number of finite points = first sorted position whose key has the sentinel bit: count via head scan
+    // (sentinel keys form at most one extra segment at the end)
+    int64_t nunits = 0;
+    s = build_units(h, ks, n, &nunits);
+    if (s) return s;
+    // peel the sentinel segment if present
+    uint64_t lastkey = 0; uint32_t laststart = 0;
+    CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int64_t n_fin = n;
+    if (lastkey >> (3 * h->depth)) { n_fin = laststart; nunits--; }
+    h->n_finite = n_fin;
+    h->n_voxels = nunits;
+    if (h->mode == VGS_MODE_VGS) {
+      h->d_keys = ks; h->d_perm = vs;
+      h->nu = nunits; h->n_valid = n_fin;
+      h->have_units = true;
+    }
+    t.stop();
+  }
+  h->voxelized = true;
+  return VGS_OK;
+}
+
+vgs_status vgs_get_bounding_box(vgs_handle h, double out6[6]) {
+  if (!h || !out6) return VGS_ERR_INVALID;
+  if (!h->voxelized) return h->fail(VGS_ERR_STATE, "vgs_get_bounding_box: call vgs_voxelize first");
+  for (int a = 0; a < 3; a++) { out6[a] = h->box.mn[a]; out6[3 + a] = h->box.mx[a]; }
+  return VGS_OK;
+}
+
+vgs_status vgs_voxel_count(vgs_handle h, int64_t* nv) {
+  if (!h || !nv) return VGS_ERR_INVALID;
+  if (!h->voxelized) return h->fail(VGS_ERR_STATE, "vgs_voxel_count: call vgs_voxelize first");
+  *nv = h->n_voxels;
+  return VGS_OK;
+}
+
+static vgs_status build_svgs_units(vgs_handle h) {
+  if (!h->d_labels) return h->fail(VGS_ERR_STATE, "SVGS: call vgs_set_supervoxel_labels first");
+  const int64_t n = h->n;
+  int32_t ml = h->max_label;
+  if (ml <= 0) ml = std::numeric_limits<int32_t>::max();
+  CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
+  CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
+  LAUNCH(k_label_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_labels, h->d_xyz, h->stride, n, ml, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>());
+  uint64_t* ks; uint32_t* vs;
+  vgs_status s = radix_sort(h, n, 33, &ks, &vs);
+  if (s) return s;
+  int64_t nunits = 0;
+  s = build_units(h, ks, n, &nunits);
+  if (s) return s;
+  uint64_t lastkey = 0; uint32_t laststart = 0;
+  CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int64_t nval = n;
+  if (lastkey >> 32) { nval = laststart; nunits--; }
+  h->d_keys = ks; h->d_perm = vs;
+  h->nu = nunits; h->n_valid = nval;
+  h->have_units = true;
+  return VGS_OK;
+}
+
+vgs_status vgs_unit_count(vgs_handle h, int64_t* nunits) {
+  if (!h || !nunits) return VGS_ERR_INVALID;
+  if (!h->have_units) return h->fail(VGS_ERR_STATE, "vgs_unit_count: units not built yet");
+  *nunits = h->nu;
+  return VGS_OK;
+}
+
+vgs_status vgs_compute_features(vgs_handle h, int points_min) {
+  if (!h) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  StageTimer t(h, &h->tm.features_ms, 3);
+  if (h->mode == VGS_MODE_SVGS) {
+    vgs_status s = build_svgs_units(h);
+    if (s) return s;
+  }
+  if (!h->have_units) return h->fail(VGS_ERR_STATE, "vgs_compute_features: call vgs_voxelize first (test:54-62)");
+  h->points_min = points_min;
+  h->have_features = h->have_adj = h->have_segments = false;
+  const int64_t nu = h->nu;
+  if (nu <= 0) return h->fail(VGS_ERR_INVALID, "vgs_compute_features: no units");
+  CK(h->rec.reserve((size_t)nu * REC_FLOATS * 4));
+  CK(h->key3.reserve((size_t)nu * 12)); CK(h->center.reserve((size_t)nu * 12));
+  unsigned long long* d_used = h->small.as<unsigned long long>() + 16;
+  CK(cudaMemsetAsync(d_used, 0, 8, h->stream));
+  // float-narrowed members of the reference class (VS.h:127, 136-142, 1121-1123)
+  float res_f = (float)(double)h->voxel_size;
+  LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
+         h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->ukey.as<uint64_t>(), h->depth,
+         h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, res_f, (float)h->box.mn[0], (float)h->box.mn[1], (float)h->box.mn[2],
+         h->key3.as<uint32_t>(), h->center.as<float>(), d_used);
+  unsigned long long used = 0;
+  CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_used = (int64_t)used;
+  h->have_features = true;
+  t.stop();
+  return VGS_OK;
+}
+
+vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz) {
+  if (!h || !xyz) return VGS_ERR_INVALID;
+  if (h->mode != VGS_MODE_VGS || !h->have_features)
+    return h->fail(VGS_ERR_STATE, "vgs_get_voxel_centers: VGS centres are produced by vgs_compute_features");
+  CK(cudaMemcpyAsync(xyz, h->center.p, (size_t)h->nu * 12, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return VGS_OK;
+}
+
+vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
+  if (!h) return VGS_ERR_INVALID;
+  if (!h->have_features) return h->fail(VGS_ERR_STATE, "vgs_find_adjacency: call vgs_compute_features first");
+  if (!(graph_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_find_adjacency: graph_size must be > 0");
+  if (h->mode == VGS_MODE_SVGS) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: SVGS neighbour search not built yet");
+  CK(cudaSetDevice(h->device));
+  StageTimer t(h, &h->tm.adjacency_ms, 4);
+  h->graph_size = graph_size;
+  h->have_adj = h->have_segments = false;
+  const int64_t nu = h->nu;
+  // hash table: plain morton -> voxel id
+  uint64_t capacity = 64;
+  while (capacity < (uint64_t)nu * 2) capacity <<= 1;
+  h->hmask = capacity - 1;
+  CK(h->plainm.reserve((size_t)nu * 8));
+  CK(h->tk.reserve(capacity * 8)); CK(h->tv.reserve(capacity * 4));
+  CK(cudaMemsetAsync(h->tk.p, 0xff, capacity * 8, h->stream));
+  LAUNCH(k_plain_morton, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, h->plainm.as<uint64_t>());
+  LAUNCH(k_hash_insert, (unsigned)cdiv(nu, 256), 256, 0, h->plainm.as<uint64_t>(), nu, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask);
+  std::vector<int4> st = make_stencil(h->voxel_size, graph_size);
+  const int nst = (int)st.size();
+  const int wpb = 4;
+  size_t smem = (size_t)wpb * nst * 8;
+  if (smem > 200 * 1024) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
+  CK(h->stencil.reserve((size_t)nst * sizeof(int4)));
+  CK(cudaMemcpyAsync(h->stencil.p, st.data(), (size_t)nst * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  double r = (double)graph_size;
+  float r2 = (float)(r * r);
+  CK(h->adj_cnt.reserve((size_t)(nu + 1) * 4)); CK(h->adj_off.reserve((size_t)(nu + 1) * 4));
+  LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
+         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 0,
+         h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, (int32_t*)nullptr, nst);
+  unsigned long long total = 0;
+  vgs_status s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, &total);
+  if (s) return s;
+  if (total >= (1ull << 32)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: more than 2^32 adjacency entries on one device");
+  uint32_t tot32 = (uint32_t)total;
+  CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, &tot32, 4, cudaMemcpyHostToDevice, h->stream));
+  h->n_adj = (int64_t)total;
+  CK(h->adj_idx.reserve((size_t)total * 4 + 16));
+  LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
+         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
+         h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), nst);
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_adj = true;
+  t.stop();
+  return VGS_OK;
+}
+
+vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
+  if (!h || !sg) return VGS_ERR_INVALID;
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_segment: call vgs_find_adjacency first");
+  CK(cudaSetDevice(h->device));
+  const int64_t nu = h->nu;
+  h->have_segments = false;
+  h->have_cluster_stats = false;
+  GraphParams gp;
+  gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
+  gp.cut = cut_thred;
+  const size_t E = (size_t)h->n_adj;
+  CK(h->conn0_cnt.reserve((size_t)nu * 4)); CK(h->conn0_idx.reserve(E * 4 + 16));
+  CK(h->conn1_cnt.reserve((size_t)nu * 4)); CK(h->conn1_idx.reserve(E * 4 + 16));
+  CK(h->attach.reserve((size_t)nu * 4)); CK(h->parent.reserve((size_t)nu * 4)); CK(h->root.reserve((size_t)nu * 4));
+  // ---- stage 4+5a: local graphs ----
+  {
+    StageTimer t(h, &h->tm.graph_ms, 5);
+    CK(h->class_count.reserve(64)); CK(h->class_list.reserve((size_t)N_CLASSES * nu * 4));
+    unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
+    CK(cudaMemsetAsync(h->class_count.p, 0, 64, h->stream));
+    CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
+    CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));
+    LAUNCH(k_bin_classes, (unsigned)cdiv(nu, 256), 256, 0, h->adj_off.as<uint32_t>(), h->rec.as<float>(), nu,
+           h->class_count.as<uint32_t>(), h->class_list.as<uint32_t>(), d_stats);
+    uint32_t cc[N_CLASSES];
+    unsigned long long stats[3];
+    CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
+    if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a neighbourhood has more than 181 units (graph_size / unit spacing too large)");
+    for (int c = 0; c < N_CLASSES; c++) {
+      if (!cc[c]) continue;
+      const int ncap = CLASS_N_HOST[c], mcap = CLASS_M_HOST[c], T = CLASS_T_HOST[c];
+      size_t smem = (size_t)ncap * 80 + (size_t)mcap * 6 + 16;
+      const uint32_t* list = h->class_list.as<uint32_t>() + (size_t)c * nu;
+#define LG(TT)                                                                                                         \
+  LAUNCH(k_local_graph<TT>, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),       \
+         h->rec.as<float>(), gp, ncap, mcap, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>())
+      if (T == 64) LG(64); else if (T == 128) LG(128); else if (T == 256) LG(256); else LG(512);
+#undef LG
+    }
+    t.stop();
+  }
+  // ---- stage 5b: mutual filter ----
+  {
+    StageTimer t(h, &h->tm.mutual_ms, 6);
+    LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
+           h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
+    t.stop();
+  }
+  // ---- stage 5c: closest check ----
+  {
+    StageTimer t(h, &h->tm.closest_ms, 7);
+    CK(cudaMemsetAsync(h->attach.p, 0xff, (size_t)nu * 4, h->stream));
+    uint32_t* d_changed = h->small.as<uint32_t>() + 128;
+    unsigned long long* d_singles = h->small.as<unsigned long long>() + 40;
+    CK(cudaMemsetAsync(d_singles, 0, 8, h->stream));
+    int rounds = 0;
+    while (true) {
+      CK(cudaMemsetAsync(d_changed, 0, 4, h->stream));
+      LAUNCH(k_closest_round, (unsigned)cdiv(nu, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+             h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, adjacency_min, gp.pp, h->attach.as<int32_t>(), d_changed,
+             rounds == 0 ? d_singles : (unsigned long long*)nullptr);
+      uint32_t changed = 0;
+      CK(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      rounds++;
+      if (!changed) break;
+      if (rounds > 100000) return h->fail(VGS_ERR_LIMIT, "vgs_segment: closest-check did not converge");
+    }
+    unsigned long long singles = 0;
+    CK(cudaMemcpyAsync(&singles, d_singles, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_singles = (int64_t)singles;
+    h->closest_rounds = rounds;
+    t.stop();
+  }
+  // ---- stage 5d: components ----
+  {
+    StageTimer t(h, &h->tm.components_ms, 8);
+    LAUNCH(k_iota, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu);
+    LAUNCH(k_cc_hook, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(),
+           h->conn1_idx.as<int32_t>(), h->attach.as<int32_t>(), nu, h->parent.as<int>());
+    LAUNCH(k_cc_flatten, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu, h->root.as<int>());
+    t.stop();
+  }
+  h->have_segments = true;
+  return VGS_OK;
+}
+
+static vgs_status ensure_cluster_stats(vgs_handle h, int voxels_min) {
+  if (!h->have_segments) return h->fail(VGS_ERR_STATE, "results requested before vgs_segment");
+  const int min_excl = h->mode == VGS_MODE_SVGS ? -1 : voxels_min;
+  if (h->have_cluster_stats && h->last_voxels_min == min_excl) return VGS_OK;
+  const int64_t nu = h->nu;
+  CK(h->csize.reserve((size_t)nu * 4)); CK(h->cminpt.reserve((size_t)nu * 4));
+  CK(cudaMemsetAsync(h->csize.p, 0, (size_t)nu * 4, h->stream));
+  CK(cudaMemsetAsync(h->cminpt.p, 0xff, (size_t)nu * 4, h->stream));
+  LAUNCH(k_cluster_stats, (unsigned)cdiv(nu, 256), 256, 0, h->root.as<int>(), h->ustart.as<uint32_t>(), h->d_perm, nu,
+         h->csize.as<uint32_t>(), h->cminpt.as<uint32_t>());
+  unsigned long long* d_cnt = h->small.as<unsigned long long>() + 48;
+  CK(cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+  LAUNCH(k_cluster_count, (unsigned)cdiv(nu, 256), 256, 0, h->root.as<int>(), h->csize.as<uint32_t>(), nu, min_excl, d_cnt);
+  unsigned long long c2[2];
+  CK(cudaMemcpyAsync(c2, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_clusters_all = (int64_t)c2[0]; h->n_clusters_exp = (int64_t)c2[1];
+  h->have_cluster_stats = true; h->last_voxels_min = min_excl;
+  return VGS_OK;
+}
+
+vgs_status vgs_cluster_count(vgs_handle h, int voxels_min, int64_t* n_all, int64_t* n_exported) {
+  if (!h) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  vgs_status s = ensure_cluster_stats(h, voxels_min);
+  if (s) return s;
+  if (n_all) *n_all = h->n_clusters_all;
+  if (n_exported) *n_exported = h->n_clusters_exp;
+  return VGS_OK;
+}
+
+vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, int on_device) {
+  if (!h || !labels) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  StageTimer t(h, &h->tm.labels_ms, 9);
+  vgs_status s = ensure_cluster_stats(h, voxels_min);
+  if (s) return s;
+  const int min_excl = h->mode == VGS_MODE_SVGS ? -1 : voxels_min;
+  int32_t* d_out = labels;
+  if (!on_device) { CK(h->labels_out.reserve((size_t)h->n * 4)); d_out = h->labels_out.as<int32_t>(); }
+  LAUNCH(k_point_labels, (unsigned)cdiv(h->n, 256), 256, 0, h->d_perm, h->pos_unit.as<uint32_t>(), h->root.as<int>(),
+         h->csize.as<uint32_t>(), h->cminpt.as<uint32_t>(), h->n, h->n_valid, min_excl, d_out, (int32_t*)nullptr);
+  t.stop();
+  if (!on_device) {
+    StageTimer t2(h, &h->tm.d2h_ms, 10);
+    CK(cudaMemcpyAsync(labels, d_out, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    t2.stop();
+  }
+  return VGS_OK;
+}
+
+vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_clusters, int64_t* n_points_total, int64_t* offsets,
+                                int32_t* point_idx) {
+  if (!h) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  vgs_status s = ensure_cluster_stats(h, voxels_min);
+  if (s) return s;
+  // Output formatting of a finished result: canonical labels come from the device; grouping the
+  // point indices by label into the reference's vector<vector<int>> layout is done here.
+  const int64_t n = h->n;
+  CK(cudaStreamSynchronize(h->stream));
+  // cluster order of the reference = ascending smallest voxel id (clusteringVoxels seeds, VS.h:2064);
+  // root ids are exactly those seeds.  Fetch per-point unit + per-unit root to order clusters.
+  std::vector<int32_t> root((size_t)h->nu);
+  CK(cudaMemcpy(root.data(), h->root.p, (size_t)h->nu * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> csize((size_t)h->nu), ustart((size_t)h->nu + 1), perm((size_t)n);
+  CK(cudaMemcpy(csize.data(), h->csize.p, (size_t)h->nu * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ustart.data(), h->ustart.p, ((size_t)h->nu + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(perm.data(), h->d_perm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  const int min_excl = h->mode == VGS_MODE_SVGS ? -1 : voxels_min;
+  std::vector<int64_t> cl_of_root((size_t)h->nu, -1);
+  std::vector<int64_t> sizes;
+  for (int64_t u = 0; u < h->nu; u++)
+    if (root[u] == (int32_t)u && (int)csize[u] > min_excl) { cl_of_root[u] = (int64_t)sizes.size(); sizes.push_back(0); }
+  for (int64_t u = 0; u < h->nu; u++) { int64_t c = cl_of_root[root[u]]; if (c >= 0) sizes[c] += ustart[u + 1] - ustart[u]; }
+  int64_t total = 0;
+  for (auto v : sizes) total += v;
+  if (n_clusters) *n_clusters = (int64_t)sizes.size();
+  if (n_points_total) *n_points_total = total;
+  if (offsets && point_idx) {
+    std::vector<int64_t> cur(sizes.size() + 1, 0);
+    for (size_t c = 0; c < sizes.size(); c++) cur[c + 1] = cur[c] + sizes[c];
+    for (size_t c = 0; c <= sizes.size(); c++) offsets[c] = cur[c];
+    for (int64_t u = 0; u < h->nu; u++) {
+      int64_t c = cl_of_root[root[u]];
+      if (c < 0) continue;
+      for (uint32_t p = ustart[u]; p < ustart[u + 1]; p++) point_idx[cur[c]++] = (int32_t)perm[p];
+    }
+  }
+  return VGS_OK;
+}
+
+vgs_status vgs_run(vgs_handle h, const vgs_params* p, int32_t* labels, int on_device) {
+  if (!h || !p) return VGS_ERR_INVALID;
+  cudaEvent_t a = h->ev[14], b = h->ev[15];
+  cudaEventRecord(a, h->stream);
+  vgs_status s;
+  if ((s = vgs_voxelize(h, p->voxel_size))) return s;
+  if ((s = vgs_compute_features(h, p->points_min))) return s;
+  if ((s = vgs_find_adjacency(h, p->graph_size))) return s;
+  if ((s = vgs_segment(h, &p->sig, p->cut_thred, p->adjacency_min))) return s;
+  if (labels && (s = vgs_get_point_labels(h, p->voxels_min, labels, on_device))) return s;
+  cudaEventRecord(b, h->stream);
+  cudaEventSynchronize(b);
+  cudaEventElapsedTime(&h->tm.total_ms, a, b);
+  return VGS_OK;
+}
+
+vgs_status vgs_get_counts(vgs_handle h, vgs_counts* out) {
+  if (!h || !out) return VGS_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  out->n_points = h->n; out->n_finite = h->n_finite; out->n_voxels = h->n_voxels; out->n_units = h->nu;
+  out->n_used = h->n_used; out->n_adjacency = h->n_adj; out->n_pairs = h->n_pairs; out->n_singles = h->n_singles;
+  out->n_clusters_all = h->n_clusters_all; out->n_clusters_exported = h->n_clusters_exp; out->octree_depth = h->depth;
+  out->closest_rounds = h->closest_rounds; out->max_neighbours = h->max_n;
+  return VGS_OK;
+}
+
+vgs_status vgs_stage_timings(vgs_handle h, vgs_timings* out) {
+  if (!h || !out) return VGS_ERR_INVALID;
+  *out = h->tm;
+  out->kernel_launches = h->launches;
+  return VGS_OK;
+}
+
+vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* bytes) {
+  if (!h || !bytes) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n, nu = h->nu;
+  auto copy_out = [&](const void* src, size_t nbytes) -> vgs_status {
+    if (!dst) { *bytes = nbytes; return VGS_OK; }
+    if (*bytes < nbytes) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost));
+    *bytes = nbytes;
+    return VGS_OK;
+  };
+  switch (kind) {
+    case VGS_BLOB_POINT_KEY: {
+      if (!h->voxelized) return h->fail(VGS_ERR_STATE, "debug: not voxelized");
+      if (!dst) { *bytes = (size_t)n * 12; return VGS_OK; }
+      CK(h->tmp.reserve((size_t)n * 12 + (size_t)n * 12));
+      uint32_t* k3 = h->tmp.as<uint32_t>();
+      // keys/vals scratch of a throw-away quantise pass (the sorted arrays stay untouched)
+      DBuf sk, sv;
+      CK(sk.reserve((size_t)n * 8)); CK(sv.reserve((size_t)n * 4));
+      LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth,
+             h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, sk.as<uint64_t>(), sv.as<uint32_t>(), k3);
+      vgs_status s = copy_out(k3, (size_t)n * 12);
+      sk.release(); sv.release();
+      return s;
+    }
+    case VGS_BLOB_POINT_UNIT: {
+      if (!h->have_units) return h->fail(VGS_ERR_STATE, "debug: units not built");
+      if (!dst) { *bytes = (size_t)n * 4; return VGS_OK; }
+      CK(h->tmp.reserve((size_t)n * 4));
+      LAUNCH(k_point_labels, (unsigned)cdiv(n, 256), 256, 0, h->d_perm, h->pos_unit.as<uint32_t>(), (const int*)nullptr,
+             (const uint32_t*)nullptr, (const uint32_t*)nullptr, n, h->n_valid, 0, (int32_t*)nullptr, h->tmp.as<int32_t>());
+      return copy_out(h->tmp.p, (size_t)n * 4);
+    }
+    case VGS_BLOB_UNIT_KEY: if (!h->have_features) break; return copy_out(h->key3.p, (size_t)nu * 12);
+    case VGS_BLOB_UNIT_CENTER: if (!h->have_features) break; return copy_out(h->center.p, (size_t)nu * 12);
+    case VGS_BLOB_UNIT_OFFSETS: {
+      if (!h->have_units) break;
+      if (!dst) { *bytes = (size_t)(nu + 1) * 8; return VGS_OK; }
+      if (*bytes < (size_t)(nu + 1) * 8) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
+      std::vector<uint32_t> t32((size_t)nu + 1);
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaMemcpy(t32.data(), h->ustart.p, ((size_t)nu + 1) * 4, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i <= nu; i++) ((int64_t*)dst)[i] = t32[i];
+      *bytes = (size_t)(nu + 1) * 8;
+      return VGS_OK;
+    }
+    case VGS_BLOB_UNIT_POINTS: if (!h->have_units) break; return copy_out(h->d_perm, (size_t)h->n_valid * 4);
+    case VGS_BLOB_RECORDS: if (!h->have_features) break; return copy_out(h->rec.p, (size_t)nu * REC_FLOATS * 4);
+    case VGS_BLOB_ADJ_OFFSETS: {
+      if (!h->have_adj) break;
+      if (!dst) { *bytes = (size_t)(nu + 1) * 8; return VGS_OK; }
+      if (*bytes < (size_t)(nu + 1) * 8) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
+      std::vector<uint32_t> t32((size_t)nu + 1);
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaMemcpy(t32.data(), h->adj_off.p, ((size_t)nu + 1) * 4, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i <= nu; i++) ((int64_t*)dst)[i] = t32[i];
+      *bytes = (size_t)(nu + 1) * 8;
+      return VGS_OK;
+    }
+    case VGS_BLOB_ADJ_IDX: if (!h->have_adj) break; return copy_out(h->adj_idx.p, (size_t)h->n_adj * 4);
+    case VGS_BLOB_CONN0_COUNT: if (!h->have_segments) break; return copy_out(h->conn0_cnt.p, (size_t)nu * 4);
+    case VGS_BLOB_CONN0_IDX: if (!h->have_segments) break; return copy_out(h->conn0_idx.p, (size_t)h->n_adj * 4);
+    case VGS_BLOB_CONN1_COUNT: if (!h->have_segments) break; return copy_out(h->conn1_cnt.p, (size_t)nu * 4);
+    case VGS_BLOB_CONN1_IDX: if (!h->have_segments) break; return copy_out(h->conn1_idx.p, (size_t)h->n_adj * 4);
+    case VGS_BLOB_ATTACH: if (!h->have_segments) break; return copy_out(h->attach.p, (size_t)nu * 4);
+    case VGS_BLOB_UNIT_ROOT: if (!h->have_segments) break; return copy_out(h->root.p, (size_t)nu * 4);
+    default: return h->fail(VGS_ERR_INVALID, "vgs_debug_get: unknown blob kind");
+  }
+  return h->fail(VGS_ERR_STATE, "vgs_debug_get: blob not available yet");
+}
+
+}  // extern "C"
