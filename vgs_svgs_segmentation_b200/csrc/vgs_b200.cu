@@ -87,7 +87,7 @@ struct vgs_context {
   uint64_t hmask = 0;
 
   vgs_timings tm{};
-  cudaEvent_t ev[16] = {};
+  cudaEvent_t ev[32] = {};
 
   vgs_status fail(vgs_status s, const std::string& m) { err = m; return s; }
   vgs_status fail_cuda(cudaError_t e, const char* what, int line) {
@@ -296,17 +296,26 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     h->own_stream = true;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
-  // opt in to large dynamic shared memory for the local-graph kernel
-  cudaFuncSetAttribute(k_local_graph<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_local_graph<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_local_graph<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_local_graph<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_adjacency, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(e);
-    delete h;
-    return VGS_ERR_CUDA;
+  // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
+  {
+    auto optin = [&](const void* fn, size_t want_total) -> cudaError_t {
+      cudaFuncAttributes fa;
+      cudaError_t r = cudaFuncGetAttributes(&fa, fn);
+      if (r != cudaSuccess) return r;
+      return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(want_total - fa.sharedSizeBytes));
+    };
+    const size_t kMax = 227 * 1024;
+    cudaError_t r = optin((const void*)k_local_graph<64>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph<128>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph<256>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph<512>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
+    if (r != cudaSuccess) {
+      g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
+      cudaGetLastError();
+      delete h;
+      return VGS_ERR_CUDA;
+    }
   }
   *out = h;
   return VGS_OK;
@@ -773,7 +782,7 @@ vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_cluster
 
 vgs_status vgs_run(vgs_handle h, const vgs_params* p, int32_t* labels, int on_device) {
   if (!h || !p) return VGS_ERR_INVALID;
-  cudaEvent_t a = h->ev[14], b = h->ev[15];
+  cudaEvent_t a = h->ev[30], b = h->ev[31];
   cudaEventRecord(a, h->stream);
   vgs_status s;
   if ((s = vgs_voxelize(h, p->voxel_size))) return s;
