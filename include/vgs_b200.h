@@ -96,6 +96,9 @@ vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_
  *    (VS.h:84, test:51-60, VS.h:146-189): PCL's dynamic bounding box is emulated exactly. -- */
 vgs_status vgs_voxelize(vgs_handle h, float voxel_size);
 vgs_status vgs_get_bounding_box(vgs_handle h, double out6[6]);          /* PCL getBoundingBox, test:56 */
+/* setBoundingBox VS.h:133-144: the values are narrowed to float and used as the origin of the voxel
+ * centres (VS.h:2102-2109); the octree keys themselves are not affected (as in the reference). */
+vgs_status vgs_set_bounding_box(vgs_handle h, const double in6[6]);
 vgs_status vgs_voxel_count(vgs_handle h, int64_t* n_voxels);            /* getVoxelNum VS.h:104 */
 vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz /* V x 3 */); /* getVoxelCenters VS.h:191 */
 

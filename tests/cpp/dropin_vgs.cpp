@@ -1,0 +1,70 @@
+// dropin_vgs.cpp — test program: drives pcl::VoxelBasedSegmentation through exactly the call
+// sequence of the reference's usage snippet (reference file `test`, lines 51-76) using the drop-in
+// header, on a raw float32 xyz file, and writes canonical labels for comparison with the oracle.
+//   dropin_vgs <xyz.f32> <n> <labels.i32> voxel graph sig_p sig_n sig_o sig_e sig_c sig_w cut points_min adjacency_min voxels_min
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "vgs_dropin/voxel_segmentation.h"
+
+int main(int argc, char** argv) {
+  if (argc < 16) { fprintf(stderr, "usage\n"); return 2; }
+  const char* in = argv[1];
+  long n = atol(argv[2]);
+  const char* out = argv[3];
+  float voxel_size = (float)atof(argv[4]), graph_size = (float)atof(argv[5]);
+  float sig_p = (float)atof(argv[6]), sig_n = (float)atof(argv[7]), sig_o = (float)atof(argv[8]), sig_e = (float)atof(argv[9]),
+        sig_c = (float)atof(argv[10]), sig_w = (float)atof(argv[11]), cut_thred = (float)atof(argv[12]);
+  int points_min = atoi(argv[13]), adjacency_min = atoi(argv[14]), voxels_min = atoi(argv[15]);
+
+  PCXYZPtr input_cloud(new PCXYZ);
+  {
+    std::vector<float> buf((size_t)n * 3);
+    FILE* f = fopen(in, "rb");
+    if (!f || fread(buf.data(), 4, (size_t)n * 3, f) != (size_t)n * 3) { fprintf(stderr, "read failed\n"); return 3; }
+    fclose(f);
+    for (long i = 0; i < n; i++) input_cloud->push_back(pcl::PointXYZ(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]));
+  }
+  try {
+    double min_x = 0, min_y = 0, min_z = 0, max_x = 0, max_y = 0, max_z = 0;
+    pcl::PointCloud<pcl::PointXYZRGB>::Ptr clustered_cloud(new PCXYZRGB);
+    std::vector<pcl::PointXYZ, Eigen::aligned_allocator<pcl::PointXYZ>> voxel_centers;
+
+    // Voxelization (test:51-57)
+    pcl::VoxelBasedSegmentation<pcl::PointXYZ> voxel_structure(voxel_size);
+    voxel_structure.setInputCloud(input_cloud);
+    voxel_structure.getCloudPointNum(input_cloud);
+    voxel_structure.addPointsFromInputCloud();
+    voxel_structure.setVoxelSize(voxel_size, points_min, voxels_min, adjacency_min);
+    voxel_structure.getBoundingBox(min_x, min_y, min_z, max_x, max_y, max_z);
+    voxel_structure.setBoundingBox(min_x, min_y, min_z, max_x, max_y, max_z);
+    // centres (test:60-62)
+    voxel_structure.setVoxelCenters();
+    voxel_centers = voxel_structure.getVoxelCenters();
+    int nvox = voxel_structure.getVoxelNum();
+    // features, adjacency, segmentation (test:65-71)
+    voxel_structure.calcualteVoxelCloudAttributes(input_cloud);
+    voxel_structure.findAllVoxelAdjacency(graph_size);
+    voxel_structure.segmentVoxelCloudWithGraphModel(cut_thred, sig_p, sig_n, sig_o, sig_e, sig_c, sig_w);
+    // output (test:74-76)
+    voxel_structure.drawColorMapofPointsinClusters(clustered_cloud);
+    std::vector<std::vector<int>> clusters_points_idx = voxel_structure.getClusterIdx();
+
+    std::vector<int> lab((size_t)n, -1);
+    for (auto& cl : clusters_points_idx) {
+      int mn = cl.empty() ? -1 : cl[0];
+      for (int p : cl) mn = p < mn ? p : mn;
+      for (int p : cl) lab[p] = mn;
+    }
+    FILE* f = fopen(out, "wb");
+    fwrite(lab.data(), 4, (size_t)n, f);
+    fclose(f);
+    printf("voxels %d centers %zu clusters_all %d exported %zu coloured_points %zu\n", nvox, voxel_centers.size(),
+           voxel_structure.getClusterNum(), clusters_points_idx.size(), clustered_cloud->size());
+  } catch (const std::exception& e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -55,7 +55,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
              CONN1_IDX=(16, np.int32), ATTACH=(17, np.int32), UNIT_ROOT=(19, np.int32))
 
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
-            "vgs_get_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_unit_count",
+            "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
             "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get"]
 
@@ -78,6 +78,7 @@ def load():
         L.vgs_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]
         L.vgs_voxelize.argtypes = [C.c_void_p, C.c_float]
         L.vgs_get_bounding_box.argtypes = [C.c_void_p, C.c_void_p]
+        L.vgs_set_bounding_box.argtypes = [C.c_void_p, C.c_void_p]
         L.vgs_voxel_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.vgs_get_voxel_centers.argtypes = [C.c_void_p, C.c_void_p]
         L.vgs_set_supervoxel_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
@@ -158,6 +159,10 @@ class Handle:
         out = np.zeros(6, np.float64)
         self._ck(self.L.vgs_get_bounding_box(self.h, out.ctypes.data))
         return out
+
+    def set_bounding_box(self, box6):
+        b = np.ascontiguousarray(box6, dtype=np.float64)
+        self._ck(self.L.vgs_set_bounding_box(self.h, b.ctypes.data))
 
     def voxel_count(self):
         v = C.c_int64()

@@ -69,7 +69,8 @@ struct vgs_context {
   // units
   int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
   int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
-  bool have_units = false, have_features = false, have_adj = false, have_segments = false;
+  bool have_units = false, have_features = false, have_adj = false, have_segments = false, have_geometry = false;
+  float bb_f[6] = {0, 0, 0, 0, 0, 0};   // float-narrowed bounding box members (VS.h:1123)
   int64_t n_used = 0, n_adj = 0, n_pairs = 0, max_n = 0, n_singles = 0, n_attached = 0, closest_rounds = 0;
   int last_voxels_min = std::numeric_limits<int>::min();
   bool have_cluster_stats = false;
@@ -423,6 +424,8 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     t.stop();
   }
   for (int a = 0; a < 3; a++) { h->box.mn[a] = st.mn[a]; h->box.mx[a] = st.mx[a]; }
+  for (int a = 0; a < 3; a++) { h->bb_f[a] = (float)st.mn[a]; h->bb_f[3 + a] = (float)st.mx[a]; }
+  h->have_geometry = false;
   h->depth = (int)st.depth;
 
   // ---- stage 1: keys, sort, voxel table ----
@@ -521,15 +524,10 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   const int64_t nu = h->nu;
   if (nu <= 0) return h->fail(VGS_ERR_INVALID, "vgs_compute_features: no units");
   CK(h->rec.reserve((size_t)nu * REC_FLOATS * 4));
-  CK(h->key3.reserve((size_t)nu * 12)); CK(h->center.reserve((size_t)nu * 12));
   unsigned long long* d_used = h->small.as<unsigned long long>() + 16;
   CK(cudaMemsetAsync(d_used, 0, 8, h->stream));
-  // float-narrowed members of the reference class (VS.h:127, 136-142, 1121-1123)
-  float res_f = (float)(double)h->voxel_size;
   LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
-         h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->ukey.as<uint64_t>(), h->depth,
-         h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, res_f, (float)h->box.mn[0], (float)h->box.mn[1], (float)h->box.mn[2],
-         h->key3.as<uint32_t>(), h->center.as<float>(), d_used);
+         h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), d_used);
   unsigned long long used = 0;
   CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -539,10 +537,32 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   return VGS_OK;
 }
 
+static vgs_status ensure_geometry(vgs_handle h) {
+  if (h->mode != VGS_MODE_VGS || !h->voxelized) return h->fail(VGS_ERR_STATE, "voxel geometry needs vgs_voxelize in VGS mode");
+  if (h->have_geometry) return VGS_OK;
+  const int64_t nu = h->nu;
+  CK(h->key3.reserve((size_t)nu * 12 + 16)); CK(h->center.reserve((size_t)nu * 12 + 16));
+  float res_f = (float)(double)h->voxel_size;   // setVoxelSize narrows the resolution to float (VS.h:127)
+  LAUNCH(k_voxel_geometry, (unsigned)cdiv(nu, 256), 256, 0, h->ukey.as<uint64_t>(), nu, h->depth,
+         h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, res_f, h->bb_f[0], h->bb_f[1], h->bb_f[2], h->key3.as<uint32_t>(),
+         h->center.as<float>());
+  h->have_geometry = true;
+  return VGS_OK;
+}
+
+vgs_status vgs_set_bounding_box(vgs_handle h, const double in6[6]) {
+  if (!h || !in6) return VGS_ERR_INVALID;
+  if (!h->voxelized) return h->fail(VGS_ERR_STATE, "vgs_set_bounding_box: call vgs_voxelize first (test:56-57)");
+  for (int a = 0; a < 6; a++) h->bb_f[a] = (float)in6[a];
+  h->have_geometry = false;
+  h->have_adj = h->have_segments = false;
+  return VGS_OK;
+}
+
 vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz) {
   if (!h || !xyz) return VGS_ERR_INVALID;
-  if (h->mode != VGS_MODE_VGS || !h->have_features)
-    return h->fail(VGS_ERR_STATE, "vgs_get_voxel_centers: VGS centres are produced by vgs_compute_features");
+  CK(cudaSetDevice(h->device));
+  { vgs_status s = ensure_geometry(h); if (s) return s; }
   CK(cudaMemcpyAsync(xyz, h->center.p, (size_t)h->nu * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return VGS_OK;
@@ -555,6 +575,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   if (h->mode == VGS_MODE_SVGS) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: SVGS neighbour search not built yet");
   CK(cudaSetDevice(h->device));
   StageTimer t(h, &h->tm.adjacency_ms, 4);
+  { vgs_status sg_ = ensure_geometry(h); if (sg_) return sg_; }
   h->graph_size = graph_size;
   h->have_adj = h->have_segments = false;
   const int64_t nu = h->nu;
@@ -848,8 +869,8 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
              (const uint32_t*)nullptr, (const uint32_t*)nullptr, n, h->n_valid, 0, (int32_t*)nullptr, h->tmp.as<int32_t>());
       return copy_out(h->tmp.p, (size_t)n * 4);
     }
-    case VGS_BLOB_UNIT_KEY: if (!h->have_features) break; return copy_out(h->key3.p, (size_t)nu * 12);
-    case VGS_BLOB_UNIT_CENTER: if (!h->have_features) break; return copy_out(h->center.p, (size_t)nu * 12);
+    case VGS_BLOB_UNIT_KEY: { vgs_status s = ensure_geometry(h); if (s) return s; return copy_out(h->key3.p, (size_t)nu * 12); }
+    case VGS_BLOB_UNIT_CENTER: { vgs_status s = ensure_geometry(h); if (s) return s; return copy_out(h->center.p, (size_t)nu * 12); }
     case VGS_BLOB_UNIT_OFFSETS: {
       if (!h->have_units) break;
       if (!dst) { *bytes = (size_t)(nu + 1) * 8; return VGS_OK; }

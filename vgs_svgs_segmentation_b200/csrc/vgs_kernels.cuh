@@ -114,13 +114,10 @@ __global__ void __launch_bounds__(256) k_head_write(const uint64_t* __restrict__
 
 // ---- stage 2: per-unit record (centroid, scatter, eigen33, normal, 8 eigen features).
 //      One thread per unit, points visited in ascending index order so the fp32 sums are the
-//      reference's sums bit for bit.  VGS also emits the voxel key and centre (VS.h:2102-2109). ----
+//      reference's sums bit for bit. ----
 __global__ void __launch_bounds__(128) k_features(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
                                                 const uint32_t* __restrict__ ustart, int64_t nunits, int points_min, int svgs,
-                                                float* __restrict__ rec, const uint64_t* __restrict__ ukey, int depth,
-                                                int descending, float res_f, float mnx, float mny, float mnz,
-                                                uint32_t* __restrict__ key3, float* __restrict__ center,
-                                                unsigned long long* __restrict__ n_used) {
+                                                float* __restrict__ rec, unsigned long long* __restrict__ n_used) {
   int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nunits) return;
   uint32_t s = ustart[u], e = ustart[u + 1];
@@ -139,17 +136,25 @@ __global__ void __launch_bounds__(128) k_features(const float* __restrict__ xyz,
   out[2] = make_float4(r[8], r[9], r[10], r[11]);
   out[3] = make_float4(r[12], r[13], r[14], r[15]);
   if (used) atomicAdd(n_used, 1ull);
-  if (!svgs) {
-    uint64_t m = ukey[u];
-    const uint64_t mask = (1ull << (3 * depth)) - 1ull;
-    if (descending) m = ~m & mask;
-    uint32_t kx, ky, kz;
-    morton_decode(m, kx, ky, kz);
-    key3[3 * u] = kx; key3[3 * u + 1] = ky; key3[3 * u + 2] = kz;
-    center[3 * u] = (float)(((double)kx + 0.5f) * res_f + mnx);
-    center[3 * u + 1] = (float)(((double)ky + 0.5f) * res_f + mny);
-    center[3 * u + 2] = (float)(((double)kz + 0.5f) * res_f + mnz);
-  }
+}
+
+// voxel key + centre of every leaf (setVoxelCenters VS.h:146-189, getVoxelCenterFromOctreeKey
+// VS.h:2102-2109): centre = (float)(((double)key + 0.5f) * res_f + min_f) with the FLOAT members
+// the reference narrows in setVoxelSize / setBoundingBox (VS.h:127, 136-142, 1121-1123).
+__global__ void __launch_bounds__(256) k_voxel_geometry(const uint64_t* __restrict__ ukey, int64_t nu, int depth, int descending,
+                                                      float res_f, float mnx, float mny, float mnz,
+                                                      uint32_t* __restrict__ key3, float* __restrict__ center) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu) return;
+  uint64_t m = ukey[u];
+  const uint64_t mask = (1ull << (3 * depth)) - 1ull;
+  if (descending) m = ~m & mask;
+  uint32_t kx, ky, kz;
+  morton_decode(m, kx, ky, kz);
+  key3[3 * u] = kx; key3[3 * u + 1] = ky; key3[3 * u + 2] = kz;
+  center[3 * u] = (float)(((double)kx + 0.5f) * res_f + mnx);
+  center[3 * u + 1] = (float)(((double)ky + 0.5f) * res_f + mny);
+  center[3 * u + 2] = (float)(((double)kz + 0.5f) * res_f + mnz);
 }
 
 // plain (non-complemented) morton of each voxel, the hash-table key
