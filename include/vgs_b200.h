@@ -55,6 +55,8 @@ typedef struct vgs_timings {  /* CUDA-event milliseconds of the last run of each
   float h2d_ms, origin_ms, voxelize_ms, features_ms, adjacency_ms, graph_ms, mutual_ms, closest_ms,
       components_ms, labels_ms, d2h_ms, total_ms;
   int64_t kernel_launches;   /* kernels of this library launched since vgs_create / last reset */
+  float pair_cache_ms;       /* part of graph_ms spent building the pair-weight cache (VGS) */
+  float reserved[3];
 } vgs_timings;
 
 typedef struct vgs_counts {

@@ -151,3 +151,28 @@ def test_state_errors(built_lib):
     with pytest.raises(capi.VgsError):
         h.find_adjacency(0.5)
     h.close()
+
+
+def test_vgs_without_pair_cache(built_lib, monkeypatch):
+    """VGS_B200_NO_PAIR_CACHE=1: weights evaluated inside every local graph (the SVGS code path) must
+    give the same lists and labels as the offset-indexed pair cache."""
+    monkeypatch.setenv("VGS_B200_NO_PAIR_CACHE", "1")
+    xyz = _scene("site")
+    g = gpu_stages(xyz)
+    assert g["timings"]["pair_cache_ms"] == 0.0
+    monkeypatch.delenv("VGS_B200_NO_PAIR_CACHE")
+    g2 = gpu_stages(xyz)
+    assert g2["timings"]["pair_cache_ms"] > 0.0
+    r = oracle.run(xyz, math=1)
+    _compare_vgs(xyz, g, r)
+    _compare_vgs(xyz, g2, r)
+
+
+def test_vgs_large_cut_keeps_zero_weights(built_lib):
+    """cut_thred > 0.5 makes the cut bound negative: zero-weight entries (pairs with unused voxels)
+    stay in play and may merge (SURVEY.md A.5 last bullet)."""
+    xyz = _scene("two_planes")
+    kw = dict(cut_thred=0.8)
+    g = gpu_stages(xyz, **kw)
+    r = oracle.run(xyz, math=1, **kw)
+    _compare_vgs(xyz, g, r)

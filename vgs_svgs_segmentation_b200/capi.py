@@ -40,7 +40,7 @@ class Params(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("h2d_ms", "origin_ms", "voxelize_ms", "features_ms", "adjacency_ms", "graph_ms",
                                          "mutual_ms", "closest_ms", "components_ms", "labels_ms", "d2h_ms", "total_ms")] + \
-               [("kernel_launches", C.c_int64)]
+               [("kernel_launches", C.c_int64), ("pair_cache_ms", C.c_float), ("reserved", C.c_float * 3)]
 
 
 class Counts(C.Structure):
@@ -218,7 +218,7 @@ class Handle:
     def timings(self) -> dict:
         t = Timings()
         self._ck(self.L.vgs_stage_timings(self.h, C.byref(t)))
-        return {k: getattr(t, k) for k, _ in Timings._fields_}
+        return {k: getattr(t, k) for k, _ in Timings._fields_ if k != "reserved"}
 
     def blob(self, name: str) -> np.ndarray:
         kind, dt = BLOBS[name]

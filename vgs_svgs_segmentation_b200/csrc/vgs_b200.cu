@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -86,6 +87,9 @@ struct vgs_context {
   uint64_t* d_keys = nullptr;   // sorted keys (points to keysA or keysB)
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
+  std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
+  DBuf stencil2, pair_table;
+  int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
 
   vgs_timings tm{};
   cudaEvent_t ev[32] = {};
@@ -297,6 +301,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     h->own_stream = true;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
   {
     auto optin = [&](const void* fn, size_t want_total) -> cudaError_t {
@@ -306,10 +311,14 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
       return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(want_total - fa.sharedSizeBytes));
     };
     const size_t kMax = 227 * 1024;
-    cudaError_t r = optin((const void*)k_local_graph<64>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph<128>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph<256>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph<512>, kMax);
+    cudaError_t r = optin((const void*)k_local_graph2<64, true>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, true>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, true>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<512, true>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<64, false>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, false>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, false>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<512, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
@@ -330,7 +339,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -589,6 +598,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   LAUNCH(k_plain_morton, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, h->plainm.as<uint64_t>());
   LAUNCH(k_hash_insert, (unsigned)cdiv(nu, 256), 256, 0, h->plainm.as<uint64_t>(), nu, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask);
   std::vector<int4> st = make_stencil(h->voxel_size, graph_size);
+  h->stencil_host = st;
   const int nst = (int)st.size();
   const int wpb = 4;
   size_t smem = (size_t)wpb * nst * 8;
@@ -649,15 +659,56 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
     CK(cudaStreamSynchronize(h->stream));
     h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
     if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a neighbourhood has more than 181 units (graph_size / unit spacing too large)");
+    // pair-weight cache (VGS lattice): each unordered pair of used voxels evaluated once
+    bool cached = false;
+    int half = 0, r2 = 0;
+    if (h->mode == VGS_MODE_VGS && h->use_pair_cache && !h->stencil_host.empty()) {
+      int rho = 0;
+      for (const int4& o : h->stencil_host) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
+      r2 = 2 * rho;
+      const int S = 2 * r2 + 1;
+      half = (S * S * S - 1) / 2;
+      size_t bytes = (size_t)nu * (size_t)half * sizeof(float2);
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      if (bytes <= h->pair_table.cap || bytes < free_b / 2) {
+        // offsets that are differences of two stencil offsets, lexicographically positive half
+        std::vector<char> seen((size_t)S * S * S, 0);
+        std::vector<int4> st2;
+        for (const int4& p1 : h->stencil_host)
+          for (const int4& p2 : h->stencil_host) {
+            int dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+            if (!(dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0))))) continue;
+            int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2);
+            if (seen[code]) continue;
+            seen[code] = 1;
+            st2.push_back(make_int4(dx, dy, dz, code - half - 1));
+          }
+        CK(h->pair_table.reserve(bytes));
+        CK(h->stencil2.reserve(st2.size() * sizeof(int4)));
+        CK(cudaMemcpyAsync(h->stencil2.p, st2.data(), st2.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
+        LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
+               h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
+               h->pair_table.as<float2>(), half);
+        tpc.stop();
+        cached = true;
+      }
+    }
     for (int c = 0; c < N_CLASSES; c++) {
       if (!cc[c]) continue;
-      const int ncap = CLASS_N_HOST[c], mcap = CLASS_M_HOST[c], T = CLASS_T_HOST[c];
-      size_t smem = (size_t)ncap * 80 + (size_t)mcap * 6 + 16;
+      const int ncap = CLASS_N_HOST[c], mcap = ncap * (ncap - 1), T = CLASS_T_HOST[c];
+      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (12 + (cached ? 16 : 4 * REC_PAD)) + (LG_BINS + 1) * 4 + 64;
       const uint32_t* list = h->class_list.as<uint32_t>() + (size_t)c * nu;
-#define LG(TT)                                                                                                         \
-  LAUNCH(k_local_graph<TT>, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),       \
-         h->rec.as<float>(), gp, ncap, mcap, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>())
-      if (T == 64) LG(64); else if (T == 128) LG(128); else if (T == 256) LG(256); else LG(512);
+#define LG(TT, CC)                                                                                                  \
+  do {                                                                                                              \
+    auto kfn = k_local_graph2<TT, CC>;                                                                              \
+    LAUNCH(kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),                  \
+           h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2,        \
+           h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
+  } while (0)
+      if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else if (T == 256) LG(256, true); else LG(512, true); }
+      else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else if (T == 256) LG(256, false); else LG(512, false); }
 #undef LG
     }
     t.stop();

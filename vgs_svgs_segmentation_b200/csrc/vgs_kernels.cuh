@@ -6,12 +6,14 @@
 namespace vgs {
 
 constexpr int MAX_EPOCHS = 40;
-constexpr int N_CLASSES = 7;
-// class c holds neighbourhoods with n(n-1) <= CLASS_M[c] directed off-diagonal weights
-__constant__ int c_class_n[N_CLASSES] = {16, 32, 45, 64, 91, 128, 181};
-constexpr int CLASS_N_HOST[N_CLASSES] = {16, 32, 45, 64, 91, 128, 181};
-constexpr int CLASS_M_HOST[N_CLASSES] = {256, 1024, 2048, 4096, 8192, 16384, 32768};
-constexpr int CLASS_T_HOST[N_CLASSES] = {64, 128, 128, 256, 256, 512, 512};
+constexpr int N_CLASSES = 9;
+// class c holds neighbourhoods with n <= CLASS_N[c]; capacity n(n-1) directed off-diagonal weights
+__constant__ int c_class_n[N_CLASSES] = {16, 32, 48, 64, 80, 96, 112, 128, 181};
+constexpr int CLASS_N_HOST[N_CLASSES] = {16, 32, 48, 64, 80, 96, 112, 128, 181};
+constexpr int CLASS_T_HOST[N_CLASSES] = {64, 128, 128, 256, 256, 256, 512, 512, 512};
+constexpr int LG_CS = 1024;    // staging capacity (entries) of one sorted chunk
+constexpr int LG_CH = 512;     // target chunk size
+constexpr int LG_BINS = 256;   // weight histogram bins
 constexpr int MAX_NEIGH = 181;
 constexpr int REC_PAD = 17;  // smem row stride of a 16-float record (bank-conflict free)
 
@@ -239,53 +241,148 @@ __global__ void __launch_bounds__(256) k_bin_classes(const uint32_t* __restrict_
   class_list[(int64_t)c * nu + pos] = (uint32_t)u;
 }
 
+// ---- stage 4 (VGS, cached): every unordered pair of USED voxels closer than two stencil radii is
+//      evaluated ONCE and stored by lattice offset: table[a*half + code(key_b - key_a)] =
+//      (w(a->b), w(b->a)), a = the voxel whose offset to b is lexicographically positive.
+//      A pair's weight does not depend on the local graph it appears in (buildAdjacencyGraph
+//      VS.h:1796-1910 recomputes it for every centre voxel).  One warp per voxel: hash probes of
+//      the offset list, hits queued in shared memory, 32 pair evaluations per warp step. ----
+__global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv,
+                                                  int depth, const int4* __restrict__ st2, int nst2,
+                                                  const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
+                                                  uint64_t mask, PairParams pp, float2* __restrict__ table, int half) {
+  __shared__ int pend_b[4][64];
+  __shared__ int pend_i[4][64];
+  __shared__ float s_ra[4][REC_FLOATS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t v = (int64_t)blockIdx.x * 4 + w;
+  if (v >= nv) return;
+  if (!(f2i(rec[v * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
+  if (lane < REC_FLOATS) s_ra[w][lane] = rec[v * REC_FLOATS + lane];
+  __syncwarp();
+  const uint32_t kx = key3[3 * v], ky = key3[3 * v + 1], kz = key3[3 * v + 2];
+  const int64_t lim = 1ll << depth;
+  int npend = 0;
+  auto process = [&](int cnt) {
+    if (lane < cnt) {
+      const int b = pend_b[w][lane], idx = pend_i[w][lane];
+      float rb[REC_FLOATS];
+      const float4* src = reinterpret_cast<const float4*>(rec + (int64_t)b * REC_FLOATS);
+#pragma unroll
+      for (int q = 0; q < 4; q++) { float4 t = __ldg(src + q); rb[4 * q] = t.x; rb[4 * q + 1] = t.y; rb[4 * q + 2] = t.z; rb[4 * q + 3] = t.w; }
+      float w_ab, w_ba;
+      pair_weights(s_ra[w], rb, pp, w_ab, w_ba);
+      table[(size_t)v * half + idx] = make_float2(w_ab, w_ba);
+    }
+  };
+  for (int base = 0; base < nst2; base += 32) {
+    const int s = base + lane;
+    int id = -1, code = 0;
+    if (s < nst2) {
+      int4 o = st2[s];
+      code = o.w;
+      int64_t x = (int64_t)kx + o.x, y = (int64_t)ky + o.y, z = (int64_t)kz + o.z;
+      if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim) {
+        id = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+        if (id >= 0 && !(f2i(__ldg(rec + (int64_t)id * REC_FLOATS + REC_FLAGS)) & F_USED)) id = -1;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
+    if (id >= 0) { int pos = npend + __popc(bal & ((1u << lane) - 1u)); pend_b[w][pos] = id; pend_i[w][pos] = code; }
+    npend += __popc(bal);
+    __syncwarp();
+    if (npend >= 32) {
+      process(32);
+      __syncwarp();
+      const int rem = npend - 32;
+      int tb = 0, ti = 0;
+      if (lane < rem) { tb = pend_b[w][32 + lane]; ti = pend_i[w][32 + lane]; }
+      __syncwarp();
+      if (lane < rem) { pend_b[w][lane] = tb; pend_i[w][lane] = ti; }
+      __syncwarp();
+      npend = rem;
+    }
+  }
+  process(npend);
+}
+
 // ---- stage 4+5a: local affinity graph + Felzenszwalb-style cut of ONE unit per CTA
 //      (buildAdjacencyGraph VS.h:1796-1910 + cutGraphSegmentation VS.h:1913-2029).
-//      smem: neighbour records, directed weights (float) + flat index (u16), segment state.
-//      Weights w <= 1-2k+k/n can never merge (DESIGN.md §cut bound) and are dropped before the
-//      sort; order = (w desc, flat index asc); merge scans 32 sorted entries per warp step. ----
+//      1. directed weights of all pairs of the neighbourhood: CACHED -> one 8-byte load per unordered
+//         pair from the offset-indexed table; else evaluated here from the records.  Weights
+//         w <= 1-2k+k/n can never merge (cut bound) and are dropped.
+//      2. the reference sorts all n^2 weights; here a 256-bin histogram of the weights delimits
+//         chunks of ~512 entries that are sorted (bitonic, shared memory) and merged in descending
+//         order (w desc, flat index asc) until exactly nothing more can merge: one segment left, or
+//         the next weight does not exceed the smallest live threshold Int(C) - k/|C|.
+//      3. the merge scans 32 sorted entries per warp step: the first mergeable entry merges, the
+//         later ones are re-evaluated against the new state. ----
 struct GraphParams {
   PairParams pp;
   float cut;
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_local_graph(const uint32_t* __restrict__ list, uint32_t nlist,
-                                                       const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
-                                                       const float* __restrict__ rec, GraphParams gp, int ncap, int mcap,
-                                                       uint32_t* __restrict__ conn_cnt, int32_t* __restrict__ conn_idx) {
+template <int THREADS, bool CACHED>
+__global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __restrict__ list, uint32_t nlist,
+                                                        const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
+                                                        const float* __restrict__ rec, const uint32_t* __restrict__ key3,
+                                                        GraphParams gp, int ncap, int mcap, const float2* __restrict__ table,
+                                                        int half, int r2, uint32_t* __restrict__ conn_cnt,
+                                                        int32_t* __restrict__ conn_idx) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  float* s_rec = reinterpret_cast<float*>(smraw);                       // ncap * REC_PAD
-  float* s_w = s_rec + (size_t)ncap * REC_PAD;                          // mcap
-  float* s_int = s_w + mcap;                                            // ncap
-  int* s_gid = reinterpret_cast<int*>(s_int + ncap);                    // ncap
-  unsigned short* s_f = reinterpret_cast<unsigned short*>(s_gid + ncap);  // mcap
-  unsigned short* s_seg = s_f + mcap;                                   // ncap
-  unsigned short* s_size = s_seg + ncap;                                // ncap
-  __shared__ int s_m;
-  __shared__ int s_nseg;
+  constexpr int AUX = CACHED ? 4 : REC_PAD;
+  float* A_w = reinterpret_cast<float*>(smraw);                                  // mcap: weight pool (append order)
+  float* C_w = A_w + mcap;                                                       // LG_CS: sorted chunk
+  float* s_int = C_w + LG_CS;                                                    // ncap
+  int* s_gid = reinterpret_cast<int*>(s_int + ncap);                             // ncap
+  int* s_aux = s_gid + ncap;                                                     // AUX*ncap: (kx,ky,kz,flags) | records
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_aux + (size_t)AUX * ncap);    // LG_BINS+1
+  unsigned short* A_f = reinterpret_cast<unsigned short*>(s_hist + LG_BINS + 1); // mcap: flat index col*n+row
+  unsigned short* C_f = A_f + mcap;                                              // LG_CS
+  unsigned short* s_seg = C_f + LG_CS;                                           // ncap
+  unsigned short* s_size = s_seg + ncap;                                         // ncap
+  __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot;
+  __shared__ float s_minthr, s_wempty, s_ratio;
 
   const int tid = threadIdx.x;
   if (blockIdx.x >= nlist) return;
   const uint32_t u = list[blockIdx.x];
   const uint32_t off = adj_off[u];
   const int n = (int)(adj_off[u + 1] - off);
-  if (tid == 0) { s_m = 0; s_nseg = n; }
+  const float k = gp.cut;
+  if (tid == 0) { s_m = 0; s_nseg = n; s_done = (n <= 1) ? 1 : 0; s_minthr = 1.0f - k / 1.0f; s_ratio = 1.0f; }
+  for (int i = tid; i <= LG_BINS; i += THREADS) s_hist[i] = 0;
   for (int i = tid; i < n; i += THREADS) {
     s_gid[i] = adj_idx[off + i];
     s_seg[i] = (unsigned short)i; s_size[i] = 1; s_int[i] = 1.0f;
   }
   __syncthreads();
-  for (int t = tid; t < n * 4; t += THREADS) {  // 4 x float4 per record
-    int i = t >> 2, q = t & 3;
-    float4 val = __ldg(reinterpret_cast<const float4*>(rec + (int64_t)s_gid[i] * REC_FLOATS) + q);
-    float* d = s_rec + i * REC_PAD + q * 4;
-    d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
+  if (CACHED) {
+    for (int i = tid; i < n; i += THREADS) {
+      const int64_t g = s_gid[i];
+      s_aux[4 * i] = (int)key3[3 * g]; s_aux[4 * i + 1] = (int)key3[3 * g + 1]; s_aux[4 * i + 2] = (int)key3[3 * g + 2];
+      s_aux[4 * i + 3] = f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS));
+    }
+    if (tid == 0) {  // weight of any pair that involves an unused (all-empty) unit
+      float z[REC_FLOATS];
+      for (int q = 0; q < REC_FLOATS; q++) z[q] = 0.f;
+      float a, b;
+      pair_weights(z, z, gp.pp, a, b);
+      s_wempty = a;
+    }
+  } else {
+    float* s_rec = reinterpret_cast<float*>(s_aux);
+    for (int t = tid; t < n * 4; t += THREADS) {
+      int i = t >> 2, q = t & 3;
+      float4 val = __ldg(reinterpret_cast<const float4*>(rec + (int64_t)s_gid[i] * REC_FLOATS) + q);
+      float* d = s_rec + i * REC_PAD + q * 4;
+      d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
+    }
   }
   __syncthreads();
-  // --- directed weights of all unordered pairs ---
-  const float k = gp.cut;
+  // --- 1. directed weights of all unordered pairs -> pool + histogram ---
   const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
+  const float scale = (float)LG_BINS / fmaxf(1.0f - lb, 1e-3f);
   const int npairs = n * (n - 1) / 2;
   for (int p = tid; p < npairs; p += THREADS) {
     int r = p / (n - 1), c = p - r * (n - 1);
@@ -293,80 +390,194 @@ __global__ void __launch_bounds__(THREADS) k_local_graph(const uint32_t* __restr
     if (c < n - 1 - r) { a = r; b = r + 1 + c; }
     else { a = n - 1 - r; b = a + 1 + (c - (n - 1 - r)); }
     float w_ab, w_ba;
-    pair_weights(s_rec + a * REC_PAD, s_rec + b * REC_PAD, gp.pp, w_ab, w_ba);
-    // matrix entry (row i, col j) = weight(v1=idx[i], v2=idx[j]); flat index = col*n + row
-    if (w_ab > lb) { int s = atomicAdd(&s_m, 1); s_w[s] = w_ab; s_f[s] = (unsigned short)(b * n + a); }
-    if (w_ba > lb) { int s = atomicAdd(&s_m, 1); s_w[s] = w_ba; s_f[s] = (unsigned short)(a * n + b); }
+    if (CACHED) {
+      const int fa = s_aux[4 * a + 3], fb = s_aux[4 * b + 3];
+      if (!(fa & F_USED) || !(fb & F_USED)) { w_ab = w_ba = s_wempty; }
+      else {
+        int dx = s_aux[4 * b] - s_aux[4 * a], dy = s_aux[4 * b + 1] - s_aux[4 * a + 1], dz = s_aux[4 * b + 2] - s_aux[4 * a + 2];
+        const bool pos = dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0)));
+        if (!pos) { dx = -dx; dy = -dy; dz = -dz; }
+        const int S = 2 * r2 + 1;
+        const int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2) - half - 1;
+        const float2 e = __ldg(table + (size_t)(pos ? s_gid[a] : s_gid[b]) * half + code);
+        w_ab = pos ? e.x : e.y;
+        w_ba = pos ? e.y : e.x;
+      }
+    } else {
+      const float* s_rec = reinterpret_cast<const float*>(s_aux);
+      pair_weights(s_rec + a * REC_PAD, s_rec + b * REC_PAD, gp.pp, w_ab, w_ba);
+    }
+    // matrix entry (row i, col j) = weight(v1=idx[i], v2=idx[j]); the reference's flat index is
+    // col*n + row (VS.h:1922) and it reads v1 = col, v2 = row back (VS.h:1959-1960).  Stored packed
+    // as (col << 8) | row, which orders exactly like the flat index (row < n <= 256).
+    if (w_ab > lb) {
+      int s = atomicAdd(&s_m, 1); A_w[s] = w_ab; A_f[s] = (unsigned short)((b << 8) | a);
+      atomicAdd(&s_hist[min(LG_BINS - 1, (int)((1.0f - w_ab) * scale))], 1u);
+    }
+    if (w_ba > lb) {
+      int s = atomicAdd(&s_m, 1); A_w[s] = w_ba; A_f[s] = (unsigned short)((a << 8) | b);
+      atomicAdd(&s_hist[min(LG_BINS - 1, (int)((1.0f - w_ba) * scale))], 1u);
+    }
   }
   __syncthreads();
   const int m = s_m;
-  int mpad = 32;
-  while (mpad < m) mpad <<= 1;
-  for (int i = m + tid; i < mpad; i += THREADS) { s_w[i] = -1.0f; s_f[i] = 0xffff; }
-  __syncthreads();
-  // --- bitonic sort: (w desc, f asc) ---
-  for (int kk = 2; kk <= mpad; kk <<= 1) {
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < mpad; i += THREADS) {
-        int x = i ^ j;
-        if (x > i) {
-          float wi = s_w[i], wx = s_w[x];
-          unsigned short fi = s_f[i], fx = s_f[x];
-          bool x_before_i = (wx > wi) || (wx == wi && fx < fi);
-          bool up = (i & kk) == 0;
-          if (x_before_i == up) { s_w[i] = wx; s_w[x] = wi; s_f[i] = fx; s_f[x] = fi; }
+  // --- 2+3. chunks of descending weight: gather -> sort -> merge, until nothing more can merge.
+  //     Entries whose two vertices already share a segment are no-ops for ever (segments only
+  //     grow) and are skipped at gather time; s_ratio tracks how many entries survive that, so the
+  //     bin range of the next chunk is sized for ~LG_CH surviving entries. ---
+  int c0 = 0;
+  while (c0 < LG_BINS && !s_done && m > 0) {
+    if (tid == 0) {
+      while (c0 < LG_BINS && s_hist[c0] == 0) c0++;   // skip empty bins
+      int c1 = c0, tot = 0;
+      if (c0 < LG_BINS) { tot = (int)s_hist[c0]; c1 = c0 + 1; }
+      const float ratio = s_ratio;
+      while (c1 < LG_BINS && (float)(tot + (int)s_hist[c1]) * ratio <= (float)LG_CH) { tot += (int)s_hist[c1]; c1++; }
+      s_c1 = c1; s_cnt = 0; s_tot = tot;
+      s_hist[LG_BINS] = (unsigned)c0;
+    }
+    __syncthreads();
+    c0 = (int)s_hist[LG_BINS];
+    const int c1 = s_c1;
+    if (c0 >= LG_BINS) break;
+    const int L = s_tot;
+    const bool single_big = (c1 == c0 + 1) && (L > LG_CS);
+    int kept = 0;
+    if (!single_big) {
+      // gather the chunk's still-useful entries
+      for (int i = tid; i < m; i += THREADS) {
+        const float w = A_w[i];
+        const int bin = min(LG_BINS - 1, (int)((1.0f - w) * scale));
+        if (bin >= c0 && bin < c1) {
+          const unsigned short f = A_f[i];
+          if (s_seg[f >> 8] != s_seg[f & 255]) {
+            int s = atomicAdd(&s_cnt, 1);
+            if (s < LG_CS) { C_w[s] = w; C_f[s] = f; }
+          }
         }
       }
       __syncthreads();
-    }
-  }
-  // --- merge (warp 0): 32 sorted entries per step, first mergeable entry merges, rest re-evaluated ---
-  if (tid < 32) {
-    const int lane = tid;
-    int nseg = n;
-    for (int base = 0; base < m && nseg > 1; base += 32) {
-      int e = base + lane;
-      bool valid = e < m;
-      float w = valid ? s_w[e] : 0.f;
-      int f = valid ? (int)s_f[e] : 0;
-      int v1 = f / n, v2 = f - v1 * n;
-      uint32_t todo = __ballot_sync(0xffffffffu, valid);
-      while (todo) {
-        bool pred = false;
-        int sa = 0, sb = 0;
-        float thr = 0.f;
-        bool a_wins = true;
-        if ((todo >> lane) & 1u) {
-          sa = s_seg[v1]; sb = s_seg[v2];
-          if (sa != sb) {
-            float m1 = s_int[sa] - k / (float)(int)s_size[sa];
-            float m2 = s_int[sb] - k / (float)(int)s_size[sb];
-            a_wins = (m1 >= m2);
-            thr = a_wins ? m1 : m2;
-            pred = w > thr;
-          }
-        }
-        uint32_t bal = __ballot_sync(0xffffffffu, pred);
-        if (!bal) break;
-        int L = __ffs(bal) - 1;
-        int keep = __shfl_sync(0xffffffffu, a_wins ? sa : sb, L);
-        int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, L);
-        float wl = __shfl_sync(0xffffffffu, w, L);
-        for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned short)keep;
-        if (lane == 0) { s_int[keep] = wl; s_size[keep] = (unsigned short)(s_size[keep] + s_size[drop]); s_size[drop] = 0; }
-        nseg--;
-        __syncwarp();
-        todo &= ~((2u << L) - 1u);  // entries up to and including L are settled
-        if (nseg <= 1) break;
+      kept = s_cnt;
+      if (kept > LG_CS) {       // estimate was too optimistic: retry this range conservatively
+        __syncthreads();
+        if (tid == 0) s_ratio = 1.0f;
+        __syncthreads();
+        continue;
       }
     }
-    // --- emit the segment that contains local vertex 0 (the unit itself) ---
+    const int nwin = single_big ? (L + LG_CS - 1) / LG_CS : 1;
+    for (int win = 0; win < nwin; win++) {
+      int Lw;
+      if (!single_big) {
+        Lw = kept;
+        int P = 32;
+        while (P < Lw) P <<= 1;
+        for (int i = Lw + tid; i < P; i += THREADS) { C_w[i] = -1.0f; C_f[i] = 0xffff; }
+        __syncthreads();
+        // bitonic sort: (w desc, packed index asc)
+        for (int kk = 2; kk <= P; kk <<= 1) {
+          for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += THREADS) {
+              const int x = i ^ j;
+              if (x > i) {
+                const float wi = C_w[i], wx = C_w[x];
+                const unsigned short fi = C_f[i], fx = C_f[x];
+                const bool x_before_i = (wx > wi) || (wx == wi && fx < fi);
+                const bool up = (i & kk) == 0;
+                if (x_before_i == up) { C_w[i] = wx; C_w[x] = wi; C_f[i] = fx; C_f[x] = fi; }
+              }
+            }
+            __syncthreads();
+          }
+        }
+      } else {
+        // one bin holds more entries than the staging buffer: place by exact rank, window by window
+        Lw = min(LG_CS, L - win * LG_CS);
+        for (int i = tid; i < m; i += THREADS) {
+          const float w = A_w[i];
+          if (min(LG_BINS - 1, (int)((1.0f - w) * scale)) != c0) continue;
+          const unsigned short f = A_f[i];
+          int rank = 0;
+          for (int y = 0; y < m; y++) {
+            const float wy = A_w[y];
+            if (min(LG_BINS - 1, (int)((1.0f - wy) * scale)) == c0 && ((wy > w) || (wy == w && A_f[y] < f))) rank++;
+          }
+          if (rank >= win * LG_CS && rank < (win + 1) * LG_CS) { C_w[rank - win * LG_CS] = w; C_f[rank - win * LG_CS] = f; }
+        }
+        __syncthreads();
+      }
+      // merge (warp 0)
+      if (tid < 32) {
+        const int lane = tid;
+        int nseg = s_nseg;
+        const float minthr = s_minthr;
+        // nothing at or below the smallest live threshold can ever merge: w > max(thr1,thr2) >= minthr
+        const bool below = (Lw > 0) && !(C_w[0] > minthr);
+        bool stop = below || nseg <= 1;
+        for (int base = 0; base < Lw && !stop; base += 32) {
+          const int e = base + lane;
+          const bool valid = e < Lw;
+          const float w = valid ? C_w[e] : 0.f;
+          const int f = valid ? (int)C_f[e] : 0;
+          const int v1 = f >> 8, v2 = f & 255;
+          uint32_t todo = __ballot_sync(0xffffffffu, valid);
+          while (todo) {
+            bool pred = false, a_wins = true;
+            int sa = 0, sb = 0;
+            if ((todo >> lane) & 1u) {
+              sa = s_seg[v1]; sb = s_seg[v2];
+              if (sa != sb) {
+                const float m1 = s_int[sa] - k / (float)(int)s_size[sa];
+                const float m2 = s_int[sb] - k / (float)(int)s_size[sb];
+                a_wins = (m1 >= m2);
+                pred = w > (a_wins ? m1 : m2);
+              }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+            if (!bal) break;
+            const int Lm = __ffs(bal) - 1;
+            const int keep = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
+            const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
+            const float wl = __shfl_sync(0xffffffffu, w, Lm);
+            for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned short)keep;
+            if (lane == 0) { s_int[keep] = wl; s_size[keep] = (unsigned short)(s_size[keep] + s_size[drop]); s_size[drop] = 0; }
+            nseg--;
+            __syncwarp();
+            todo &= ~((2u << Lm) - 1u);
+            if (nseg <= 1) { stop = true; break; }
+          }
+        }
+        // smallest threshold among live segments that still have candidate entries
+        float mt = 3.0e38f;
+        for (int v = lane; v < n; v += 32) {
+          const int sz = (int)s_size[v];
+          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        if (lane == 0) {
+          s_nseg = nseg; s_minthr = mt;
+          if (nseg <= 1 || below) s_done = 1;
+          if (!single_big) {
+            float r = 1.5f * (float)(kept + 8) / (float)(L + 8);
+            s_ratio = fminf(1.0f, fmaxf(r, 1.0f / 64.0f));
+          }
+        }
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+    c0 = c1;
+  }
+  // --- emit the segment that contains local vertex 0 (the unit itself) ---
+  if (tid < 32) {
+    const int lane = tid;
     const int s0 = s_seg[0];
     int cnt = 0;
     for (int b = 0; b < n; b += 32) {
-      int v = b + lane;
-      bool in = v < n && s_seg[v] == s0;
-      uint32_t bal = __ballot_sync(0xffffffffu, in);
+      const int v = b + lane;
+      const bool in = v < n && s_seg[v] == s0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, in);
       if (in) conn_idx[off + cnt + __popc(bal & ((1u << lane) - 1u))] = s_gid[v];
       cnt += __popc(bal);
     }
