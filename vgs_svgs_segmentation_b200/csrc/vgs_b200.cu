@@ -314,11 +314,9 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     cudaError_t r = optin((const void*)k_local_graph2<64, true>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, true>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, true>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<512, true>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<64, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, false>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<512, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
@@ -645,20 +643,25 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
   // ---- stage 4+5a: local graphs ----
   {
     StageTimer t(h, &h->tm.graph_ms, 5);
-    CK(h->class_count.reserve(64)); CK(h->class_list.reserve((size_t)N_CLASSES * nu * 4));
+    CK(h->class_count.reserve(256)); CK(h->class_list.reserve((size_t)N_CLASSES * nu * 4));
     unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
-    CK(cudaMemsetAsync(h->class_count.p, 0, 64, h->stream));
+    float* d_wempty = h->small.as<float>() + 160;
+    uint32_t* d_maxn = h->class_count.as<uint32_t>() + 32;
+    CK(cudaMemsetAsync(h->class_count.p, 0, 256, h->stream));
     CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));
-    LAUNCH(k_bin_classes, (unsigned)cdiv(nu, 256), 256, 0, h->adj_off.as<uint32_t>(), h->rec.as<float>(), nu,
-           h->class_count.as<uint32_t>(), h->class_list.as<uint32_t>(), d_stats);
-    uint32_t cc[N_CLASSES];
+    LAUNCH(k_wempty, 1, 1, 0, gp.pp, d_wempty);
+    LAUNCH(k_bin_classes, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+           h->rec.as<float>(), nu, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(), d_maxn,
+           h->class_list.as<uint32_t>(), d_stats);
+    uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
     unsigned long long stats[3];
     CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cmaxn, d_maxn, sizeof(cmaxn), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
-    if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a neighbourhood has more than 181 units (graph_size / unit spacing too large)");
+    if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a local graph has more than 181 enumerated (or 255 total) units (graph_size / unit spacing too large)");
     // pair-weight cache (VGS lattice): each unordered pair of used voxels evaluated once
     bool cached = false;
     int half = 0, r2 = 0;
@@ -697,18 +700,18 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
     }
     for (int c = 0; c < N_CLASSES; c++) {
       if (!cc[c]) continue;
-      const int ncap = CLASS_N_HOST[c], mcap = ncap * (ncap - 1), T = CLASS_T_HOST[c];
-      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (12 + (cached ? 16 : 4 * REC_PAD)) + (LG_BINS + 1) * 4 + 64;
+      const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
+      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (LG_BINS + 1) * 4 + 64;
       const uint32_t* list = h->class_list.as<uint32_t>() + (size_t)c * nu;
 #define LG(TT, CC)                                                                                                  \
   do {                                                                                                              \
     auto kfn = k_local_graph2<TT, CC>;                                                                              \
     LAUNCH(kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),                  \
            h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2,        \
-           h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
+           d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
   } while (0)
-      if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else if (T == 256) LG(256, true); else LG(512, true); }
-      else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else if (T == 256) LG(256, false); else LG(512, false); }
+      if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else LG(256, true); }
+      else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else LG(256, false); }
 #undef LG
     }
     t.stop();

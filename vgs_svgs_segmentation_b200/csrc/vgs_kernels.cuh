@@ -6,13 +6,14 @@
 namespace vgs {
 
 constexpr int MAX_EPOCHS = 40;
-constexpr int N_CLASSES = 9;
-// class c holds neighbourhoods with n <= CLASS_N[c]; capacity n(n-1) directed off-diagonal weights
-__constant__ int c_class_n[N_CLASSES] = {16, 32, 48, 64, 80, 96, 112, 128, 181};
-constexpr int CLASS_N_HOST[N_CLASSES] = {16, 32, 48, 64, 80, 96, 112, 128, 181};
-constexpr int CLASS_T_HOST[N_CLASSES] = {64, 128, 128, 256, 256, 256, 512, 512, 512};
-constexpr int LG_CS = 1024;    // staging capacity (entries) of one sorted chunk
-constexpr int LG_CH = 512;     // target chunk size
+constexpr int N_CLASSES = 10;
+// class c holds local graphs whose ENUMERATED vertex count (used neighbours; all neighbours when the
+// empty-pair weight can merge) is <= CLASS_N[c]; pool capacity CLASS_N(CLASS_N-1) directed weights
+__constant__ int c_class_n[N_CLASSES] = {16, 32, 40, 48, 64, 80, 96, 112, 128, 181};
+constexpr int CLASS_N_HOST[N_CLASSES] = {16, 32, 40, 48, 64, 80, 96, 112, 128, 181};
+constexpr int CLASS_T_HOST[N_CLASSES] = {64, 64, 64, 64, 128, 128, 128, 256, 256, 256};
+constexpr int LG_CS = 512;     // staging capacity (entries) of one sorted chunk
+constexpr int LG_CH = 128;     // target chunk size (all merges of a planar neighbourhood happen in the top ~100 weights)
 constexpr int LG_BINS = 256;   // weight histogram bins
 constexpr int MAX_NEIGH = 181;
 constexpr int REC_PAD = 17;  // smem row stride of a 16-float record (bank-conflict free)
@@ -223,20 +224,45 @@ __global__ void __launch_bounds__(128) k_adjacency(const uint32_t* __restrict__ 
   }
 }
 
-// ---- bin used units by neighbourhood size class ----
-__global__ void __launch_bounds__(256) k_bin_classes(const uint32_t* __restrict__ adj_off, const float* __restrict__ rec, int64_t nu,
-                                                   uint32_t* __restrict__ class_count, uint32_t* __restrict__ class_list,
-                                                   unsigned long long* __restrict__ stats /* [0]=sum n^2 [1]=max n [2]=overflow */) {
-  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// weight of any pair that involves an unused (all-empty) unit: one value per parameter set
+__global__ void k_wempty(PairParams pp, float* __restrict__ out) {
+  float z[REC_FLOATS];
+  for (int q = 0; q < REC_FLOATS; q++) z[q] = 0.f;
+  float a, b;
+  pair_weights(z, z, pp, a, b);
+  out[0] = a;
+}
+
+// ---- bin used units by the size of their local graph.  One warp per unit: counts the USED
+//      neighbours; pairs with an unused unit are enumerated only if their constant weight could
+//      merge (w_empty > cut bound), which never happens with the reference's parameter sets. ----
+__global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
+                                                   const float* __restrict__ rec, int64_t nu, float cut, int svgs,
+                                                   const float* __restrict__ wempty, uint32_t* __restrict__ class_count,
+                                                   uint32_t* __restrict__ class_maxn, uint32_t* __restrict__ class_list,
+                                                   unsigned long long* __restrict__ stats /* [0]=sum n(n-1) [1]=max n [2]=overflow */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= nu) return;
-  int fl = f2i(rec[u * REC_FLOATS + REC_FLAGS]);
-  if (!(fl & F_USED)) return;
-  int n = (int)(adj_off[u + 1] - adj_off[u]);
+  if (!(f2i(rec[u * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off);
+  int used = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    bool us = false;
+    if (e < n) us = (f2i(__ldg(rec + (int64_t)adj_idx[off + e] * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+    used += __popc(__ballot_sync(0xffffffffu, us));
+  }
+  if (lane != 0) return;
+  const float lb = (float)(1.0 - 2.0 * (double)cut + (double)cut / (double)n - 4e-7 * (double)(n + 8));
+  const int need = (svgs || wempty[0] > lb) ? n : used;
   int c = 0;
-  while (c < N_CLASSES && n > c_class_n[c]) c++;
+  while (c < N_CLASSES && need > c_class_n[c]) c++;
   atomicMax(&stats[1], (unsigned long long)n);
-  if (c >= N_CLASSES) { atomicAdd(&stats[2], 1ull); return; }
+  if (c >= N_CLASSES || n > 255) { atomicAdd(&stats[2], 1ull); return; }
   atomicAdd(&stats[0], (unsigned long long)n * (unsigned long long)(n - 1));
+  atomicMax(&class_maxn[c], (uint32_t)n);
   uint32_t pos = atomicAdd(&class_count[c], 1u);
   class_list[(int64_t)c * nu + pos] = (uint32_t)u;
 }
@@ -327,8 +353,8 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
                                                         const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
                                                         const float* __restrict__ rec, const uint32_t* __restrict__ key3,
                                                         GraphParams gp, int ncap, int mcap, const float2* __restrict__ table,
-                                                        int half, int r2, uint32_t* __restrict__ conn_cnt,
-                                                        int32_t* __restrict__ conn_idx) {
+                                                        int half, int r2, const float* __restrict__ wempty,
+                                                        uint32_t* __restrict__ conn_cnt, int32_t* __restrict__ conn_idx) {
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int AUX = CACHED ? 4 : REC_PAD;
   float* A_w = reinterpret_cast<float*>(smraw);                                  // mcap: weight pool (append order)
@@ -341,7 +367,8 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   unsigned short* C_f = A_f + mcap;                                              // LG_CS
   unsigned short* s_seg = C_f + LG_CS;                                           // ncap
   unsigned short* s_size = s_seg + ncap;                                         // ncap
-  __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot;
+  unsigned short* s_ul = s_size + ncap;                                          // ncap: local ids of the used vertices
+  __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot, s_nu, s_c0b;
   __shared__ float s_minthr, s_wempty, s_ratio;
 
   const int tid = threadIdx.x;
@@ -363,13 +390,6 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
       s_aux[4 * i] = (int)key3[3 * g]; s_aux[4 * i + 1] = (int)key3[3 * g + 1]; s_aux[4 * i + 2] = (int)key3[3 * g + 2];
       s_aux[4 * i + 3] = f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS));
     }
-    if (tid == 0) {  // weight of any pair that involves an unused (all-empty) unit
-      float z[REC_FLOATS];
-      for (int q = 0; q < REC_FLOATS; q++) z[q] = 0.f;
-      float a, b;
-      pair_weights(z, z, gp.pp, a, b);
-      s_wempty = a;
-    }
   } else {
     float* s_rec = reinterpret_cast<float*>(s_aux);
     for (int t = tid; t < n * 4; t += THREADS) {
@@ -379,16 +399,35 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
       d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
     }
   }
+  if (tid == 0) s_wempty = wempty[0];
+  __syncthreads();
+  if (tid < 32) {   // ordered list of the used local vertices
+    int cnt = 0;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      const int v = b0 + tid;
+      bool us = false;
+      if (v < n) us = ((CACHED ? s_aux[4 * v + 3] : s_aux[v * REC_PAD + REC_FLAGS]) & F_USED) != 0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, us);
+      if (us) s_ul[cnt + __popc(bal & ((1u << tid) - 1u))] = (unsigned short)v;
+      cnt += __popc(bal);
+    }
+    if (tid == 0) s_nu = cnt;
+  }
   __syncthreads();
   // --- 1. directed weights of all unordered pairs -> pool + histogram ---
   const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
   const float scale = (float)LG_BINS / fmaxf(1.0f - lb, 1e-3f);
-  const int npairs = n * (n - 1) / 2;
+  // Pairs with an unused (all-empty) unit all have the same weight w_empty; when that weight cannot
+  // merge (w_empty <= lb, the normal case) only pairs of USED vertices are enumerated.
+  const bool all_pairs = s_wempty > lb;
+  const int nv = all_pairs ? n : s_nu;
+  const int npairs = nv * (nv - 1) / 2;
   for (int p = tid; p < npairs; p += THREADS) {
-    int r = p / (n - 1), c = p - r * (n - 1);
+    int r = p / (nv - 1), c = p - r * (nv - 1);
     int a, b;
-    if (c < n - 1 - r) { a = r; b = r + 1 + c; }
-    else { a = n - 1 - r; b = a + 1 + (c - (n - 1 - r)); }
+    if (c < nv - 1 - r) { a = r; b = r + 1 + c; }
+    else { a = nv - 1 - r; b = a + 1 + (c - (nv - 1 - r)); }
+    if (!all_pairs) { a = s_ul[a]; b = s_ul[b]; }
     float w_ab, w_ba;
     if (CACHED) {
       const int fa = s_aux[4 * a + 3], fb = s_aux[4 * b + 3];
@@ -425,23 +464,44 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   //     Entries whose two vertices already share a segment are no-ops for ever (segments only
   //     grow) and are skipped at gather time; s_ratio tracks how many entries survive that, so the
   //     bin range of the next chunk is sized for ~LG_CH surviving entries. ---
+  // inclusive prefix sums of the histogram (warp 0), so a chunk boundary is a short search
+  if (tid < 32) {
+    constexpr int PER = LG_BINS / 32;
+    unsigned loc[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { sum += s_hist[tid * PER + q]; loc[q] = sum; }
+    unsigned inc = warp_incl_scan(sum, tid);
+    const unsigned base = inc - sum;
+#pragma unroll
+    for (int q = 0; q < PER; q++) s_hist[tid * PER + q] = base + loc[q];
+  }
+  __syncthreads();
   int c0 = 0;
   while (c0 < LG_BINS && !s_done && m > 0) {
     if (tid == 0) {
-      while (c0 < LG_BINS && s_hist[c0] == 0) c0++;   // skip empty bins
-      int c1 = c0, tot = 0;
-      if (c0 < LG_BINS) { tot = (int)s_hist[c0]; c1 = c0 + 1; }
+      const int before = c0 > 0 ? (int)s_hist[c0 - 1] : 0;    // entries in bins < c0
+      // target: (count in [c0,c1)) * ratio <= LG_CH, at least one non-empty bin
       const float ratio = s_ratio;
-      while (c1 < LG_BINS && (float)(tot + (int)s_hist[c1]) * ratio <= (float)LG_CH) { tot += (int)s_hist[c1]; c1++; }
-      s_c1 = c1; s_cnt = 0; s_tot = tot;
-      s_hist[LG_BINS] = (unsigned)c0;
+      const int budget = before + max(1, (int)((float)LG_CH / ratio));
+      int lo = c0, hi = LG_BINS;       // largest c1 with prefix[c1-1] <= budget
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)s_hist[mid - 1] <= budget) lo = mid; else hi = mid - 1; }
+      int c1 = lo;
+      if (c1 <= c0 || (int)s_hist[c1 - 1] == before) {   // next non-empty bin alone exceeds the budget (or none left)
+        int l2 = c0, h2 = LG_BINS;      // smallest c1 with prefix[c1-1] > before
+        while (l2 < h2) { int mid = (l2 + h2) >> 1; if (mid >= 1 && (int)s_hist[mid - 1] > before) h2 = mid; else l2 = mid + 1; }
+        c1 = l2;
+        if (c1 > LG_BINS) c1 = LG_BINS;
+        if (c1 >= 1 && c1 <= LG_BINS && (int)s_hist[c1 - 1] == before) c1 = LG_BINS;   // nothing left
+      }
+      s_c1 = c1; s_cnt = 0; s_tot = (c1 >= 1 ? (int)s_hist[c1 - 1] : 0) - before;
+      s_c0b = (s_tot == 0) ? LG_BINS : c0;
     }
     __syncthreads();
-    c0 = (int)s_hist[LG_BINS];
+    c0 = s_c0b;
     const int c1 = s_c1;
     if (c0 >= LG_BINS) break;
     const int L = s_tot;
-    const bool single_big = (c1 == c0 + 1) && (L > LG_CS);
+    const bool single_big = (L > LG_CS) && s_ratio >= 1.0f;   // one bin alone overflows the staging buffer
     int kept = 0;
     if (!single_big) {
       // gather the chunk's still-useful entries
@@ -462,6 +522,11 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
         __syncthreads();
         if (tid == 0) s_ratio = 1.0f;
         __syncthreads();
+        continue;
+      }
+      if (kept == 0) {          // every entry of this range is already inside one segment
+        __syncthreads();
+        c0 = c1;
         continue;
       }
     }
@@ -495,12 +560,14 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
         Lw = min(LG_CS, L - win * LG_CS);
         for (int i = tid; i < m; i += THREADS) {
           const float w = A_w[i];
-          if (min(LG_BINS - 1, (int)((1.0f - w) * scale)) != c0) continue;
+          const int bx = min(LG_BINS - 1, (int)((1.0f - w) * scale));
+          if (bx < c0 || bx >= c1) continue;
           const unsigned short f = A_f[i];
           int rank = 0;
           for (int y = 0; y < m; y++) {
             const float wy = A_w[y];
-            if (min(LG_BINS - 1, (int)((1.0f - wy) * scale)) == c0 && ((wy > w) || (wy == w && A_f[y] < f))) rank++;
+            const int by = min(LG_BINS - 1, (int)((1.0f - wy) * scale));
+            if (by >= c0 && by < c1 && ((wy > w) || (wy == w && A_f[y] < f))) rank++;
           }
           if (rank >= win * LG_CS && rank < (win + 1) * LG_CS) { C_w[rank - win * LG_CS] = w; C_f[rank - win * LG_CS] = f; }
         }
