@@ -176,3 +176,50 @@ def test_vgs_large_cut_keeps_zero_weights(built_lib):
     g = gpu_stages(xyz, **kw)
     r = oracle.run(xyz, math=1, **kw)
     _compare_vgs(xyz, g, r)
+
+
+def _compare_svgs(xyz, labels, g, r):
+    np.testing.assert_array_equal(g["point_unit"], r.point_unit)           # supervoxel ids = ascending label
+    np.testing.assert_array_equal(g["unit_offsets"], r.unit_offsets)
+    np.testing.assert_array_equal(g["unit_points"], r.unit_points)
+    for k in ("centroid", "normal", "eigen"):
+        a, b = g[k], r[k]
+        nbad = int((a.view(np.uint32) != b.view(np.uint32)).sum())
+        rel = float((np.abs(a - b) / np.maximum(np.abs(b), 1e-30)).max())
+        print(f"{k}: {nbad} of {a.size} floats not bit-identical, max rel err {rel:.3g}")
+        assert rel <= FEATURE_RTOL and nbad == 0, k
+    np.testing.assert_array_equal(g["adj_offsets"], r.adj_offsets)
+    np.testing.assert_array_equal(g["adj_idx"], r.adj_idx)
+    off = g["adj_offsets"]
+    assert csr_sets(off, g["conn0_count"], g["conn0_idx"]) == oracle_conn_sets(r.conn0_offsets, r.conn0_idx)
+    assert csr_sets(off, g["conn1_count"], g["conn1_idx"]) == oracle_conn_sets(r.conn1_offsets, r.conn1_idx)
+    np.testing.assert_array_equal(g["attach"], r.attach)
+    np.testing.assert_array_equal(g["unit_root"], _roots(r.unit_cluster))
+    assert g["n_clusters"] == (r.stats["n_clusters_all"], r.stats["n_clusters_exported"])
+    np.testing.assert_array_equal(g["point_label"], r.point_label)
+
+
+@pytest.mark.parametrize("name,seed_size", [("town", 0.25), ("site", 0.25), ("two_planes", 0.2)])
+def test_svgs_stage_parity(built_lib, name, seed_size):
+    """SVGS downstream of supplied per-point supervoxel labels (the VCCS generator itself is PCL
+    code with unpinned parity): Task_File_SVGS.txt parameters."""
+    xyz = _scene(name)
+    labels = scenes.supervoxel_labels_grid(xyz, seed_size)
+    ml = int(labels.max()) + 1
+    g = gpu_stages(xyz, mode=1, labels=labels, max_label=ml)
+    r = oracle.run(xyz, labels=labels, max_label=ml, mode=1, math=1)
+    print(name, g["counts"], g["timings"])
+    assert g["n_voxels"] == r.stats["max_n_or_voxels"]          # getVoxelNum of the 0.05 m octree (SV.h:111)
+    _compare_svgs(xyz, labels, g, r)
+
+
+def test_svgs_drops_max_label_and_unlabelled(built_lib):
+    """SV.h:303-323: label 0 is unlabelled, and the label loop stops before max_label."""
+    xyz = _scene("two_planes")
+    labels = scenes.supervoxel_labels_grid(xyz, 0.25)
+    labels[::17] = 0
+    ml = int(labels.max())          # getMaxLabel(): the largest label is dropped by `k < max_label`
+    g = gpu_stages(xyz, mode=1, labels=labels, max_label=ml)
+    r = oracle.run(xyz, labels=labels, max_label=ml, mode=1, math=1)
+    _compare_svgs(xyz, labels, g, r)
+    assert np.all(g["point_label"][labels == 0] == -1) and np.all(g["point_label"][labels == ml] == -1)

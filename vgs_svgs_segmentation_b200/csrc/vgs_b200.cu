@@ -89,6 +89,7 @@ struct vgs_context {
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
   DBuf stencil2, pair_table;
+  DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
 
   vgs_timings tm{};
@@ -135,9 +136,9 @@ vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, 
 }
 
 // stable LSD radix sort of (key,val) over the low nbits bits; result pointers returned
-vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out) {
-  uint64_t* ka = h->keysA.as<uint64_t>(); uint64_t* kb = h->keysB.as<uint64_t>();
-  uint32_t* va = h->valsA.as<uint32_t>(); uint32_t* vb = h->valsB.as<uint32_t>();
+vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out,
+                      uint64_t* ka = nullptr, uint64_t* kb = nullptr, uint32_t* va = nullptr, uint32_t* vb = nullptr) {
+  if (!ka) { ka = h->keysA.as<uint64_t>(); kb = h->keysB.as<uint64_t>(); va = h->valsA.as<uint32_t>(); vb = h->valsB.as<uint32_t>(); }
   int64_t nblk = cdiv(n, RS_TILE);
   if (nblk < 1) nblk = 1;
   CK(h->hist.reserve((size_t)nblk * 256 * 4));
@@ -153,22 +154,24 @@ vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, u
 }
 
 // sorted keys -> unit table.  n_valid = number of sorted positions with key < sentinel.
-vgs_status build_units(vgs_handle h, const uint64_t* keys, int64_t n_valid, int64_t* n_units) {
+vgs_status build_units(vgs_handle h, const uint64_t* keys, int64_t n_valid, int64_t* n_units, DBuf* ustart = nullptr,
+                       DBuf* ukey = nullptr, DBuf* pos_unit = nullptr) {
+  if (!ustart) { ustart = &h->ustart; ukey = &h->ukey; pos_unit = &h->pos_unit; }
   if (n_valid <= 0) { *n_units = 0; return VGS_OK; }
   CK(h->flags.reserve((size_t)n_valid * 4));
   CK(h->scan.reserve((size_t)n_valid * 4));
-  CK(h->pos_unit.reserve((size_t)n_valid * 4));
+  CK(pos_unit->reserve((size_t)n_valid * 4));
   LAUNCH(k_head_flags, (unsigned)cdiv(n_valid, 256), 256, 0, keys, n_valid, h->flags.as<uint32_t>());
   unsigned long long total = 0;
   vgs_status s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid, &total);
   if (s) return s;
   *n_units = (int64_t)total;
-  CK(h->ustart.reserve((size_t)(total + 1) * 4));
-  CK(h->ukey.reserve((size_t)(total + 1) * 8));
+  CK(ustart->reserve((size_t)(total + 1) * 4));
+  CK(ukey->reserve((size_t)(total + 1) * 8));
   LAUNCH(k_head_write, (unsigned)cdiv(n_valid, 256), 256, 0, keys, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid,
-         h->ustart.as<uint32_t>(), h->ukey.as<uint64_t>(), h->pos_unit.as<uint32_t>());
+         ustart->as<uint32_t>(), ukey->as<uint64_t>(), pos_unit->as<uint32_t>());
   uint32_t endv = (uint32_t)n_valid;
-  CK(cudaMemcpyAsync(h->ustart.as<uint32_t>() + total, &endv, 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(ustart->as<uint32_t>() + total, &endv, 4, cudaMemcpyHostToDevice, h->stream));
   return VGS_OK;
 }
 
@@ -337,7 +340,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -390,7 +393,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   const int64_t n = h->n;
   h->voxel_size = voxel_size;
   h->voxelized = false;
-  if (h->mode == VGS_MODE_VGS) h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  h->have_units = h->have_features = h->have_adj = h->have_segments = false;   // the sort buffers are shared
   CK(h->small.reserve(4096));
 
   // ---- stage 0: PCL dynamic bounding box (origin) ----
@@ -579,9 +582,67 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   if (!h) return VGS_ERR_INVALID;
   if (!h->have_features) return h->fail(VGS_ERR_STATE, "vgs_find_adjacency: call vgs_compute_features first");
   if (!(graph_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_find_adjacency: graph_size must be > 0");
-  if (h->mode == VGS_MODE_SVGS) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: SVGS neighbour search not built yet");
   CK(cudaSetDevice(h->device));
   StageTimer t(h, &h->tm.adjacency_ms, 4);
+  if (h->mode == VGS_MODE_SVGS) {
+    // findAllSupervoxelNeighbors SV.h:1477-1521: FLANN radius search over supervoxel CENTROIDS
+    // (arbitrary floats).  A uniform grid of cell size 1.01 r only prunes candidates; the float test
+    // and the (dist2, id) order are FLANN's.
+    h->graph_size = graph_size;
+    h->have_adj = h->have_segments = false;
+    h->stencil_host.clear();
+    const int64_t nu = h->nu;
+    const float cell = graph_size * 1.01f;
+    CK(h->gridmin.reserve(64));
+    const uint32_t init[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+    CK(cudaMemcpyAsync(h->gridmin.p, init, 12, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_centroid_min, (unsigned)std::min<int64_t>(cdiv(nu, 256), 1024), 256, 0, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>());
+    CK(h->ckeysA.reserve((size_t)nu * 8)); CK(h->ckeysB.reserve((size_t)nu * 8));
+    CK(h->cvalsA.reserve((size_t)nu * 4)); CK(h->cvalsB.reserve((size_t)nu * 4));
+    LAUNCH(k_cell_keys, (unsigned)cdiv(nu, 256), 256, 0, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
+           h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>());
+    uint64_t* ks; uint32_t* vs;
+    vgs_status s = radix_sort(h, nu, 63, &ks, &vs, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(), h->cvalsA.as<uint32_t>(),
+                              h->cvalsB.as<uint32_t>());
+    if (s) return s;
+    int64_t ncells = 0;
+    s = build_units(h, ks, nu, &ncells, &h->cstart, &h->ckey, &h->cpos);
+    if (s) return s;
+    uint64_t capacity = 64;
+    while (capacity < (uint64_t)ncells * 2) capacity <<= 1;
+    h->hmask = capacity - 1;
+    CK(h->tk.reserve(capacity * 8)); CK(h->tv.reserve(capacity * 4));
+    CK(cudaMemsetAsync(h->tk.p, 0xff, capacity * 8, h->stream));
+    LAUNCH(k_hash_insert, (unsigned)cdiv(ncells, 256), 256, 0, h->ckey.as<uint64_t>(), ncells, h->tk.as<unsigned long long>(),
+           h->tv.as<uint32_t>(), h->hmask);
+    double r = (double)graph_size;
+    float r2 = (float)(r * r);
+    const int cap = 256, wpb = 4;
+    size_t smem = (size_t)wpb * cap * 8;
+    CK(h->adj_cnt.reserve((size_t)(nu + 1) * 4)); CK(h->adj_off.reserve((size_t)(nu + 1) * 4));
+    unsigned long long* d_over = h->small.as<unsigned long long>() + 56;
+    CK(cudaMemsetAsync(d_over, 0, 8, h->stream));
+    LAUNCH(k_adjacency_svgs, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
+           h->cstart.as<uint32_t>(), vs, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 0,
+           h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, (int32_t*)nullptr, cap, d_over);
+    unsigned long long total = 0, over = 0;
+    s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, &total);
+    if (s) return s;
+    CK(cudaMemcpyAsync(&over, d_over, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (over) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: a supervoxel has more than 255 neighbours within graph_size");
+    uint32_t tot32 = (uint32_t)total;
+    CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, &tot32, 4, cudaMemcpyHostToDevice, h->stream));
+    h->n_adj = (int64_t)total;
+    CK(h->adj_idx.reserve((size_t)total * 4 + 16));
+    LAUNCH(k_adjacency_svgs, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
+           h->cstart.as<uint32_t>(), vs, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
+           h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), cap, d_over);
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_adj = true;
+    t.stop();
+    return VGS_OK;
+  }
   { vgs_status sg_ = ensure_geometry(h); if (sg_) return sg_; }
   h->graph_size = graph_size;
   h->have_adj = h->have_segments = false;

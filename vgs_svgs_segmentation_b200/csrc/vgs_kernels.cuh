@@ -224,6 +224,92 @@ __global__ void __launch_bounds__(128) k_adjacency(const uint32_t* __restrict__ 
   }
 }
 
+// ---- stage 3 (SVGS): radius search over supervoxel centroids (SV.h:1477-1521).  Uniform grid of
+//      cell size >= r: a unit's neighbours lie in the 27 cells around its own. ----
+__device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void __launch_bounds__(256) k_centroid_min(const float* __restrict__ rec, int64_t nu, uint32_t* __restrict__ gmin) {
+  uint32_t m[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += (int64_t)gridDim.x * blockDim.x)
+    for (int a = 0; a < 3; a++) m[a] = min(m[a], f2ord(rec[u * REC_FLOATS + a]));
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[a] = min(m[a], __shfl_xor_sync(0xffffffffu, m[a], o));
+    if ((threadIdx.x & 31) == 0) atomicMin(&gmin[a], m[a]);
+  }
+}
+__device__ __forceinline__ void cell_of(const float* c, const uint32_t* gmin, float cell, int& cx, int& cy, int& cz) {
+  cx = (int)floorf((c[0] - ord2f(gmin[0])) / cell);
+  cy = (int)floorf((c[1] - ord2f(gmin[1])) / cell);
+  cz = (int)floorf((c[2] - ord2f(gmin[2])) / cell);
+}
+__global__ void __launch_bounds__(256) k_cell_keys(const float* __restrict__ rec, int64_t nu, const uint32_t* __restrict__ gmin, float cell,
+                                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu) return;
+  int cx, cy, cz;
+  cell_of(rec + u * REC_FLOATS, gmin, cell, cx, cy, cz);
+  keys[u] = morton_encode((uint32_t)cx & 0x1fffffu, (uint32_t)cy & 0x1fffffu, (uint32_t)cz & 0x1fffffu);
+  vals[u] = (uint32_t)u;
+}
+// one warp per unit; cstart/cunits = cell table (units sorted by cell key); fill as in k_adjacency
+__global__ void __launch_bounds__(128) k_adjacency_svgs(const float* __restrict__ rec, int64_t nu, const uint32_t* __restrict__ gmin,
+                                                      float cell, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ cunits,
+                                                      const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
+                                                      uint64_t mask, float r2, int fill, uint32_t* __restrict__ adj_cnt,
+                                                      const uint32_t* __restrict__ adj_off, int32_t* __restrict__ adj_idx, int cap,
+                                                      unsigned long long* __restrict__ overflow) {
+  extern __shared__ unsigned char smraw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* sd2 = reinterpret_cast<float*>(smraw) + (size_t)w * cap;
+  int* sid = reinterpret_cast<int*>(smraw + (size_t)wpb * cap * sizeof(float)) + (size_t)w * cap;
+  const int64_t v = (int64_t)blockIdx.x * wpb + w;
+  if (v >= nu) return;
+  const float qx = rec[v * REC_FLOATS], qy = rec[v * REC_FLOATS + 1], qz = rec[v * REC_FLOATS + 2];
+  int cx, cy, cz;
+  cell_of(rec + v * REC_FLOATS, gmin, cell, cx, cy, cz);
+  int count = 0;
+  for (int d = 0; d < 27; d++) {
+    const int x = cx + d / 9 - 1, y = cy + (d / 3) % 3 - 1, z = cz + d % 3 - 1;
+    if (x < 0 || y < 0 || z < 0) continue;
+    const int c = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+    if (c < 0) continue;
+    const uint32_t s = cstart[c], e = cstart[c + 1];
+    for (uint32_t b = s; b < e; b += 32) {
+      const uint32_t i = b + lane;
+      int id = -1;
+      float d2 = 0.f;
+      if (i < e) {
+        id = (int)cunits[i];
+        const float* t = rec + (int64_t)id * REC_FLOATS;
+        const float dx = qx - t[0], dy = qy - t[1], dz = qz - t[2];
+        d2 = 0.f; d2 += dx * dx; d2 += dy * dy; d2 += dz * dz;
+        if (!(d2 < r2)) id = -1;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
+      if (fill && id >= 0) {
+        const int pos = count + __popc(bal & ((1u << lane) - 1u));
+        if (pos < cap) { sd2[pos] = d2; sid[pos] = id; }
+      }
+      count += __popc(bal);
+    }
+  }
+  if (count >= cap) { if (lane == 0) atomicAdd(overflow, 1ull); count = cap - 1; }
+  if (!fill) { if (lane == 0) adj_cnt[v] = (uint32_t)count; return; }
+  __syncwarp();
+  const uint32_t off = adj_off[v];
+  for (int e = lane; e < count; e += 32) {
+    const float d = sd2[e]; const int id = sid[e];
+    int rank = 0;
+    for (int j = 0; j < count; j++) {
+      const float dj = sd2[j]; const int ij = sid[j];
+      rank += (dj < d || (dj == d && ij < id)) ? 1 : 0;
+    }
+    adj_idx[off + rank] = id;
+  }
+}
+
 // weight of any pair that involves an unused (all-empty) unit: one value per parameter set
 __global__ void k_wempty(PairParams pp, float* __restrict__ out) {
   float z[REC_FLOATS];
