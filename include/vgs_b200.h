@@ -108,6 +108,9 @@ vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz /* V x 3 */); /* getVo
  *    them (SV.h:283-323; 0 = unlabelled, labels >= max_label are dropped, max_label <= 0 keeps all).
  *    on_device as above. -- */
 vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* label_per_point, int32_t max_label, int on_device);
+/* Stand-in for createSupervoxels when no VCCS labels are supplied: one supervoxel per occupied cell of a
+ * seed_size grid anchored at the octree origin (deterministic; NOT PCL's VCCS, whose parity is unpinned). */
+vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size);
 vgs_status vgs_unit_count(vgs_handle h, int64_t* n_units);              /* getSuperVoxelNum SV.h:118 */
 
 /* -- stage 2: calcualteVoxelCloudAttributes VS.h:290-369 / calcualteSupervoxelCloudAttributes SV.h:1238 -- */

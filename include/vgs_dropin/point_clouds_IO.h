@@ -1,0 +1,114 @@
+// point_clouds_IO.h (drop-in) — the I/O entry points the reference's driver uses (reference
+// point_clouds_IO.h:64-108, point_clouds_IO.cpp:22-76, 147-169), without PCL:
+//   inputTaskTxtFile      : every line of the task file, comments and blanks included; parameter k = line k
+//   inputPointCloudData   : PCD v0.7 reader (DATA ascii | binary; x y z as F 4, other fields skipped)
+//   saveColoredClusters   : PCD writer (binary, x y z rgb), one deterministic colour per cluster
+// The reference's PCLVisualizer windows (showColoredClusters) are out of scope (GUI).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pcl_shim.h"
+
+// IO.cpp:147-169 — getline per line; a trailing '\r' (the shipped task files are CRLF) stays in the string,
+// atof/atoi ignore it (test:25-37)
+inline std::vector<std::string> inputTaskTxtFile(const std::string& pathname_file) {
+  std::vector<std::string> task_vector;
+  std::ifstream f(pathname_file.c_str());
+  std::string line;
+  while (std::getline(f, line)) task_vector.push_back(line);
+  return task_vector;
+}
+
+inline std::string vgs_rstrip(const std::string& s) {
+  size_t e = s.size();
+  while (e > 0 && (s[e - 1] == '\r' || s[e - 1] == '\n' || s[e - 1] == ' ' || s[e - 1] == '\t')) e--;
+  return s.substr(0, e);
+}
+
+// IO.h:64-80 (pcl::io::loadPCDFile into PointXYZ: only x, y, z survive)
+inline int inputPointCloudData(const std::string& name, PCXYZPtr cloud) {
+  std::ifstream f(name.c_str(), std::ios::binary);
+  if (!f) return -1;
+  std::vector<std::string> fields; std::vector<int> sizes, counts; std::vector<char> types;
+  long npoints = -1; std::string data, line;
+  while (std::getline(f, line)) {
+    line = vgs_rstrip(line);
+    if (line.empty() || line[0] == '#') continue;
+    std::istringstream ss(line); std::string key; ss >> key;
+    if (key == "FIELDS") { std::string t; while (ss >> t) fields.push_back(t); }
+    else if (key == "SIZE") { int t; while (ss >> t) sizes.push_back(t); }
+    else if (key == "TYPE") { char t; while (ss >> t) types.push_back(t); }
+    else if (key == "COUNT") { int t; while (ss >> t) counts.push_back(t); }
+    else if (key == "POINTS") ss >> npoints;
+    else if (key == "DATA") { ss >> data; break; }
+  }
+  if (counts.empty()) counts.assign(fields.size(), 1);
+  if (npoints < 0 || fields.size() != sizes.size() || fields.size() != types.size()) return -2;
+  int ix = -1, iy = -1, iz = -1; std::vector<int> offs(fields.size()); int rec = 0;
+  for (size_t i = 0; i < fields.size(); i++) {
+    offs[i] = rec; rec += sizes[i] * counts[i];
+    if (fields[i] == "x") ix = (int)i;
+    if (fields[i] == "y") iy = (int)i;
+    if (fields[i] == "z") iz = (int)i;
+  }
+  if (ix < 0 || iy < 0 || iz < 0) return -3;
+  cloud->points.clear();
+  cloud->points.reserve((size_t)npoints);
+  if (data == "ascii") {
+    for (long p = 0; p < npoints; p++) {
+      if (!std::getline(f, line)) break;
+      std::istringstream ss(line); std::vector<double> v; double t;
+      while (ss >> t) v.push_back(t);
+      int col = 0; float xyz[3] = {0, 0, 0};
+      for (size_t i = 0; i < fields.size(); i++) {
+        if ((int)i == ix && col < (int)v.size()) xyz[0] = (float)v[col];
+        if ((int)i == iy && col < (int)v.size()) xyz[1] = (float)v[col];
+        if ((int)i == iz && col < (int)v.size()) xyz[2] = (float)v[col];
+        col += counts[i];
+      }
+      cloud->points.push_back(pcl::PointXYZ(xyz[0], xyz[1], xyz[2]));
+    }
+  } else if (data == "binary") {
+    if (types[ix] != 'F' || sizes[ix] != 4 || types[iy] != 'F' || sizes[iy] != 4 || types[iz] != 'F' || sizes[iz] != 4) return -4;
+    std::vector<char> buf((size_t)rec * (size_t)npoints);
+    f.read(buf.data(), (std::streamsize)buf.size());
+    if ((size_t)f.gcount() != buf.size()) return -5;
+    for (long p = 0; p < npoints; p++) {
+      float x, y, z;
+      std::memcpy(&x, &buf[(size_t)p * rec + offs[ix]], 4);
+      std::memcpy(&y, &buf[(size_t)p * rec + offs[iy]], 4);
+      std::memcpy(&z, &buf[(size_t)p * rec + offs[iz]], 4);
+      cloud->points.push_back(pcl::PointXYZ(x, y, z));
+    }
+  } else return -6;   // binary_compressed (LZF) is not supported yet
+  cloud->width = (std::uint32_t)cloud->points.size(); cloud->height = 1;
+  return 0;
+}
+
+// IO.cpp:22-71 — coloured copy of the clustered points (points outside every cluster are not written)
+inline void saveColoredClusters(const std::string& fileoutpath_name, PCXYZPtr input_cloud,
+                                const std::vector<std::vector<int>>& clusters_points_idx) {
+  size_t total = 0;
+  for (auto& c : clusters_points_idx) total += c.size();
+  FILE* f = std::fopen(fileoutpath_name.c_str(), "wb");
+  if (!f) throw std::runtime_error("saveColoredClusters: cannot open " + fileoutpath_name);
+  std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\n"
+                  "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", total, total);
+  for (size_t c = 0; c < clusters_points_idx.size(); c++) {
+    std::uint32_t hsh = (std::uint32_t)c * 2654435761u;
+    std::uint32_t rgb = (((hsh >> 8) & 255u) << 16) | (((hsh >> 16) & 255u) << 8) | ((hsh >> 24) & 255u);
+    for (int p : clusters_points_idx[c]) {
+      float xyz[3] = {input_cloud->points[p].x, input_cloud->points[p].y, input_cloud->points[p].z};
+      std::fwrite(xyz, 4, 3, f);
+      std::fwrite(&rgb, 4, 1, f);
+    }
+  }
+  std::fclose(f);
+}

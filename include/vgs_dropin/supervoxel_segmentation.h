@@ -1,0 +1,141 @@
+// supervoxel_segmentation.h (drop-in) — pcl::SuperVoxelBasedSegmentation<PointT> with the reference's
+// public member names and call order (reference supervoxel_segmentation.h:85-421, 613, driven as in
+// test:138-160), forwarded to the C ABI of libvgs_b200.so in SVGS mode.
+//
+// The reference obtains its supervoxels from PCL's VCCS (pcl::SupervoxelClustering, SV.h:265-284 — third-party
+// code).  Here the per-point supervoxel labels are either supplied (setSupervoxelLabels: what
+// getLabeledCloud()/getMaxLabel() returned, SV.h:283-284) or, if none were supplied, made by the built-in
+// seed-grid stand-in (vgs_make_supervoxels_grid).  Everything downstream of the labels is the reference's
+// algorithm on the GPU.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../vgs_b200.h"
+#include "pcl_shim.h"
+
+namespace pcl {
+
+template <typename PointT>
+class SuperVoxelBasedSegmentation {
+ public:
+  typedef typename pcl::PointCloud<PointT>::ConstPtr PointCloudConstPtr;
+
+  explicit SuperVoxelBasedSegmentation(double input_resolution, int device = 0) : resolution_(input_resolution) {  // SV.h:85
+    vgs_config cfg{};
+    cfg.mode = VGS_MODE_SVGS;
+    cfg.device = device;
+    cfg.leaf_order = VGS_LEAF_DESCENDING;
+    if (vgs_create(&h_, &cfg) != VGS_OK) throw std::runtime_error(std::string("vgs_create: ") + vgs_last_error(nullptr));
+  }
+  ~SuperVoxelBasedSegmentation() { vgs_destroy(h_); }
+  SuperVoxelBasedSegmentation(const SuperVoxelBasedSegmentation&) = delete;
+  SuperVoxelBasedSegmentation& operator=(const SuperVoxelBasedSegmentation&) = delete;
+
+  void setInputCloud(const PointCloudConstPtr& cloud) { input_ = cloud; }            // PCL, test:139
+  void addPointsFromInputCloud() {                                                   // PCL, test:141
+    if (!input_ || input_->points.empty()) throw std::runtime_error("addPointsFromInputCloud: no input cloud");
+    ck(vgs_set_points(h_, &input_->points[0].x, (int64_t)input_->points.size(), (int)sizeof(PointT), 0));
+    ck(vgs_voxelize(h_, (float)resolution_));
+  }
+  void getBoundingBox(double& min_x, double& min_y, double& min_z, double& max_x, double& max_y, double& max_z) {
+    double b[6];
+    ck(vgs_get_bounding_box(h_, b));
+    min_x = b[0]; min_y = b[1]; min_z = b[2]; max_x = b[3]; max_y = b[4]; max_z = b[5];
+  }
+  int getCloudPointNum(PCXYZPtr input_data) {                                        // SV.h:101
+    points_num_ = (int)input_data->points.size();
+    points_cloud_ = input_data;
+    return points_num_;
+  }
+  int getVoxelNum() { int64_t v = 0; ck(vgs_voxel_count(h_, &v)); voxels_num_ = (int)v; return voxels_num_; }  // SV.h:111
+  int getSuperVoxelNum() { return supervoxels_num_; }                                // SV.h:118
+  int getClusterNum() { return clusters_num_; }                                      // SV.h:124
+  std::vector<std::vector<int>> getClusterIdx() { return clusters_point_idx_; }      // SV.h:130
+
+  void setVoxelSize(double input_resolution, int points_num_min) {                   // SV.h:143
+    voxel_resolution_ = (float)input_resolution; voxel_points_min_ = points_num_min;
+  }
+  void setSupervoxelSize(double input_resolution, int voxels_num_min, int points_num_min, int adjacency_num_min) {  // SV.h:150
+    seed_resolution_ = (float)input_resolution; supervoxel_voxel_min_ = voxels_num_min;
+    supervoxel_point_min_ = points_num_min; supervoxel_adjacency_min_ = adjacency_num_min;
+  }
+  void setGraphSize(double small_resolution, double large_resolution) {              // SV.h:159
+    graph_resolution_ = (float)large_resolution; adjacent_resolution_ = (float)small_resolution;
+  }
+  void setBoundingBox(double min_x, double min_y, double min_z, double max_x, double max_y, double max_z) {  // SV.h:166
+    double b[6] = {min_x, min_y, min_z, max_x, max_y, max_z};
+    ck(vgs_set_bounding_box(h_, b));
+  }
+  void setSupervoxelCentersCentroids() {}   // SV.h:178: its results are never consumed by the SVGS path
+
+  // extension: the labels pcl::SupervoxelClustering::getLabeledCloud() / getMaxLabel() gave (SV.h:283-284)
+  void setSupervoxelLabels(const std::vector<int>& label_per_point, int max_label) {
+    labels_ = label_per_point; max_label_ = max_label; have_labels_ = true;
+  }
+
+  // SV.h:362.  sig_a/sig_b/sig_l are the VCCS colour/spatial/normal importances (SV.h:366-369): they only
+  // matter inside the supervoxel generator.
+  void segmentSupervoxelCloudWithGraphModel(float /*sig_a*/, float /*sig_b*/, float /*sig_l*/, float cut_thred, float sig_p,
+                                            float sig_n, float sig_o, float sig_e, float sig_c, float sig_w) {
+    if (have_labels_) {
+      if ((int)labels_.size() != points_num_) throw std::runtime_error("setSupervoxelLabels: one label per input point expected");
+      ck(vgs_set_supervoxel_labels(h_, labels_.data(), max_label_, 0));
+    } else {
+      ck(vgs_make_supervoxels_grid(h_, seed_resolution_));
+    }
+    ck(vgs_compute_features(h_, supervoxel_point_min_));       // calcualteSupervoxelCloudAttributes SV.h:1238
+    int64_t nsv = 0;
+    ck(vgs_unit_count(h_, &nsv));
+    supervoxels_num_ = (int)nsv;
+    ck(vgs_find_adjacency(h_, graph_resolution_));             // findAllSupervoxelNeighbors SV.h:1477
+    vgs_sigmas s{sig_p, sig_n, sig_o, sig_e, sig_c, sig_w};
+    ck(vgs_segment(h_, &s, cut_thred, supervoxel_adjacency_min_));
+    // clusteringSupervoxels builds the point lists right away (SV.h:2109-2126), all clusters, no filter
+    int64_t nc = 0, nt = 0;
+    ck(vgs_get_clusters_csr(h_, 0, &nc, &nt, nullptr, nullptr));
+    std::vector<int64_t> off((size_t)nc + 1);
+    std::vector<int32_t> idx((size_t)(nt > 0 ? nt : 1));
+    ck(vgs_get_clusters_csr(h_, 0, &nc, &nt, off.data(), idx.data()));
+    clusters_point_idx_.assign((size_t)nc, std::vector<int>());
+    for (int64_t c = 0; c < nc; c++) clusters_point_idx_[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
+    clusters_num_ = (int)nc;
+  }
+
+  void drawColorMapofPointsinClusters(pcl::PointCloud<pcl::PointXYZRGB>::Ptr output_cloud) {   // SV.h:613
+    if (!output_cloud || !points_cloud_) return;
+    for (size_t c = 0; c < clusters_point_idx_.size(); c++) {
+      uint32_t hsh = (uint32_t)c * 2654435761u;
+      for (int p : clusters_point_idx_[c]) {
+        pcl::PointXYZRGB q;
+        q.x = points_cloud_->points[p].x; q.y = points_cloud_->points[p].y; q.z = points_cloud_->points[p].z;
+        q.r = (uint8_t)(hsh >> 8); q.g = (uint8_t)(hsh >> 16); q.b = (uint8_t)(hsh >> 24);
+        output_cloud->push_back(q);
+      }
+    }
+  }
+  std::vector<int> getPointLabels() {
+    std::vector<int> lab((size_t)points_num_);
+    ck(vgs_get_point_labels(h_, 0, lab.data(), 0));
+    return lab;
+  }
+  vgs_handle handle() { return h_; }
+
+ private:
+  void ck(vgs_status s) { if (s != VGS_OK) throw std::runtime_error(std::string("libvgs_b200: ") + vgs_last_error(h_)); }
+  vgs_handle h_ = nullptr;
+  double resolution_;
+  PointCloudConstPtr input_;
+  PCXYZPtr points_cloud_;
+  std::vector<int> labels_;
+  int max_label_ = 0;
+  bool have_labels_ = false;
+  int points_num_ = 0, voxels_num_ = 0, supervoxels_num_ = 0, clusters_num_ = 0;
+  int voxel_points_min_ = 0, supervoxel_voxel_min_ = 0, supervoxel_point_min_ = 0, supervoxel_adjacency_min_ = 0;
+  float voxel_resolution_ = 0, seed_resolution_ = 0, graph_resolution_ = 0, adjacent_resolution_ = 0;
+  std::vector<std::vector<int>> clusters_point_idx_;
+};
+
+}  // namespace pcl

@@ -55,7 +55,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
              CONN1_IDX=(16, np.int32), ATTACH=(17, np.int32), UNIT_ROOT=(19, np.int32))
 
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
-            "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_unit_count",
+            "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
             "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get"]
 
@@ -82,6 +82,7 @@ def load():
         L.vgs_voxel_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.vgs_get_voxel_centers.argtypes = [C.c_void_p, C.c_void_p]
         L.vgs_set_supervoxel_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
+        L.vgs_make_supervoxels_grid.argtypes = [C.c_void_p, C.c_float]
         L.vgs_unit_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.vgs_compute_features.argtypes = [C.c_void_p, C.c_int]
         L.vgs_find_adjacency.argtypes = [C.c_void_p, C.c_float]
@@ -150,6 +151,9 @@ class Handle:
     def set_supervoxel_labels(self, labels: np.ndarray, max_label: int = 0):
         labels = np.ascontiguousarray(labels, dtype=np.int32)
         self._ck(self.L.vgs_set_supervoxel_labels(self.h, labels.ctypes.data, max_label, 0))
+
+    def make_supervoxels_grid(self, seed_size):
+        self._ck(self.L.vgs_make_supervoxels_grid(self.h, seed_size))
 
     # --- stages ---
     def voxelize(self, voxel_size):

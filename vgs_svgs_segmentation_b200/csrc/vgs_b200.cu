@@ -70,6 +70,7 @@ struct vgs_context {
   // units
   int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
   int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
+  bool units_external = false;   // SVGS units made by vgs_make_supervoxels_grid (not from labels)
   bool have_units = false, have_features = false, have_adj = false, have_segments = false, have_geometry = false;
   float bb_f[6] = {0, 0, 0, 0, 0, 0};   // float-narrowed bounding box members (VS.h:1123)
   int64_t n_used = 0, n_adj = 0, n_pairs = 0, max_n = 0, n_singles = 0, n_attached = 0, closest_rounds = 0;
@@ -381,6 +382,7 @@ vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* labels, int32_
     h->d_labels = h->labels_own.as<int32_t>();
   }
   h->max_label = max_label;
+  h->units_external = false;
   h->have_units = h->have_features = h->have_adj = h->have_segments = false;
   return VGS_OK;
 }
@@ -394,6 +396,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   h->voxel_size = voxel_size;
   h->voxelized = false;
   h->have_units = h->have_features = h->have_adj = h->have_segments = false;   // the sort buffers are shared
+  h->units_external = false;
   CK(h->small.reserve(4096));
 
   // ---- stage 0: PCL dynamic bounding box (origin) ----
@@ -513,6 +516,37 @@ static vgs_status build_svgs_units(vgs_handle h) {
   return VGS_OK;
 }
 
+vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
+  if (!h) return VGS_ERR_INVALID;
+  if (h->mode != VGS_MODE_SVGS) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_grid: handle is not in SVGS mode");
+  if (!h->voxelized) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_grid: call vgs_voxelize first (the grid is anchored at the octree origin)");
+  if (!(seed_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_make_supervoxels_grid: seed_size must be > 0");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
+  CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
+  LAUNCH(k_seed_cell_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->box.mn[0], h->box.mn[1], h->box.mn[2],
+         (double)seed_size, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>());
+  uint64_t* ks; uint32_t* vs;
+  vgs_status s = radix_sort(h, n, 64, &ks, &vs);
+  if (s) return s;
+  int64_t nunits = 0;
+  s = build_units(h, ks, n, &nunits);
+  if (s) return s;
+  uint64_t lastkey = 0; uint32_t laststart = 0;
+  CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int64_t nval = n;
+  if (lastkey >> 63) { nval = laststart; nunits--; }
+  h->d_keys = ks; h->d_perm = vs;
+  h->nu = nunits; h->n_valid = nval;
+  h->have_units = true;
+  h->units_external = true;
+  h->have_features = h->have_adj = h->have_segments = false;
+  return VGS_OK;
+}
+
 vgs_status vgs_unit_count(vgs_handle h, int64_t* nunits) {
   if (!h || !nunits) return VGS_ERR_INVALID;
   if (!h->have_units) return h->fail(VGS_ERR_STATE, "vgs_unit_count: units not built yet");
@@ -524,7 +558,7 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   if (!h) return VGS_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   StageTimer t(h, &h->tm.features_ms, 3);
-  if (h->mode == VGS_MODE_SVGS) {
+  if (h->mode == VGS_MODE_SVGS && !(h->units_external && h->have_units)) {
     vgs_status s = build_svgs_units(h);
     if (s) return s;
   }

@@ -96,6 +96,21 @@ __global__ void __launch_bounds__(256) k_label_keys(const int32_t* __restrict__ 
   keys[i] = ok ? (uint64_t)(uint32_t)l : (1ull << 32);
 }
 
+// Built-in stand-in for the supervoxel generator (the reference calls PCL's VCCS, SV.h:265-284, which
+// is third-party code): one supervoxel per occupied cell of a seed-resolution grid anchored at the
+// octree origin.  Deterministic; NOT VCCS.
+__global__ void __launch_bounds__(256) k_seed_cell_keys(const float* __restrict__ xyz, int stride, int64_t n, double ox, double oy, double oz,
+                                                      double seed, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + i * stride;
+  float x = p[0], y = p[1], z = p[2];
+  vals[i] = (uint32_t)i;
+  if (!finite3(x, y, z)) { keys[i] = 1ull << 63; return; }
+  uint32_t cx = (uint32_t)(((double)x - ox) / seed), cy = (uint32_t)(((double)y - oy) / seed), cz = (uint32_t)(((double)z - oz) / seed);
+  keys[i] = morton_encode(cx & 0x1fffffu, cy & 0x1fffffu, cz & 0x1fffffu);
+}
+
 // ---- stage 1b: segment heads of the sorted keys ----
 __global__ void __launch_bounds__(256) k_head_flags(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
