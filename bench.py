@@ -141,6 +141,9 @@ def main():
     ap.add_argument("--ref-points", type=int, default=400_000)
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "partitioned"],
+                    help="N>1: 'tiles' = one independent site tile per rank (weak scaling, no exchange); "
+                         "'partitioned' = ONE scene, local-graph stage split over ranks + NCCL exchange (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -164,7 +167,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    pts = make_scene(args.points, rank)
+    partitioned = args.mode == "partitioned" and world > 1
+    pts = make_scene(args.points, 0 if partitioned else rank)
     n = pts.shape[0]
     host_xyz = torch.from_numpy(pts).pin_memory()
     host_lab = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -180,13 +184,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from vgs_svgs_segmentation_b200.multigpu import segment_partitioned
+
     def step_resident():
         h.set_points_device(dev_xyz.data_ptr(), n, 12)
-        h.run(params, dev_lab.data_ptr(), on_device=True)
+        if partitioned:
+            segment_partitioned(h, params, rank, world, dev_lab.data_ptr(), on_device=True)
+        else:
+            h.run(params, dev_lab.data_ptr(), on_device=True)
 
     def step_e2e():
         h.set_points_host_ptr(host_xyz.data_ptr(), n, 12)
-        h.run(params, host_lab.numpy(), on_device=False)
+        if partitioned:
+            segment_partitioned(h, params, rank, world, host_lab.numpy(), on_device=False)
+        else:
+            h.run(params, host_lab.numpy(), on_device=False)
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
@@ -237,7 +249,7 @@ def main():
         ms, ms_e2e = float(t[0]), float(t[1])
         tot = torch.tensor([n], device="cuda", dtype=torch.int64)
         dist.all_reduce(tot)
-        total_points = int(tot[0])
+        total_points = n if partitioned else int(tot[0])
     else:
         total_points = n
 
@@ -261,11 +273,13 @@ def main():
         out = {
             "metric": "points/sec segmented end-to-end", "value": total_points / (ms / 1e3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"VGS, synthetic construction-site scene {n} points per GPU (BASELINE.json configs[2]), "
+            "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": (f"VGS, ONE synthetic construction-site scene of {n} points, local-graph stage partitioned over "
+                                    f"{world} GPUs + NCCL exchange of connect lists, " if partitioned else
+                                    f"VGS, synthetic construction-site scene {n} points per GPU (BASELINE.json configs[2]), ") +
                                    "Task_File_VGS.txt parameters (voxel 0.15, graph 0.5, sigma 0.2 x5, sig_w 2, cut 0.3, "
                                    "points_min 10, adjacency_min 3, voxels_min 3)",
-                       "points_per_gpu": n, "l2": "512 MB buffer written between timed steps (L2 flush); per-step working set > 1 GB",
+                       "multi_gpu_mode": args.mode if world > 1 else "single", "points_per_gpu": n, "l2": "512 MB buffer written between timed steps (L2 flush); per-step working set > 1 GB",
                        "tiles": world, "voxels": V, "used_voxels": counts["n_used"], "adjacency_entries": E,
                        "pair_weights": counts["n_pairs"], "clusters": counts["n_clusters_exported"]},
             "e2e": {"value": total_points / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 12 * n,

@@ -70,6 +70,7 @@ struct vgs_context {
   // units
   int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
   int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
+  bool have_graph = false;       // connect lists of stage 4+5a complete (own range computed or imported)
   bool units_external = false;   // SVGS units made by vgs_make_supervoxels_grid (not from labels)
   bool have_units = false, have_features = false, have_adj = false, have_segments = false, have_geometry = false;
   float bb_f[6] = {0, 0, 0, 0, 0, 0};   // float-narrowed bounding box members (VS.h:1123)
@@ -89,7 +90,7 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  DBuf stencil2, pair_table;
+  DBuf stencil2, pair_table, need_rows;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
 
@@ -341,7 +342,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -721,12 +722,78 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   return VGS_OK;
 }
 
+static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first, int64_t last);
+static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min);
+
 vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   if (!h || !sg) return VGS_ERR_INVALID;
   if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_segment: call vgs_find_adjacency first");
+  vgs_status s = segment_graph(h, sg, cut_thred, 0, h->nu);
+  if (s) return s;
+  return segment_finish(h, sg, cut_thred, adjacency_min);
+}
+
+vgs_status vgs_segment_partial(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first_unit, int64_t last_unit) {
+  if (!h || !sg) return VGS_ERR_INVALID;
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_segment_partial: call vgs_find_adjacency first");
+  if (first_unit < 0 || last_unit > h->nu || first_unit > last_unit) return h->fail(VGS_ERR_INVALID, "vgs_segment_partial: bad unit range");
+  return segment_graph(h, sg, cut_thred, first_unit, last_unit);
+}
+
+vgs_status vgs_segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
+  if (!h || !sg) return VGS_ERR_INVALID;
+  if (!h->have_graph) return h->fail(VGS_ERR_STATE, "vgs_segment_finish: call vgs_segment_partial (and import the other ranges) first");
+  return segment_finish(h, sg, cut_thred, adjacency_min);
+}
+
+vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, int64_t* e_first, int64_t* e_last) {
+  if (!h || !e_first || !e_last) return VGS_ERR_INVALID;
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_adj_range: call vgs_find_adjacency first");
+  if (first_unit < 0 || last_unit > h->nu || first_unit > last_unit) return h->fail(VGS_ERR_INVALID, "vgs_adj_range: bad unit range");
+  CK(cudaSetDevice(h->device));
+  uint32_t a = 0, b = 0;
+  CK(cudaMemcpyAsync(&a, h->adj_off.as<uint32_t>() + first_unit, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&b, h->adj_off.as<uint32_t>() + last_unit, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *e_first = a; *e_last = b;
+  return VGS_OK;
+}
+
+static vgs_status connect_copy(vgs_handle h, int64_t first, int64_t last, int32_t* cnt_dev, int32_t* idx_dev, bool to_caller) {
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "connect lists: call vgs_find_adjacency first");
+  if (first < 0 || last > h->nu || first > last || !cnt_dev || !idx_dev) return h->fail(VGS_ERR_INVALID, "connect lists: bad range or buffer");
+  CK(cudaSetDevice(h->device));
+  int64_t e0, e1;
+  vgs_status s = vgs_adj_range(h, first, last, &e0, &e1);
+  if (s) return s;
+  const size_t E = (size_t)h->n_adj;
+  CK(h->conn0_cnt.reserve((size_t)h->nu * 4)); CK(h->conn0_idx.reserve(E * 4 + 16));
+  void* c = h->conn0_cnt.as<uint32_t>() + first; void* i = h->conn0_idx.as<int32_t>() + e0;
+  if (to_caller) {
+    CK(cudaMemcpyAsync(cnt_dev, c, (size_t)(last - first) * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(idx_dev, i, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    CK(cudaMemcpyAsync(c, cnt_dev, (size_t)(last - first) * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(i, idx_dev, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
+    h->have_graph = true;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return VGS_OK;
+}
+vgs_status vgs_export_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, int32_t* cnt_dev, int32_t* idx_dev) {
+  if (!h) return VGS_ERR_INVALID;
+  return connect_copy(h, first_unit, last_unit, cnt_dev, idx_dev, true);
+}
+vgs_status vgs_import_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, const int32_t* cnt_dev, const int32_t* idx_dev) {
+  if (!h) return VGS_ERR_INVALID;
+  return connect_copy(h, first_unit, last_unit, const_cast<int32_t*>(cnt_dev), const_cast<int32_t*>(idx_dev), false);
+}
+
+static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first, int64_t last) {
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
   h->have_segments = false;
+  h->have_graph = false;
   h->have_cluster_stats = false;
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
@@ -746,9 +813,16 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
     CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));
     LAUNCH(k_wempty, 1, 1, 0, gp.pp, d_wempty);
-    LAUNCH(k_bin_classes, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
-           h->rec.as<float>(), nu, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(), d_maxn,
-           h->class_list.as<uint32_t>(), d_stats);
+    const bool partial = !(first == 0 && last == nu);
+    uint8_t* d_need = nullptr;
+    if (partial) {   // pair-cache rows this rank's local graphs will read
+      CK(h->need_rows.reserve((size_t)nu + 16));
+      d_need = h->need_rows.as<uint8_t>();
+      CK(cudaMemsetAsync(d_need, 0, (size_t)nu, h->stream));
+    }
+    LAUNCH(k_bin_classes, (unsigned)cdiv((last - first) * 32 + 1, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+           h->rec.as<float>(), nu, first, last, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
+           d_maxn, h->class_list.as<uint32_t>(), d_stats, d_need);
     uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
     unsigned long long stats[3];
     CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
@@ -788,7 +862,7 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
         StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
         LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
                h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
-               h->pair_table.as<float2>(), half);
+               h->pair_table.as<float2>(), half, d_need);
         tpc.stop();
         cached = true;
       }
@@ -811,6 +885,19 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int 
     }
     t.stop();
   }
+  h->have_graph = true;
+  return VGS_OK;
+}
+
+static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
+  CK(cudaSetDevice(h->device));
+  const int64_t nu = h->nu;
+  GraphParams gp;
+  gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
+  gp.cut = cut_thred;
+  const size_t E = (size_t)h->n_adj;
+  CK(h->conn1_cnt.reserve((size_t)nu * 4)); CK(h->conn1_idx.reserve(E * 4 + 16));
+  CK(h->attach.reserve((size_t)nu * 4)); CK(h->parent.reserve((size_t)nu * 4)); CK(h->root.reserve((size_t)nu * 4));
   // ---- stage 5b: mutual filter ----
   {
     StageTimer t(h, &h->tm.mutual_ms, 6);

@@ -338,13 +338,14 @@ __global__ void k_wempty(PairParams pp, float* __restrict__ out) {
 //      neighbours; pairs with an unused unit are enumerated only if their constant weight could
 //      merge (w_empty > cut bound), which never happens with the reference's parameter sets. ----
 __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
-                                                   const float* __restrict__ rec, int64_t nu, float cut, int svgs,
-                                                   const float* __restrict__ wempty, uint32_t* __restrict__ class_count,
+                                                   const float* __restrict__ rec, int64_t nu, int64_t first, int64_t last, float cut,
+                                                   int svgs, const float* __restrict__ wempty, uint32_t* __restrict__ class_count,
                                                    uint32_t* __restrict__ class_maxn, uint32_t* __restrict__ class_list,
-                                                   unsigned long long* __restrict__ stats /* [0]=sum n(n-1) [1]=max n [2]=overflow */) {
+                                                   unsigned long long* __restrict__ stats /* [0]=sum n(n-1) [1]=max n [2]=overflow */,
+                                                   uint8_t* __restrict__ need_rows) {
   const int lane = threadIdx.x & 31;
-  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (u >= nu) return;
+  const int64_t u = first + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (u >= last) return;
   if (!(f2i(rec[u * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
   const uint32_t off = adj_off[u];
   const int n = (int)(adj_off[u + 1] - off);
@@ -352,7 +353,11 @@ __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict_
   for (int b = 0; b < n; b += 32) {
     const int e = b + lane;
     bool us = false;
-    if (e < n) us = (f2i(__ldg(rec + (int64_t)adj_idx[off + e] * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+    if (e < n) {
+      const int64_t g = adj_idx[off + e];
+      us = (f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+      if (need_rows && us) need_rows[g] = 1;
+    }
     used += __popc(__ballot_sync(0xffffffffu, us));
   }
   if (lane != 0) return;
@@ -377,7 +382,8 @@ __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict_
 __global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv,
                                                   int depth, const int4* __restrict__ st2, int nst2,
                                                   const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
-                                                  uint64_t mask, PairParams pp, float2* __restrict__ table, int half) {
+                                                  uint64_t mask, PairParams pp, float2* __restrict__ table, int half,
+                                                  const uint8_t* __restrict__ need_rows) {
   __shared__ int pend_b[4][64];
   __shared__ int pend_i[4][64];
   __shared__ float s_ra[4][REC_FLOATS];
@@ -385,6 +391,7 @@ __global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__
   const int64_t v = (int64_t)blockIdx.x * 4 + w;
   if (v >= nv) return;
   if (!(f2i(rec[v * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
+  if (need_rows && !need_rows[v]) return;   // multi-GPU: only rows read by this rank's local graphs
   if (lane < REC_FLOATS) s_ra[w][lane] = rec[v * REC_FLOATS + lane];
   __syncwarp();
   const uint32_t kx = key3[3 * v], ky = key3[3 * v + 1], kz = key3[3 * v + 2];
