@@ -42,7 +42,8 @@ enum { VGS_LEAF_DESCENDING = 0 /* PCL 1.8.1 */, VGS_LEAF_ASCENDING = 1 /* PCL >=
 typedef struct vgs_config {
   int32_t mode;        /* VGS_MODE_VGS | VGS_MODE_SVGS */
   int32_t device;      /* CUDA device ordinal */
-  void* stream;        /* cudaStream_t to launch on (NULL = the handle creates its own) */
+  void* stream;        /* cudaStream_t to launch on; NULL = the handle creates its own non-blocking stream
+                          (pass cudaStreamLegacy to run on the legacy default stream) */
   int32_t leaf_order;  /* VGS_LEAF_* : octree leaf-iterator direction that defines voxel ids */
   int32_t reserved[5];
 } vgs_config;

@@ -223,3 +223,41 @@ def test_svgs_drops_max_label_and_unlabelled(built_lib):
     r = oracle.run(xyz, labels=labels, max_label=ml, mode=1, math=1)
     _compare_svgs(xyz, labels, g, r)
     assert np.all(g["point_label"][labels == 0] == -1) and np.all(g["point_label"][labels == ml] == -1)
+
+
+def test_full_size_properties_10m(built_lib):
+    """BASELINE.json configs[2] at full size (10 M points): the oracle would need minutes, so the run is
+    checked through size-independent properties: canonical labels (label = smallest point index of the
+    cluster and that point carries it), every exported cluster has more than voxels_min voxels, cluster
+    counts are consistent, a second run is bit-identical, and unlabelled points belong to dropped clusters."""
+    from vgs_svgs_segmentation_b200 import capi
+    xyz = scenes.construction_site(10_000_000, seed=1, extent=70.0)
+    h = capi.Handle()
+    h.set_points(xyz)
+    p = capi.make_params(**VGS_PARAMS)
+    lab = h.run(p).copy()
+    c = h.counts()
+    root = h.blob("UNIT_ROOT")
+    pu = h.blob("POINT_UNIT")
+    n_all, n_exp = h.cluster_count(VGS_PARAMS["voxels_min"])
+    assert c["n_points"] == 10_000_000 and c["n_voxels"] == len(root) and n_all == len(np.unique(root))
+    labelled = lab >= 0
+    ids = np.unique(lab[labelled])
+    assert len(ids) == n_exp
+    assert np.array_equal(lab[ids], ids)                       # the smallest point of a cluster carries its own index
+    first = np.full(lab.max() + 1, -1, np.int64)
+    idx = np.flatnonzero(labelled)
+    first[lab[idx][::-1]] = idx[::-1]                          # first occurrence of each label
+    assert np.array_equal(first[ids], ids)                     # ... and no smaller point has that label
+    # label is a function of the voxel's root, and exported roots have > voxels_min voxels
+    r_of_point = root[pu]
+    sizes = np.bincount(root, minlength=len(root))
+    assert np.all(sizes[r_of_point[labelled]] > VGS_PARAMS["voxels_min"])
+    assert np.all(sizes[r_of_point[~labelled]] <= VGS_PARAMS["voxels_min"])
+    lab_of_root = np.full(len(root), -2, np.int64)
+    lab_of_root[r_of_point] = lab
+    assert np.array_equal(lab_of_root[r_of_point], lab)
+    h.set_points(xyz)
+    lab2 = h.run(p)
+    h.close()
+    assert np.array_equal(lab, lab2)

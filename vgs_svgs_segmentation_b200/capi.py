@@ -116,6 +116,8 @@ class Handle:
     def __init__(self, mode=VGS_MODE_VGS, device=0, stream=None, leaf_order=0):
         self.L = load()
         self.h = C.c_void_p()
+        if stream == 0:
+            stream = 1   # torch's default stream is CUDA's legacy default stream: pass cudaStreamLegacy, not NULL (= "own stream")
         cfg = Config(mode, device, stream, leaf_order)
         st = self.L.vgs_create(C.byref(self.h), C.byref(cfg))
         if st != 0:
