@@ -870,14 +870,16 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     for (int c = 0; c < N_CLASSES; c++) {
       if (!cc[c]) continue;
       const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
-      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (LG_BINS + 1) * 4 + 64;
+      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (2 * LG_BINS + 2) * 4 + 64;
+      const int bucketed = (smem + (size_t)mcap * 2 <= 220 * 1024) ? 1 : 0;   // bin-ordered pool index if it fits
+      if (bucketed) smem += (size_t)mcap * 2;
       const uint32_t* list = h->class_list.as<uint32_t>() + (size_t)c * nu;
 #define LG(TT, CC)                                                                                                  \
   do {                                                                                                              \
     auto kfn = k_local_graph2<TT, CC>;                                                                              \
     LAUNCH(kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),                  \
            h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2,        \
-           d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
+           d_wempty, bucketed, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
   } while (0)
       if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else LG(256, true); }
       else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else LG(256, false); }

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
                                                         const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
                                                         const float* __restrict__ rec, const uint32_t* __restrict__ key3,
                                                         GraphParams gp, int ncap, int mcap, const float2* __restrict__ table,
-                                                        int half, int r2, const float* __restrict__ wempty,
+                                                        int half, int r2, const float* __restrict__ wempty, int bucketed,
                                                         uint32_t* __restrict__ conn_cnt, int32_t* __restrict__ conn_idx) {
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int AUX = CACHED ? 4 : REC_PAD;
@@ -471,12 +471,14 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   int* s_gid = reinterpret_cast<int*>(s_int + ncap);                             // ncap
   int* s_aux = s_gid + ncap;                                                     // AUX*ncap: (kx,ky,kz,flags) | records
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_aux + (size_t)AUX * ncap);    // LG_BINS+1
-  unsigned short* A_f = reinterpret_cast<unsigned short*>(s_hist + LG_BINS + 1); // mcap: flat index col*n+row
+  unsigned short* A_f = reinterpret_cast<unsigned short*>(s_hist + 2 * LG_BINS + 2); // mcap: packed (col << 8) | row
   unsigned short* C_f = A_f + mcap;                                              // LG_CS
   unsigned short* s_seg = C_f + LG_CS;                                           // ncap
   unsigned short* s_size = s_seg + ncap;                                         // ncap
   unsigned short* s_ul = s_size + ncap;                                          // ncap: local ids of the used vertices
-  __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot, s_nu, s_c0b;
+  unsigned short* B_i = s_ul + ncap;                                             // bucketed ? mcap : 0: pool indices ordered by bin
+  unsigned* s_cur = s_hist + LG_BINS + 1;                                        // LG_BINS scatter cursors (layout: hist | cursors)
+  __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot, s_nu, s_c0b, s_before;
   __shared__ float s_minthr, s_wempty, s_ratio;
 
   const int tid = threadIdx.x;
@@ -530,6 +532,13 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   const bool all_pairs = s_wempty > lb;
   const int nv = all_pairs ? n : s_nu;
   const int npairs = nv * (nv - 1) / 2;
+  if (!all_pairs) {
+    // vertices that are not enumerated have no entry at all: they stay singletons for ever and must not
+    // keep the termination tests alive (segment count, smallest live threshold)
+    for (int i = tid; i < n; i += THREADS)
+      if (!((CACHED ? s_aux[4 * i + 3] : s_aux[i * REC_PAD + REC_FLAGS]) & F_USED)) s_size[i] = 0;
+    if (tid == 0) { s_nseg = nv; if (nv <= 1) s_done = 1; }
+  }
   for (int p = tid; p < npairs; p += THREADS) {
     int r = p / (nv - 1), c = p - r * (nv - 1);
     int a, b;
@@ -584,6 +593,15 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
     for (int q = 0; q < PER; q++) s_hist[tid * PER + q] = base + loc[q];
   }
   __syncthreads();
+  if (bucketed) {   // order the pool indices by bin once, so a chunk is a contiguous index range
+    for (int b = tid; b < LG_BINS; b += THREADS) s_cur[b] = b > 0 ? s_hist[b - 1] : 0u;
+    __syncthreads();
+    for (int i = tid; i < m; i += THREADS) {
+      const int bin = min(LG_BINS - 1, (int)((1.0f - A_w[i]) * scale));
+      B_i[atomicAdd(&s_cur[bin], 1u)] = (unsigned short)i;
+    }
+    __syncthreads();
+  }
   int c0 = 0;
   while (c0 < LG_BINS && !s_done && m > 0) {
     if (tid == 0) {
@@ -601,7 +619,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
         if (c1 > LG_BINS) c1 = LG_BINS;
         if (c1 >= 1 && c1 <= LG_BINS && (int)s_hist[c1 - 1] == before) c1 = LG_BINS;   // nothing left
       }
-      s_c1 = c1; s_cnt = 0; s_tot = (c1 >= 1 ? (int)s_hist[c1 - 1] : 0) - before;
+      s_c1 = c1; s_cnt = 0; s_tot = (c1 >= 1 ? (int)s_hist[c1 - 1] : 0) - before; s_before = before;
       s_c0b = (s_tot == 0) ? LG_BINS : c0;
     }
     __syncthreads();
@@ -613,14 +631,26 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
     int kept = 0;
     if (!single_big) {
       // gather the chunk's still-useful entries
-      for (int i = tid; i < m; i += THREADS) {
-        const float w = A_w[i];
-        const int bin = min(LG_BINS - 1, (int)((1.0f - w) * scale));
-        if (bin >= c0 && bin < c1) {
+      if (bucketed) {
+        const int xs = s_before, xe = xs + L;
+        for (int x = xs + tid; x < xe; x += THREADS) {
+          const int i = B_i[x];
           const unsigned short f = A_f[i];
           if (s_seg[f >> 8] != s_seg[f & 255]) {
             int s = atomicAdd(&s_cnt, 1);
-            if (s < LG_CS) { C_w[s] = w; C_f[s] = f; }
+            if (s < LG_CS) { C_w[s] = A_w[i]; C_f[s] = f; }
+          }
+        }
+      } else {
+        for (int i = tid; i < m; i += THREADS) {
+          const float w = A_w[i];
+          const int bin = min(LG_BINS - 1, (int)((1.0f - w) * scale));
+          if (bin >= c0 && bin < c1) {
+            const unsigned short f = A_f[i];
+            if (s_seg[f >> 8] != s_seg[f & 255]) {
+              int s = atomicAdd(&s_cnt, 1);
+              if (s < LG_CS) { C_w[s] = w; C_f[s] = f; }
+            }
           }
         }
       }
