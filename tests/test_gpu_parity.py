@@ -261,3 +261,13 @@ def test_full_size_properties_10m(built_lib):
     lab2 = h.run(p)
     h.close()
     assert np.array_equal(lab, lab2)
+
+
+def test_vgs_cta_kernel_path(built_lib, monkeypatch):
+    """VGS_B200_NO_WARP_KERNEL=1: the cached CTA-per-unit kernel (also the fallback of the warp-per-unit
+    kernel) must give the oracle's lists and labels too."""
+    monkeypatch.setenv("VGS_B200_NO_WARP_KERNEL", "1")
+    xyz = _scene("site")
+    g = gpu_stages(xyz)
+    r = oracle.run(xyz, math=1)
+    _compare_vgs(xyz, g, r)

@@ -90,7 +90,9 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  DBuf stencil2, pair_table, need_rows;
+  DBuf stencil2, pair_table, need_rows, fallback;
+  int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
+  int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
 
@@ -307,6 +309,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
+  if (const char* e_nw = getenv("VGS_B200_NO_WARP_KERNEL")) h->use_warp_kernel = (e_nw[0] == '1') ? 0 : 1;
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
   {
     auto optin = [&](const void* fn, size_t want_total) -> cudaError_t {
@@ -322,6 +325,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<64, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, false>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph_warp, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
@@ -342,7 +346,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -867,9 +871,29 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         cached = true;
       }
     }
+    // warp-per-unit kernel for the cached VGS path; units it cannot handle come back in a fallback list
+    uint32_t* d_fb_count = h->class_count.as<uint32_t>() + 48;
+    const bool use_warp = cached && h->use_warp_kernel;
+    unsigned long long* d_dbg = nullptr;
+    if (getenv("VGS_B200_DEBUG_COUNTERS")) {
+      d_dbg = h->small.as<unsigned long long>() + 64;
+      CK(cudaMemsetAsync(d_dbg, 0, 64, h->stream));
+    }
+    if (use_warp) CK(h->fallback.reserve((size_t)nu * 4 + 16));
+    uint32_t max_n_all = 0;
+    for (int c = 0; c < N_CLASSES; c++) max_n_all = std::max(max_n_all, cc[c] ? cmaxn[c] : 0u);
     for (int c = 0; c < N_CLASSES; c++) {
       if (!cc[c]) continue;
       const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
+      if (use_warp && CLASS_N_HOST[c] <= 128) {
+        const size_t slice = lw_slice_bytes(ncap, mcap);
+        const uint32_t* wlist = h->class_list.as<uint32_t>() + (size_t)c * nu;
+        LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
+               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->rec.as<float>(), h->key3.as<uint32_t>(), cut_thred, ncap,
+               mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
+               h->fallback.as<uint32_t>(), d_fb_count, d_dbg);
+        continue;
+      }
       size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (2 * LG_BINS + 2) * 4 + 64;
       const int bucketed = (smem + (size_t)mcap * 2 <= 220 * 1024) ? 1 : 0;   // bin-ordered pool index if it fits
       if (bucketed) smem += (size_t)mcap * 2;
@@ -884,6 +908,29 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else LG(256, true); }
       else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else LG(256, false); }
 #undef LG
+    }
+    if (d_dbg) {
+      unsigned long long dd[8];
+      CK(cudaMemcpyAsync(dd, d_dbg, 64, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      fprintf(stderr, "[vgs debug] units %llu chunks %llu (%.2f/unit) scanned %llu (%.1f/unit) kept %llu (%.1f/unit) m/unit %.1f final_nseg/unit %.2f nv/unit %.1f\n",
+              dd[3], dd[0], (double)dd[0] / (double)std::max(1ull, dd[3]), dd[1], (double)dd[1] / (double)std::max(1ull, dd[3]), dd[2],
+              (double)dd[2] / (double)std::max(1ull, dd[3]), (double)dd[4] / (double)std::max(1ull, dd[3]),
+              (double)dd[5] / (double)std::max(1ull, dd[3]), (double)dd[6] / (double)std::max(1ull, dd[3]));
+    }
+    if (use_warp) {   // units the warp kernel handed back: general CTA kernel sized for the largest neighbourhood
+      uint32_t nfb = 0;
+      CK(cudaMemcpyAsync(&nfb, d_fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      h->n_fallback = nfb;
+      if (nfb) {
+        const int ncap = (int)((max_n_all + 3u) & ~3u), mcap = CLASS_N_HOST[N_CLASSES - 1] * (CLASS_N_HOST[N_CLASSES - 1] - 1);
+        size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + 16) + (2 * LG_BINS + 2) * 4 + 64;
+        auto kfn = k_local_graph2<256, true>;
+        LAUNCH(kfn, nfb, 256, smem, h->fallback.as<uint32_t>(), nfb, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+               h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2, d_wempty, 0,
+               h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());
+      }
     }
     t.stop();
   }
@@ -1061,7 +1108,7 @@ vgs_status vgs_get_counts(vgs_handle h, vgs_counts* out) {
   out->n_points = h->n; out->n_finite = h->n_finite; out->n_voxels = h->n_voxels; out->n_units = h->nu;
   out->n_used = h->n_used; out->n_adjacency = h->n_adj; out->n_pairs = h->n_pairs; out->n_singles = h->n_singles;
   out->n_clusters_all = h->n_clusters_all; out->n_clusters_exported = h->n_clusters_exp; out->octree_depth = h->depth;
-  out->closest_rounds = h->closest_rounds; out->max_neighbours = h->max_n;
+  out->closest_rounds = h->closest_rounds; out->max_neighbours = h->max_n; out->reserved[0] = h->n_fallback;
   return VGS_OK;
 }
 

@@ -790,6 +790,301 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   }
 }
 
+// ---- stage 4+5a, warp-per-unit variant (VGS with the pair cache): same algorithm and results as
+//      k_local_graph2, restructured so that nothing waits at a block barrier (the ncu profile of the CTA
+//      version showed 37 % of all stall samples at the barrier behind warp 0's serial merge) and so that a
+//      unit needs ~8 KB of shared memory instead of 30-40 KB: the weights are NOT kept — pass 0 reads every
+//      pair once from the offset-indexed table and stores only its histogram bin (1 byte per directed
+//      entry); each chunk then re-reads just the entries of its bin range.  Units whose weight
+//      distribution defeats this (one bin larger than the staging buffer, or empty-pair weights that can
+//      merge) are appended to `fallback` and handled by the CTA kernel. ----
+constexpr int LW_CS = 256;      // staging capacity (entries) per warp
+constexpr int LW_CH = 28;       // target number of USEFUL entries per chunk (one per lane: register sort)
+constexpr int LW_WARPS = 4;     // units per CTA
+constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
+__host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 256 * 4 + 16 + (size_t)LW_CS * 4 + (size_t)ncap * 3 + (size_t)mcap + 16;
+  return (b + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
+                                                                  const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
+                                                                  const float* __restrict__ rec, const uint32_t* __restrict__ key3,
+                                                                  float k, int ncap, int mcap, const float2* __restrict__ table, int half,
+                                                                  int r2, const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
+                                                                  int32_t* __restrict__ conn_idx, uint32_t* __restrict__ fallback,
+                                                                  uint32_t* __restrict__ fallback_count,
+                                                                  unsigned long long* __restrict__ dbg) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const uint32_t li = blockIdx.x * LW_WARPS + wq;
+  if (li >= nlist) return;
+  unsigned char* base = smraw + (size_t)wq * lw_slice_bytes(ncap, mcap);
+  float* C_w = reinterpret_cast<float*>(base);                       // LW_CS
+  float* s_int = C_w + LW_CS;                                        // ncap
+  int* s_gid = reinterpret_cast<int*>(s_int + ncap);                 // ncap
+  int* s_key = s_gid + ncap;                                         // ncap: (dx+64) | (dy+64)<<8 | (dz+64)<<16 relative to the centre
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256
+  unsigned* s_scal = s_hist + 256;                                   // 4 scalars
+  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_scal + 4);   // LW_CS
+  unsigned short* C_e = C_f + LW_CS;                                 // LW_CS: entry ids of the chunk
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(C_e + LW_CS);   // ncap
+  unsigned char* s_size = s_seg + ncap;                              // ncap
+  unsigned char* s_ul = s_size + ncap;                               // ncap: local ids of the used vertices
+  unsigned char* bins = s_ul + ncap;                                 // mcap (+pad): histogram bin of every directed entry
+  const uint32_t lt = (1u << lane) - 1u;
+
+  const uint32_t u = list[li];
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off);
+  const int cx = (int)key3[3 * (int64_t)u], cy = (int)key3[3 * (int64_t)u + 1], cz = (int)key3[3 * (int64_t)u + 2];
+  for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
+  int nv = 0;
+  for (int b0 = 0; b0 < n; b0 += 32) {   // vertex table + ordered list of the used vertices
+    const int i = b0 + lane;
+    bool us = false;
+    if (i < n) {
+      const int64_t g = adj_idx[off + i];
+      us = (f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+      s_gid[i] = (int)g;
+      s_key[i] = ((int)key3[3 * g] - cx + 64) | (((int)key3[3 * g + 1] - cy + 64) << 8) | (((int)key3[3 * g + 2] - cz + 64) << 16);
+      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, us);
+    if (us) s_ul[nv + __popc(bal & lt)] = (unsigned char)i;
+    nv += __popc(bal);
+  }
+  __syncwarp();
+  const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
+  const float scale = (float)LW_BINS / fmaxf(1.0f - lb, 1e-3f);
+  bool to_fallback = wempty[0] > lb;     // empty pairs could merge: the general kernel enumerates them
+  const int npairs = nv * (nv - 1) / 2, nent = 2 * npairs;
+  const int S = 2 * r2 + 1;
+  auto decode = [&](int p, int& a, int& b) {
+    int r = p / (nv - 1), c = p - r * (nv - 1);
+    int ia, ib;
+    if (c < nv - 1 - r) { ia = r; ib = r + 1 + c; }
+    else { ia = nv - 1 - r; ib = ia + 1 + (c - (nv - 1 - r)); }
+    a = s_ul[ia]; b = s_ul[ib];
+  };
+  auto fetch = [&](int a, int b, float& w_ab, float& w_ba) {
+    const int ka = s_key[a], kb = s_key[b];
+    int dx = (kb & 255) - (ka & 255), dy = ((kb >> 8) & 255) - ((ka >> 8) & 255), dz = ((kb >> 16) & 255) - ((ka >> 16) & 255);
+    const bool pos = dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0)));
+    if (!pos) { dx = -dx; dy = -dy; dz = -dz; }
+    const int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2) - half - 1;
+    const float2 e = __ldg(table + (size_t)(pos ? s_gid[a] : s_gid[b]) * half + code);
+    w_ab = pos ? e.x : e.y;
+    w_ba = pos ? e.y : e.x;
+  };
+  int nseg = nv;
+  bool stop = false;
+  // one batch of <= 32 entries in descending order, one per lane: the first mergeable entry merges,
+  // the later ones are re-evaluated against the new state (cutGraphSegmentation VS.h:1955-2001)
+  auto merge_batch = [&](float w, int f, bool valid) {
+    const int v1 = f >> 8, v2 = f & 255;
+    uint32_t todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+      bool pred = false, a_wins = true;
+      int sa = 0, sb = 0;
+      if ((todo >> lane) & 1u) {
+        sa = s_seg[v1]; sb = s_seg[v2];
+        if (sa != sb) {
+          const float m1 = s_int[sa] - k / (float)(int)s_size[sa];
+          const float m2 = s_int[sb] - k / (float)(int)s_size[sb];
+          a_wins = (m1 >= m2);
+          pred = w > (a_wins ? m1 : m2);
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+      if (!bal) break;
+      const int Lm = __ffs(bal) - 1;
+      const int keepl = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
+      const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
+      const float wl = __shfl_sync(0xffffffffu, w, Lm);
+      for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
+      if (lane == 0) { s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0; }
+      nseg--;
+      __syncwarp();
+      todo &= ~((2u << Lm) - 1u);
+      if (nseg <= 1) { stop = true; break; }
+    }
+  };
+  if (!to_fallback && nv > 1) {
+    // --- pass 0: bin of every directed entry + histogram ---
+    if (lane < 4) bins[(nent & ~3) + lane] = 255;   // the last partial word must read as "dropped"
+    __syncwarp();
+    for (int p = lane; p < npairs; p += 32) {
+      int a, b;
+      decode(p, a, b);
+      float w_ab, w_ba;
+      fetch(a, b, w_ab, w_ba);
+      int b0 = 255, b1 = 255;
+      if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
+      if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
+      reinterpret_cast<unsigned short*>(bins)[p] = (unsigned short)(b0 | (b1 << 8));
+    }
+    __syncwarp();
+    {   // inclusive prefix sums over the 256 counters
+      unsigned loc[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { sum += s_hist[lane * 8 + q]; loc[q] = sum; }
+      const unsigned inc = warp_incl_scan(sum, lane);
+#pragma unroll
+      for (int q = 0; q < 8; q++) s_hist[lane * 8 + q] = inc - sum + loc[q];
+    }
+    __syncwarp();
+    const int m = (int)s_hist[255];
+    const int nwords = (nent + 3) >> 2;
+    float ratio = 1.0f, minthr = 1.0f - k / 1.0f;
+    int c0 = 0;
+    bool done = false;
+    while (!done && c0 < LW_BINS && m > 0) {
+      // --- chunk boundary: bins [c0, c1) with about LW_CH / ratio entries ---
+      int c1 = 0, tot = 0;
+      if (lane == 0) {
+        const int before = c0 > 0 ? (int)s_hist[c0 - 1] : 0;
+        const int budget = before + min(LW_CS, max(1, (int)((float)LW_CH / ratio)));   // never more than the staging buffer
+        int lo = c0, hi = LW_BINS;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)s_hist[mid - 1] <= budget) lo = mid; else hi = mid - 1; }
+        c1 = lo;
+        if (c1 <= c0 || (int)s_hist[c1 - 1] == before) {
+          int l2 = c0 + 1, h2 = LW_BINS;   // smallest c1 with prefix[c1-1] > before
+          while (l2 < h2) { int mid = (l2 + h2) >> 1; if ((int)s_hist[mid - 1] > before) h2 = mid; else l2 = mid + 1; }
+          c1 = l2;
+        }
+        tot = (int)s_hist[c1 - 1] - before;
+        s_scal[0] = 0;
+      }
+      c1 = __shfl_sync(0xffffffffu, c1, 0); tot = __shfl_sync(0xffffffffu, tot, 0);
+      if (tot == 0) break;                 // nothing left
+      if (tot > LW_CS) { to_fallback = true; break; }   // one bin alone overflows the staging buffer
+      __syncwarp();
+      // --- entry ids of the chunk: 4 bins per 32-bit word, SIMD byte compares ---
+      {
+        const unsigned lo4 = (unsigned)c0 * 0x01010101u, hi4 = (unsigned)c1 * 0x01010101u;
+        const unsigned* bw = reinterpret_cast<const unsigned*>(bins);
+        for (int wi = lane; wi < nwords; wi += 32) {
+          const unsigned word = bw[wi];
+          unsigned mk = __vcmpgeu4(word, lo4) & __vcmpltu4(word, hi4);
+          while (mk) {
+            const int byte = (__ffs(mk) - 1) >> 3;
+            mk &= ~(0xffu << (byte * 8));
+            C_e[atomicAdd(&s_scal[0], 1u)] = (unsigned short)(wi * 4 + byte);
+          }
+        }
+      }
+      __syncwarp();
+      const int cntE = (int)s_scal[0];    // == tot
+      // --- fetch the still-useful ones (endpoints in different segments) ---
+      int kept = 0;
+      float rw = -1.0f;
+      int rf = 0xffff;
+      for (int x0 = 0; x0 < cntE; x0 += 32) {
+        const int x = x0 + lane;
+        bool keep = false;
+        float w = 0.f;
+        int f = 0;
+        if (x < cntE) {
+          const int e = C_e[x];
+          int a, b;
+          decode(e >> 1, a, b);
+          if (s_seg[a] != s_seg[b]) {
+            float w_ab, w_ba;
+            fetch(a, b, w_ab, w_ba);
+            keep = true;
+            // entry (row i, col j) = weight(idx[i] -> idx[j]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
+            if (e & 1) { w = w_ba; f = (a << 8) | b; } else { w = w_ab; f = (b << 8) | a; }
+          }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) { const int pos = kept + __popc(bal & lt); C_w[pos] = w; C_f[pos] = (unsigned short)f; }
+        kept += __popc(bal);
+      }
+      __syncwarp();
+      if (kept > 0) {
+        const bool below_pending = true;
+        (void)below_pending;
+        bool below;
+        if (kept <= 32) {
+          // one entry per lane: bitonic sort across the warp with shuffles, (w desc, packed index asc)
+          if (lane < kept) { rw = C_w[lane]; rf = C_f[lane]; }
+#pragma unroll
+          for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              const float wo = __shfl_xor_sync(0xffffffffu, rw, j);
+              const int fo = __shfl_xor_sync(0xffffffffu, rf, j);
+              const bool other_first = (wo > rw) || (wo == rw && fo < rf);
+              const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+              if ((up == lower) ? other_first : !other_first) { rw = wo; rf = fo; }
+            }
+          }
+          const float w0 = __shfl_sync(0xffffffffu, rw, 0);
+          below = !(w0 > minthr);       // w > max(thr1,thr2) >= minthr is impossible from here on
+          stop = below || nseg <= 1;
+          if (!stop) merge_batch(rw, rf, lane < kept);
+        } else {
+          int P = 64;
+          while (P < kept) P <<= 1;
+          for (int i = kept + lane; i < P; i += 32) { C_w[i] = -1.0f; C_f[i] = 0xffff; }
+          __syncwarp();
+          for (int kk = 2; kk <= P; kk <<= 1) {       // bitonic sort in shared memory
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              for (int i = lane; i < P; i += 32) {
+                const int x = i ^ j;
+                if (x > i) {
+                  const float wi = C_w[i], wx = C_w[x];
+                  const unsigned short fi = C_f[i], fx = C_f[x];
+                  const bool x_before_i = (wx > wi) || (wx == wi && fx < fi);
+                  const bool up = (i & kk) == 0;
+                  if (x_before_i == up) { C_w[i] = wx; C_w[x] = wi; C_f[i] = fx; C_f[x] = fi; }
+                }
+              }
+              __syncwarp();
+            }
+          }
+          below = !(C_w[0] > minthr);
+          stop = below || nseg <= 1;
+          for (int bs = 0; bs < kept && !stop; bs += 32) {
+            const int e = bs + lane;
+            const bool valid = e < kept;
+            merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
+          }
+        }
+        float mt = 3.0e38f;
+        for (int v = lane; v < n; v += 32) {
+          const int sz = (int)s_size[v];
+          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        minthr = mt;
+        if (nseg <= 1 || below) done = true;
+      }
+      ratio = fminf(1.0f, fmaxf(1.25f * (float)(kept + 2) / (float)(tot + 2), 1.0f / 256.0f));
+      c0 = c1;
+      if (dbg && lane == 0) { atomicAdd(&dbg[0], 1ull); atomicAdd(&dbg[1], (unsigned long long)tot); atomicAdd(&dbg[2], (unsigned long long)kept); }
+    }
+    if (dbg && lane == 0) { atomicAdd(&dbg[3], 1ull); atomicAdd(&dbg[4], (unsigned long long)m); atomicAdd(&dbg[5], (unsigned long long)nseg); atomicAdd(&dbg[6], (unsigned long long)nv); }
+  }
+  if (to_fallback) {
+    if (lane == 0) fallback[atomicAdd(fallback_count, 1u)] = u;
+    return;
+  }
+  // --- emit the segment that contains local vertex 0 (the unit itself) ---
+  const int s0 = s_seg[0];
+  int cnt = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int v = b + lane;
+    const bool in = v < n && s_seg[v] == s0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    if (in) conn_idx[off + cnt + __popc(bal & lt)] = s_gid[v];
+    cnt += __popc(bal);
+  }
+  if (lane == 0) conn_cnt[u] = (uint32_t)cnt;
+}
+
 // ---- stage 5b: crossValidation (VS.h:2111-2179): keep j in L[i] iff i in L[j].  One warp per unit. ----
 __global__ void __launch_bounds__(128) k_mutual(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt0,
                                               const int32_t* __restrict__ idx0, int64_t nu, uint32_t* __restrict__ cnt1,
