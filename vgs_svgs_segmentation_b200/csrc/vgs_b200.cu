@@ -812,7 +812,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(h->class_count.reserve(256)); CK(h->class_list.reserve((size_t)N_CLASSES * nu * 4));
     unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
     float* d_wempty = h->small.as<float>() + 160;
-    uint32_t* d_maxn = h->class_count.as<uint32_t>() + 32;
+    uint32_t* d_maxn = h->class_count.as<uint32_t>() + 16;
     CK(cudaMemsetAsync(h->class_count.p, 0, 256, h->stream));
     CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));

@@ -6,12 +6,12 @@
 namespace vgs {
 
 constexpr int MAX_EPOCHS = 40;
-constexpr int N_CLASSES = 10;
+constexpr int N_CLASSES = 13;
 // class c holds local graphs whose ENUMERATED vertex count (used neighbours; all neighbours when the
 // empty-pair weight can merge) is <= CLASS_N[c]; pool capacity CLASS_N(CLASS_N-1) directed weights
-__constant__ int c_class_n[N_CLASSES] = {16, 32, 40, 48, 64, 80, 96, 112, 128, 181};
-constexpr int CLASS_N_HOST[N_CLASSES] = {16, 32, 40, 48, 64, 80, 96, 112, 128, 181};
-constexpr int CLASS_T_HOST[N_CLASSES] = {64, 64, 64, 64, 128, 128, 128, 256, 256, 256};
+__constant__ int c_class_n[N_CLASSES] = {16, 24, 32, 40, 48, 56, 64, 72, 80, 96, 112, 128, 181};
+constexpr int CLASS_N_HOST[N_CLASSES] = {16, 24, 32, 40, 48, 56, 64, 72, 80, 96, 112, 128, 181};
+constexpr int CLASS_T_HOST[N_CLASSES] = {64, 64, 64, 64, 64, 128, 128, 128, 128, 128, 256, 256, 256};
 constexpr int LG_CS = 512;     // staging capacity (entries) of one sorted chunk
 constexpr int LG_CH = 128;     // target chunk size (all merges of a planar neighbourhood happen in the top ~100 weights)
 constexpr int LG_BINS = 256;   // weight histogram bins
@@ -803,7 +803,7 @@ constexpr int LW_CH = 28;       // target number of USEFUL entries per chunk (on
 constexpr int LW_WARPS = 4;     // units per CTA
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
-  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 256 * 4 + 16 + (size_t)LW_CS * 4 + (size_t)ncap * 3 + (size_t)mcap + 16;
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)mcap * 2 + (size_t)ncap * 3 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -824,14 +824,13 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   float* s_int = C_w + LW_CS;                                        // ncap
   int* s_gid = reinterpret_cast<int*>(s_int + ncap);                 // ncap
   int* s_key = s_gid + ncap;                                         // ncap: (dx+64) | (dy+64)<<8 | (dz+64)<<16 relative to the centre
-  unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256
-  unsigned* s_scal = s_hist + 256;                                   // 4 scalars
-  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_scal + 4);   // LW_CS
-  unsigned short* C_e = C_f + LW_CS;                                 // LW_CS: entry ids of the chunk
-  unsigned char* s_seg = reinterpret_cast<unsigned char*>(C_e + LW_CS);   // ncap
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
+  unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
+  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_cur + 256);   // LW_CS
+  unsigned short* ids = C_f + LW_CS;                                 // mcap: directed entry ids (2*pair + dir) ordered by bin
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(ids + mcap);    // ncap
   unsigned char* s_size = s_seg + ncap;                              // ncap
   unsigned char* s_ul = s_size + ncap;                               // ncap: local ids of the used vertices
-  unsigned char* bins = s_ul + ncap;                                 // mcap (+pad): histogram bin of every directed entry
   const uint32_t lt = (1u << lane) - 1u;
 
   const uint32_t u = list[li];
@@ -860,13 +859,6 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   bool to_fallback = wempty[0] > lb;     // empty pairs could merge: the general kernel enumerates them
   const int npairs = nv * (nv - 1) / 2, nent = 2 * npairs;
   const int S = 2 * r2 + 1;
-  auto decode = [&](int p, int& a, int& b) {
-    int r = p / (nv - 1), c = p - r * (nv - 1);
-    int ia, ib;
-    if (c < nv - 1 - r) { ia = r; ib = r + 1 + c; }
-    else { ia = nv - 1 - r; ib = ia + 1 + (c - (nv - 1 - r)); }
-    a = s_ul[ia]; b = s_ul[ib];
-  };
   auto fetch = [&](int a, int b, float& w_ab, float& w_ba) {
     const int ka = s_key[a], kb = s_key[b];
     int dx = (kb & 255) - (ka & 255), dy = ((kb >> 8) & 255) - ((ka >> 8) & 255), dz = ((kb >> 16) & 255) - ((ka >> 16) & 255);
@@ -911,37 +903,59 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
     }
   };
   if (!to_fallback && nv > 1) {
-    // --- pass 0: bin of every directed entry + histogram ---
-    if (lane < 4) bins[(nent & ~3) + lane] = 255;   // the last partial word must read as "dropped"
-    __syncwarp();
-    for (int p = lane; p < npairs; p += 32) {
-      int a, b;
-      decode(p, a, b);
-      float w_ab, w_ba;
-      fetch(a, b, w_ab, w_ba);
-      int b0 = 255, b1 = 255;
-      if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
-      if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
-      reinterpret_cast<unsigned short*>(bins)[p] = (unsigned short)(b0 | (b1 << 8));
+    // --- pass A: histogram of the kept weights (the weights themselves are not stored) ---
+    // pairs (ia < ib) of used-list positions in row-major order; each lane steps 32 pairs at a time
+    // (row wrap by subtraction, no division)
+    {
+      int ia = 0, rem = lane;              // rem = offset inside row ia, row length nv-1-ia
+      while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+      while (ia < nv - 1) {
+        float w_ab, w_ba;
+        fetch(s_ul[ia], s_ul[ia + 1 + rem], w_ab, w_ba);
+        if (w_ab > lb) atomicAdd(&s_hist[min(LW_BINS - 1, (int)((1.0f - w_ab) * scale))], 1u);
+        if (w_ba > lb) atomicAdd(&s_hist[min(LW_BINS - 1, (int)((1.0f - w_ba) * scale))], 1u);
+        rem += 32;
+        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+      }
     }
     __syncwarp();
-    {   // inclusive prefix sums over the 256 counters
+    {   // inclusive prefix sums over the 256 counters; cursors = exclusive starts
       unsigned loc[8], sum = 0;
 #pragma unroll
       for (int q = 0; q < 8; q++) { sum += s_hist[lane * 8 + q]; loc[q] = sum; }
       const unsigned inc = warp_incl_scan(sum, lane);
 #pragma unroll
-      for (int q = 0; q < 8; q++) s_hist[lane * 8 + q] = inc - sum + loc[q];
+      for (int q = 0; q < 8; q++) {
+        const unsigned cnt = q ? loc[q] - loc[q - 1] : loc[0];
+        s_hist[lane * 8 + q] = inc - sum + loc[q];
+        s_cur[lane * 8 + q] = inc - sum + loc[q] - cnt;
+      }
+    }
+    __syncwarp();
+    // --- pass B: entries ordered by bin (second read of the table, L2 hits); an entry is stored as
+    //     (ia << 8) | (ib << 1) | dir with ia < ib positions in the used list, dir 0 = a->b, 1 = b->a ---
+    {
+      int ia = 0, rem = lane;
+      while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+      while (ia < nv - 1) {
+        const int ib = ia + 1 + rem;
+        float w_ab, w_ba;
+        fetch(s_ul[ia], s_ul[ib], w_ab, w_ba);
+        const int code = (ia << 8) | (ib << 1);
+        if (w_ab > lb) ids[atomicAdd(&s_cur[min(LW_BINS - 1, (int)((1.0f - w_ab) * scale))], 1u)] = (unsigned short)code;
+        if (w_ba > lb) ids[atomicAdd(&s_cur[min(LW_BINS - 1, (int)((1.0f - w_ba) * scale))], 1u)] = (unsigned short)(code | 1);
+        rem += 32;
+        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+      }
     }
     __syncwarp();
     const int m = (int)s_hist[255];
-    const int nwords = (nent + 3) >> 2;
     float ratio = 1.0f, minthr = 1.0f - k / 1.0f;
     int c0 = 0;
     bool done = false;
     while (!done && c0 < LW_BINS && m > 0) {
       // --- chunk boundary: bins [c0, c1) with about LW_CH / ratio entries ---
-      int c1 = 0, tot = 0;
+      int c1 = 0, tot = 0, bef = 0;
       if (lane == 0) {
         const int before = c0 > 0 ? (int)s_hist[c0 - 1] : 0;
         const int budget = before + min(LW_CS, max(1, (int)((float)LW_CH / ratio)));   // never more than the staging buffer
@@ -954,28 +968,12 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
           c1 = l2;
         }
         tot = (int)s_hist[c1 - 1] - before;
-        s_scal[0] = 0;
+        bef = before;
       }
-      c1 = __shfl_sync(0xffffffffu, c1, 0); tot = __shfl_sync(0xffffffffu, tot, 0);
+      c1 = __shfl_sync(0xffffffffu, c1, 0); tot = __shfl_sync(0xffffffffu, tot, 0); bef = __shfl_sync(0xffffffffu, bef, 0);
       if (tot == 0) break;                 // nothing left
       if (tot > LW_CS) { to_fallback = true; break; }   // one bin alone overflows the staging buffer
-      __syncwarp();
-      // --- entry ids of the chunk: 4 bins per 32-bit word, SIMD byte compares ---
-      {
-        const unsigned lo4 = (unsigned)c0 * 0x01010101u, hi4 = (unsigned)c1 * 0x01010101u;
-        const unsigned* bw = reinterpret_cast<const unsigned*>(bins);
-        for (int wi = lane; wi < nwords; wi += 32) {
-          const unsigned word = bw[wi];
-          unsigned mk = __vcmpgeu4(word, lo4) & __vcmpltu4(word, hi4);
-          while (mk) {
-            const int byte = (__ffs(mk) - 1) >> 3;
-            mk &= ~(0xffu << (byte * 8));
-            C_e[atomicAdd(&s_scal[0], 1u)] = (unsigned short)(wi * 4 + byte);
-          }
-        }
-      }
-      __syncwarp();
-      const int cntE = (int)s_scal[0];    // == tot
+      const int cntE = tot;               // the chunk is the contiguous id range [bef, bef + tot)
       // --- fetch the still-useful ones (endpoints in different segments) ---
       int kept = 0;
       float rw = -1.0f;
@@ -986,9 +984,8 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
         float w = 0.f;
         int f = 0;
         if (x < cntE) {
-          const int e = C_e[x];
-          int a, b;
-          decode(e >> 1, a, b);
+          const int e = ids[bef + x];
+          const int a = s_ul[e >> 8], b = s_ul[(e >> 1) & 127];
           if (s_seg[a] != s_seg[b]) {
             float w_ab, w_ba;
             fetch(a, b, w_ab, w_ba);
