@@ -90,7 +90,7 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  DBuf stencil2, pair_table, need_rows, fallback;
+  DBuf stencil2, pair_table, need_rows, fallback, lg_scratch;
   int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -346,7 +346,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -879,7 +879,14 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       d_dbg = h->small.as<unsigned long long>() + 64;
       CK(cudaMemsetAsync(d_dbg, 0, 64, h->stream));
     }
-    if (use_warp) CK(h->fallback.reserve((size_t)nu * 4 + 16));
+    size_t scratch_off = 0;
+    if (use_warp) {
+      CK(h->fallback.reserve((size_t)nu * 4 + 16));
+      size_t need = 0;
+      for (int c = 0; c < N_CLASSES; c++)
+        if (cc[c] && CLASS_N_HOST[c] <= 128) need += (size_t)cc[c] * (size_t)CLASS_N_HOST[c] * (size_t)(CLASS_N_HOST[c] - 1);
+      CK(h->lg_scratch.reserve(need * 2 + 64));
+    }
     uint32_t max_n_all = 0;
     for (int c = 0; c < N_CLASSES; c++) max_n_all = std::max(max_n_all, cc[c] ? cmaxn[c] : 0u);
     for (int c = 0; c < N_CLASSES; c++) {
@@ -888,10 +895,12 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       if (use_warp && CLASS_N_HOST[c] <= 128) {
         const size_t slice = lw_slice_bytes(ncap, mcap);
         const uint32_t* wlist = h->class_list.as<uint32_t>() + (size_t)c * nu;
+        unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
+        scratch_off += (size_t)cc[c] * (size_t)mcap;
         LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->rec.as<float>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
-               h->fallback.as<uint32_t>(), d_fb_count, d_dbg);
+               h->fallback.as<uint32_t>(), d_fb_count, scratch, d_dbg);
         continue;
       }
       size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (2 * LG_BINS + 2) * 4 + 64;

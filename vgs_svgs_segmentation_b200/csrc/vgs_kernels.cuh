@@ -803,7 +803,8 @@ constexpr int LW_CH = 28;       // target number of USEFUL entries per chunk (on
 constexpr int LW_WARPS = 4;     // units per CTA
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
-  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)mcap * 2 + (size_t)ncap * 3 + 16;
+  (void)mcap;   // the bin-ordered entry list lives in a global scratch slice (written once, read once: L2)
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -814,6 +815,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
                                                                   int r2, const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
                                                                   int32_t* __restrict__ conn_idx, uint32_t* __restrict__ fallback,
                                                                   uint32_t* __restrict__ fallback_count,
+                                                                  unsigned short* __restrict__ scratch,
                                                                   unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -827,8 +829,8 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
   unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
   unsigned short* C_f = reinterpret_cast<unsigned short*>(s_cur + 256);   // LW_CS
-  unsigned short* ids = C_f + LW_CS;                                 // mcap: directed entry ids (2*pair + dir) ordered by bin
-  unsigned char* s_seg = reinterpret_cast<unsigned char*>(ids + mcap);    // ncap
+  unsigned short* ids = scratch + (size_t)li * (size_t)mcap;         // mcap (global): directed entries ordered by bin
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(C_f + LW_CS);   // ncap
   unsigned char* s_size = s_seg + ncap;                              // ncap
   unsigned char* s_ul = s_size + ncap;                               // ncap: local ids of the used vertices
   const uint32_t lt = (1u << lane) - 1u;
