@@ -840,6 +840,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   const int n = (int)(adj_off[u + 1] - off);
   const int cx = (int)key3[3 * (int64_t)u], cy = (int)key3[3 * (int64_t)u + 1], cz = (int)key3[3 * (int64_t)u + 2];
   for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
+  const int S = 2 * r2 + 1;
   int nv = 0;
   for (int b0 = 0; b0 < n; b0 += 32) {   // vertex table + ordered list of the used vertices
     const int i = b0 + lane;
@@ -848,7 +849,8 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       const int64_t g = adj_idx[off + i];
       us = (f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
       s_gid[i] = (int)g;
-      s_key[i] = ((int)key3[3 * g] - cx + 64) | (((int)key3[3 * g + 1] - cy + 64) << 8) | (((int)key3[3 * g + 2] - cz + 64) << 16);
+      // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
+      s_key[i] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
       s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
@@ -859,15 +861,12 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
   const float scale = (float)LW_BINS / fmaxf(1.0f - lb, 1e-3f);
   bool to_fallback = wempty[0] > lb;     // empty pairs could merge: the general kernel enumerates them
-  const int npairs = nv * (nv - 1) / 2, nent = 2 * npairs;
-  const int S = 2 * r2 + 1;
+  // table slot of the unordered pair {a,b}: row = the vertex whose offset to the other is lexicographically
+  // positive, column = |code(b) - code(a)| - 1  (== ((dx+r2)*S + (dy+r2))*S + (dz+r2) - half - 1 of k_pair_cache)
   auto fetch = [&](int a, int b, float& w_ab, float& w_ba) {
-    const int ka = s_key[a], kb = s_key[b];
-    int dx = (kb & 255) - (ka & 255), dy = ((kb >> 8) & 255) - ((ka >> 8) & 255), dz = ((kb >> 16) & 255) - ((ka >> 16) & 255);
-    const bool pos = dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0)));
-    if (!pos) { dx = -dx; dy = -dy; dz = -dz; }
-    const int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2) - half - 1;
-    const float2 e = __ldg(table + (size_t)(pos ? s_gid[a] : s_gid[b]) * half + code);
+    const int diff = s_key[b] - s_key[a];
+    const bool pos = diff > 0;
+    const float2 e = __ldg(table + (size_t)(pos ? s_gid[a] : s_gid[b]) * half + (pos ? diff : -diff) - 1);
     w_ab = pos ? e.x : e.y;
     w_ba = pos ? e.y : e.x;
   };
