@@ -271,3 +271,44 @@ def test_vgs_cta_kernel_path(built_lib, monkeypatch):
     g = gpu_stages(xyz)
     r = oracle.run(xyz, math=1)
     _compare_vgs(xyz, g, r)
+
+
+def _tiny_clouds():
+    rng = np.random.default_rng(5)
+    one = np.array([[0.3, 0.4, 0.5]], np.float32)
+    few = rng.normal(size=(5, 3)).astype(np.float32)
+    same = np.repeat(np.array([[1.25, -2.5, 0.75]], np.float32), 40, axis=0)           # one voxel, zero scatter
+    one_voxel = (np.array([[2.01, 3.01, 1.01]]) + 0.1 * rng.random((200, 3))).astype(np.float32)
+    sparse = (rng.random((300, 3)) * 30).astype(np.float32)                               # every voxel unused
+    line = np.stack([np.linspace(0, 3, 4000), np.full(4000, 0.7), np.full(4000, 0.2)], 1).astype(np.float32)
+    line += 0.002 * rng.standard_normal(line.shape).astype(np.float32)
+    return dict(one=one, few=few, same=same, one_voxel=one_voxel, sparse=sparse, line=line)
+
+
+@pytest.mark.parametrize("name", ["one", "few", "same", "one_voxel", "sparse", "line"])
+def test_vgs_tiny_and_degenerate_clouds(built_lib, name):
+    """ragged / degenerate inputs: a single point, a handful, identical points (zero scatter matrix ->
+    identity eigenvectors -> 'empty' normal), one voxel, all voxels unused, a 1-D line of voxels"""
+    xyz = _tiny_clouds()[name]
+    g = gpu_stages(xyz)
+    r = oracle.run(xyz, math=1)
+    _compare_vgs(xyz, g, r)
+
+
+def test_vgs_far_from_origin(built_lib):
+    """coordinates of ~5 km: the cross-product cue <X1 x X2, d> leaves [-1,1], acos gives NaN and the
+    convexity cue falls back to PI; keys need 16+ bits per axis"""
+    xyz = scenes.two_planes(40_000, seed=9) + np.array([5000.0, -3000.0, 150.0], np.float32)
+    g = gpu_stages(xyz)
+    r = oracle.run(xyz, math=1)
+    _compare_vgs(xyz, g, r)
+
+
+def test_svgs_tiny(built_lib):
+    rng = np.random.default_rng(2)
+    xyz = (rng.random((500, 3)) * np.array([2.0, 2.0, 0.02])).astype(np.float32) + 0.5
+    labels = scenes.supervoxel_labels_grid(xyz, 0.25)
+    ml = int(labels.max()) + 1
+    g = gpu_stages(xyz, mode=1, labels=labels, max_label=ml)
+    r = oracle.run(xyz, labels=labels, max_label=ml, mode=1, math=1)
+    _compare_svgs(xyz, labels, g, r)
