@@ -885,7 +885,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       size_t need = 0;
       for (int c = 0; c < N_CLASSES; c++)
         if (cc[c] && CLASS_N_HOST[c] <= 128) need += (size_t)cc[c] * (size_t)CLASS_N_HOST[c] * (size_t)(CLASS_N_HOST[c] - 1);
-      CK(h->lg_scratch.reserve(need * 2 + 64));
+      CK(h->lg_scratch.reserve(need * 3 + 64));
     }
     uint32_t max_n_all = 0;
     for (int c = 0; c < N_CLASSES; c++) max_n_all = std::max(max_n_all, cc[c] ? cmaxn[c] : 0u);
@@ -896,7 +896,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         const size_t slice = lw_slice_bytes(ncap, mcap);
         const uint32_t* wlist = h->class_list.as<uint32_t>() + (size_t)c * nu;
         unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
-        scratch_off += (size_t)cc[c] * (size_t)mcap;
+        scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
         LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->rec.as<float>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),

@@ -829,7 +829,10 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
   unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
   unsigned short* C_f = reinterpret_cast<unsigned short*>(s_cur + 256);   // LW_CS
-  unsigned short* ids = scratch + (size_t)li * (size_t)mcap;         // mcap (global): directed entries ordered by bin
+  // global scratch slice of this unit (written once, read once: L2): mcap entry codes ordered by bin,
+  // then mcap bytes holding the histogram bin of every directed entry in enumeration order
+  unsigned short* ids = scratch + (size_t)li * (size_t)(mcap + mcap / 2);
+  unsigned char* gbins = reinterpret_cast<unsigned char*>(ids + mcap);
   unsigned char* s_seg = reinterpret_cast<unsigned char*>(C_f + LW_CS);   // ncap
   unsigned char* s_size = s_seg + ncap;                              // ncap
   unsigned char* s_ul = s_size + ncap;                               // ncap: local ids of the used vertices
@@ -906,16 +909,19 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   if (!to_fallback && nv > 1) {
     // --- pass A: histogram of the kept weights (the weights themselves are not stored) ---
     // pairs (ia < ib) of used-list positions in row-major order; each lane steps 32 pairs at a time
-    // (row wrap by subtraction, no division)
+    // (row wrap by subtraction, no division).  The bins are parked in the scratch slice so that pass B
+    // does not have to gather from the table again.
     {
-      int ia = 0, rem = lane;              // rem = offset inside row ia, row length nv-1-ia
+      int ia = 0, rem = lane, p = lane;    // rem = offset inside row ia, row length nv-1-ia
       while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       while (ia < nv - 1) {
         float w_ab, w_ba;
         fetch(s_ul[ia], s_ul[ia + 1 + rem], w_ab, w_ba);
-        if (w_ab > lb) atomicAdd(&s_hist[min(LW_BINS - 1, (int)((1.0f - w_ab) * scale))], 1u);
-        if (w_ba > lb) atomicAdd(&s_hist[min(LW_BINS - 1, (int)((1.0f - w_ba) * scale))], 1u);
-        rem += 32;
+        int b0 = 255, b1 = 255;
+        if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
+        if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
+        reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
+        rem += 32; p += 32;
         while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
     }
@@ -933,19 +939,19 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       }
     }
     __syncwarp();
-    // --- pass B: entries ordered by bin (second read of the table, L2 hits); an entry is stored as
-    //     (ia << 8) | (ib << 1) | dir with ia < ib positions in the used list, dir 0 = a->b, 1 = b->a ---
+    // --- pass B: entries ordered by bin; an entry is stored as (ia << 8) | (ib << 1) | dir with ia < ib
+    //     positions in the used list, dir 0 = a->b, 1 = b->a ---
     {
-      int ia = 0, rem = lane;
+      int ia = 0, rem = lane, p = lane;
       while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       while (ia < nv - 1) {
         const int ib = ia + 1 + rem;
-        float w_ab, w_ba;
-        fetch(s_ul[ia], s_ul[ib], w_ab, w_ba);
+        const int bb = reinterpret_cast<const unsigned short*>(gbins)[p];
+        const int b0 = bb & 255, b1 = bb >> 8;
         const int code = (ia << 8) | (ib << 1);
-        if (w_ab > lb) ids[atomicAdd(&s_cur[min(LW_BINS - 1, (int)((1.0f - w_ab) * scale))], 1u)] = (unsigned short)code;
-        if (w_ba > lb) ids[atomicAdd(&s_cur[min(LW_BINS - 1, (int)((1.0f - w_ba) * scale))], 1u)] = (unsigned short)(code | 1);
-        rem += 32;
+        if (b0 != 255) ids[atomicAdd(&s_cur[b0], 1u)] = (unsigned short)code;
+        if (b1 != 255) ids[atomicAdd(&s_cur[b1], 1u)] = (unsigned short)(code | 1);
+        rem += 32; p += 32;
         while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
     }
