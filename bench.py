@@ -45,26 +45,48 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clocks / throttle reasons sampled DURING the timed region, through NVML in-process (one
+    `nvidia-smi -lms` child as fallback) so that the sampling itself does not perturb the GPU."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, reasons_bitmask)
         self.stop = threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.child = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+            while not self.stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                self.rows.append((float(sm), float(mx), int(rs)))
+                self.stop.wait(0.02)
+            return
+        except Exception:
+            pass
+        try:   # fallback: ONE long-running nvidia-smi child, as in the profiling recipe
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            self.child = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                           "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.child.stdout:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    self.rows.append((float(f[0]), float(f[1]), int(f[2], 16)))
+                except Exception:
+                    pass
+                if self.stop.is_set():
+                    break
+        except Exception:
+            pass
 
     def __enter__(self):
         self.th.start()
@@ -72,19 +94,18 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.child is not None:
+            try:
+                self.child.terminate()
+            except Exception:
+                pass
+        self.th.join(timeout=3)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(n for n, bit in self.BITS.items() if any(r[2] & bit for r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in self.rows), default=None),
+                "reasons": reasons, "samples": len(self.rows)}
 
 
 def make_scene(n_points, rank):
