@@ -144,8 +144,10 @@ def run_reference(args):
         "impl": "reference", "metric": "points/sec segmented end-to-end", "value": val, "unit": "points/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"VGS construction-site scene, bounded sample of {args.ref_points} points per step "
-                               f"(full workload: {args.points} points), Task_File_VGS.txt parameters"},
+        "config": {"workload": f"VGS, synthetic construction-site scene {args.points} points per GPU (BASELINE.json configs[2]), "
+                               "Task_File_VGS.txt parameters (voxel 0.15, graph 0.5, sigma 0.2 x5, sig_w 2, cut 0.3, "
+                               "points_min 10, adjacency_min 3, voxels_min 3)",
+                   "sample": f"each step = the CPU oracle on a bounded {args.ref_points}-point sample of that scene (same density)"},
         "cpu_baseline": info,
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference cannot be compiled (needs PCL 1.8.1, and voxel_segmentation.h:2279 is undefined); "
