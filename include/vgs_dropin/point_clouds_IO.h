@@ -1,7 +1,7 @@
 // point_clouds_IO.h (drop-in) — the I/O entry points the reference's driver uses (reference
 // point_clouds_IO.h:64-108, point_clouds_IO.cpp:22-76, 147-169), without PCL:
 //   inputTaskTxtFile      : every line of the task file, comments and blanks included; parameter k = line k
-//   inputPointCloudData   : PCD v0.7 reader (DATA ascii | binary; x y z as F 4, other fields skipped)
+//   inputPointCloudData   : PCD v0.7 reader (DATA ascii | binary | binary_compressed (LZF); x y z as F 4, other fields skipped)
 //   saveColoredClusters   : PCD writer (binary, x y z rgb), one deterministic colour per cluster
 // The reference's PCLVisualizer windows (showColoredClusters) are out of scope (GUI).
 #pragma once
@@ -30,6 +30,31 @@ inline std::string vgs_rstrip(const std::string& s) {
   size_t e = s.size();
   while (e > 0 && (s[e - 1] == '\r' || s[e - 1] == '\n' || s[e - 1] == ' ' || s[e - 1] == '\t')) e--;
   return s.substr(0, e);
+}
+
+// LZF decompression (the codec of PCD "binary_compressed"): literal runs (ctrl < 32) and back references
+// (length ctrl>>5 (+ extension byte when 7) + 2, offset ((ctrl & 31) << 8 | next byte) + 1)
+inline bool vgs_lzf_decompress(const unsigned char* ip, size_t in_len, unsigned char* out, size_t out_len) {
+  const unsigned char* const ie = ip + in_len;
+  size_t op = 0;
+  while (ip < ie) {
+    unsigned ctrl = *ip++;
+    if (ctrl < 32) {
+      ctrl++;
+      if (op + ctrl > out_len || ip + ctrl > ie) return false;
+      std::memcpy(out + op, ip, ctrl);
+      op += ctrl; ip += ctrl;
+    } else {
+      size_t len = ctrl >> 5;
+      if (len == 7) { if (ip >= ie) return false; len += *ip++; }
+      if (ip >= ie) return false;
+      size_t off = ((size_t)(ctrl & 0x1f) << 8) + *ip++ + 1;
+      len += 2;
+      if (off > op || op + len > out_len) return false;
+      for (size_t i = 0; i < len; i++, op++) out[op] = out[op - off];   // may overlap
+    }
+  }
+  return op == out_len;
 }
 
 // IO.h:64-80 (pcl::io::loadPCDFile into PointXYZ: only x, y, z survive)
@@ -87,7 +112,26 @@ inline int inputPointCloudData(const std::string& name, PCXYZPtr cloud) {
       std::memcpy(&z, &buf[(size_t)p * rec + offs[iz]], 4);
       cloud->points.push_back(pcl::PointXYZ(x, y, z));
     }
-  } else return -6;   // binary_compressed (LZF) is not supported yet
+  } else if (data == "binary_compressed") {
+    // u32 compressed size, u32 uncompressed size, LZF stream; the payload is field-major (all x, all y, ...)
+    if (types[ix] != 'F' || sizes[ix] != 4 || types[iy] != 'F' || sizes[iy] != 4 || types[iz] != 'F' || sizes[iz] != 4) return -4;
+    std::uint32_t csz = 0, usz = 0;
+    f.read(reinterpret_cast<char*>(&csz), 4);
+    f.read(reinterpret_cast<char*>(&usz), 4);
+    if (!f || (size_t)usz != (size_t)rec * (size_t)npoints) return -7;
+    std::vector<unsigned char> cbuf(csz), ubuf(usz);
+    f.read(reinterpret_cast<char*>(cbuf.data()), csz);
+    if ((size_t)f.gcount() != (size_t)csz) return -5;
+    if (!vgs_lzf_decompress(cbuf.data(), csz, ubuf.data(), usz)) return -8;
+    auto field_base = [&](int fi) { return (size_t)offs[fi] * (size_t)npoints; };   // field-major layout
+    for (long p = 0; p < npoints; p++) {
+      float x, y, z;
+      std::memcpy(&x, &ubuf[field_base(ix) + (size_t)p * 4], 4);
+      std::memcpy(&y, &ubuf[field_base(iy) + (size_t)p * 4], 4);
+      std::memcpy(&z, &ubuf[field_base(iz) + (size_t)p * 4], 4);
+      cloud->points.push_back(pcl::PointXYZ(x, y, z));
+    }
+  } else return -6;
   cloud->width = (std::uint32_t)cloud->points.size(); cloud->height = 1;
   return 0;
 }
