@@ -90,7 +90,7 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  DBuf stencil2, pair_table, need_rows, fallback, lg_scratch;
+  DBuf stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
   int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -346,7 +346,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
   for (DBuf* b : all) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -575,8 +575,9 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   CK(h->rec.reserve((size_t)nu * REC_FLOATS * 4));
   unsigned long long* d_used = h->small.as<unsigned long long>() + 16;
   CK(cudaMemsetAsync(d_used, 0, 8, h->stream));
+  CK(h->uflags.reserve((size_t)nu + 16));
   LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
-         h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), d_used);
+         h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->uflags.as<uint8_t>(), d_used);
   unsigned long long used = 0;
   CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -825,7 +826,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       CK(cudaMemsetAsync(d_need, 0, (size_t)nu, h->stream));
     }
     LAUNCH(k_bin_classes, (unsigned)cdiv((last - first) * 32 + 1, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
-           h->rec.as<float>(), nu, first, last, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
+           h->uflags.as<uint8_t>(), nu, first, last, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
            d_maxn, h->class_list.as<uint32_t>(), d_stats, d_need);
     uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
     unsigned long long stats[3];
@@ -866,7 +867,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
         LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
                h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
-               h->pair_table.as<float2>(), half, d_need);
+               h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
         tpc.stop();
         cached = true;
       }
@@ -898,7 +899,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
         scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
         LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
-               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->rec.as<float>(), h->key3.as<uint32_t>(), cut_thred, ncap,
+               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->uflags.as<uint8_t>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
                h->fallback.as<uint32_t>(), d_fb_count, scratch, d_dbg);
         continue;
@@ -968,14 +969,20 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     StageTimer t(h, &h->tm.closest_ms, 7);
     CK(cudaMemsetAsync(h->attach.p, 0xff, (size_t)nu * 4, h->stream));
     uint32_t* d_changed = h->small.as<uint32_t>() + 128;
-    unsigned long long* d_singles = h->small.as<unsigned long long>() + 40;
-    CK(cudaMemsetAsync(d_singles, 0, 8, h->stream));
+    uint32_t* d_scnt = h->small.as<uint32_t>() + 132;
+    CK(h->singles.reserve((size_t)nu * 4 + 16));
+    CK(cudaMemsetAsync(d_scnt, 0, 8, h->stream));
+    LAUNCH(k_collect_singles, (unsigned)cdiv(nu, 256), 256, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(), nu, adjacency_min,
+           h->singles.as<uint32_t>(), d_scnt);
+    uint32_t scnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(scnt, d_scnt, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     int rounds = 0;
-    while (true) {
+    while (scnt[0] > 0) {
       CK(cudaMemsetAsync(d_changed, 0, 4, h->stream));
-      LAUNCH(k_closest_round, (unsigned)cdiv(nu, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
-             h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, adjacency_min, gp.pp, h->attach.as<int32_t>(), d_changed,
-             rounds == 0 ? d_singles : (unsigned long long*)nullptr);
+      LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
+             h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
+             h->attach.as<int32_t>(), d_changed);
       uint32_t changed = 0;
       CK(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
@@ -983,9 +990,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
       if (!changed) break;
       if (rounds > 100000) return h->fail(VGS_ERR_LIMIT, "vgs_segment: closest-check did not converge");
     }
-    unsigned long long singles = 0;
-    CK(cudaMemcpyAsync(&singles, d_singles, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long singles = scnt[1];
     h->n_singles = (int64_t)singles;
     h->closest_rounds = rounds;
     t.stop();

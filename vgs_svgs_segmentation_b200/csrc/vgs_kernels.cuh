@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256) k_head_write(const uint64_t* __restrict__
 //      reference's sums bit for bit. ----
 __global__ void __launch_bounds__(128) k_features(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
                                                 const uint32_t* __restrict__ ustart, int64_t nunits, int points_min, int svgs,
-                                                float* __restrict__ rec, unsigned long long* __restrict__ n_used) {
+                                                float* __restrict__ rec, uint8_t* __restrict__ uflags,
+                                                unsigned long long* __restrict__ n_used) {
   int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nunits) return;
   uint32_t s = ustart[u], e = ustart[u + 1];
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(128) k_features(const float* __restrict__ xyz,
   out[1] = make_float4(r[4], r[5], r[6], r[7]);
   out[2] = make_float4(r[8], r[9], r[10], r[11]);
   out[3] = make_float4(r[12], r[13], r[14], r[15]);
+  uflags[u] = (uint8_t)f2i(r[REC_FLAGS]);   // compact copy of the flags: the graph stages test F_USED of every neighbour
   if (used) atomicAdd(n_used, 1ull);
 }
 
@@ -338,7 +340,7 @@ __global__ void k_wempty(PairParams pp, float* __restrict__ out) {
 //      neighbours; pairs with an unused unit are enumerated only if their constant weight could
 //      merge (w_empty > cut bound), which never happens with the reference's parameter sets. ----
 __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
-                                                   const float* __restrict__ rec, int64_t nu, int64_t first, int64_t last, float cut,
+                                                   const uint8_t* __restrict__ uflags, int64_t nu, int64_t first, int64_t last, float cut,
                                                    int svgs, const float* __restrict__ wempty, uint32_t* __restrict__ class_count,
                                                    uint32_t* __restrict__ class_maxn, uint32_t* __restrict__ class_list,
                                                    unsigned long long* __restrict__ stats /* [0]=sum n(n-1) [1]=max n [2]=overflow */,
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict_
   const int lane = threadIdx.x & 31;
   const int64_t u = first + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (u >= last) return;
-  if (!(f2i(rec[u * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
+  if (!(uflags[u] & F_USED)) return;
   const uint32_t off = adj_off[u];
   const int n = (int)(adj_off[u + 1] - off);
   int used = 0;
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict_
     bool us = false;
     if (e < n) {
       const int64_t g = adj_idx[off + e];
-      us = (f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+      us = (__ldg(uflags + g) & F_USED) != 0;
       if (need_rows && us) need_rows[g] = 1;
     }
     used += __popc(__ballot_sync(0xffffffffu, us));
@@ -383,14 +385,14 @@ __global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__
                                                   int depth, const int4* __restrict__ st2, int nst2,
                                                   const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
                                                   uint64_t mask, PairParams pp, float2* __restrict__ table, int half,
-                                                  const uint8_t* __restrict__ need_rows) {
+                                                  const uint8_t* __restrict__ need_rows, const uint8_t* __restrict__ uflags) {
   __shared__ int pend_b[4][64];
   __shared__ int pend_i[4][64];
   __shared__ float s_ra[4][REC_FLOATS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t v = (int64_t)blockIdx.x * 4 + w;
   if (v >= nv) return;
-  if (!(f2i(rec[v * REC_FLOATS + REC_FLAGS]) & F_USED)) return;
+  if (!(uflags[v] & F_USED)) return;
   if (need_rows && !need_rows[v]) return;   // multi-GPU: only rows read by this rank's local graphs
   if (lane < REC_FLOATS) s_ra[w][lane] = rec[v * REC_FLOATS + lane];
   __syncwarp();
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__
       int64_t x = (int64_t)kx + o.x, y = (int64_t)ky + o.y, z = (int64_t)kz + o.z;
       if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim) {
         id = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
-        if (id >= 0 && !(f2i(__ldg(rec + (int64_t)id * REC_FLOATS + REC_FLAGS)) & F_USED)) id = -1;
+        if (id >= 0 && !(__ldg(uflags + id) & F_USED)) id = -1;
       }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
@@ -804,13 +806,13 @@ constexpr int LW_WARPS = 4;     // units per CTA
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   (void)mcap;   // the bin-ordered entry list lives in a global scratch slice (written once, read once: L2)
-  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 16 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
 __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
                                                                   const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
-                                                                  const float* __restrict__ rec, const uint32_t* __restrict__ key3,
+                                                                  const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ key3,
                                                                   float k, int ncap, int mcap, const float2* __restrict__ table, int half,
                                                                   int r2, const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
                                                                   int32_t* __restrict__ conn_idx, uint32_t* __restrict__ fallback,
@@ -826,7 +828,8 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   float* s_int = C_w + LW_CS;                                        // ncap
   int* s_gid = reinterpret_cast<int*>(s_int + ncap);                 // ncap
   int* s_key = s_gid + ncap;                                         // ncap: (dx+64) | (dy+64)<<8 | (dz+64)<<16 relative to the centre
-  unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
+  float* s_wmax = reinterpret_cast<float*>(s_key + ncap);           // ncap: largest weight incident to the segment (by label)
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_wmax + ncap);    // 256: histogram, then inclusive prefix sums
   unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
   unsigned short* C_f = reinterpret_cast<unsigned short*>(s_cur + 256);   // LW_CS
   // global scratch slice of this unit (written once, read once: L2): mcap entry codes ordered by bin,
@@ -850,11 +853,11 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
     bool us = false;
     if (i < n) {
       const int64_t g = adj_idx[off + i];
-      us = (f2i(__ldg(rec + g * REC_FLOATS + REC_FLAGS)) & F_USED) != 0;
+      us = (__ldg(uflags + g) & F_USED) != 0;
       s_gid[i] = (int)g;
       // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
       s_key[i] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
-      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f;
+      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f; s_wmax[i] = 0.f;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
     if (us) s_ul[nv + __popc(bal & lt)] = (unsigned char)i;
@@ -899,7 +902,10 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
       for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
-      if (lane == 0) { s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0; }
+      if (lane == 0) {
+        s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0;
+        s_wmax[keepl] = fmaxf(s_wmax[keepl], s_wmax[drop]);
+      }
       nseg--;
       __syncwarp();
       todo &= ~((2u << Lm) - 1u);
@@ -921,6 +927,11 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
         if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
         if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
         reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
+        const float wm = fmaxf(w_ab > lb ? w_ab : 0.f, w_ba > lb ? w_ba : 0.f);   // NaN-free: NaN fails w > lb
+        if (wm > 0.f) {
+          atomicMax(reinterpret_cast<int*>(&s_wmax[s_ul[ia]]), __float_as_int(wm));
+          atomicMax(reinterpret_cast<int*>(&s_wmax[s_ul[ia + 1 + rem]]), __float_as_int(wm));
+        }
         rem += 32; p += 32;
         while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
@@ -957,9 +968,29 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
     }
     __syncwarp();
     const int m = (int)s_hist[255];
-    float ratio = 1.0f, minthr = 1.0f - k / 1.0f;
+    // A segment whose largest incident weight does not exceed its threshold can never merge again (its
+    // threshold only changes when it merges), so it is dead: only ALIVE segments count for the two exact
+    // termination tests (at most one alive segment left; next weight <= smallest alive threshold).
+    float minthr = 0.f;
+    int alive = 0;
+    auto refresh = [&]() {
+      float mt = 3.0e38f;
+      int cnt = 0;
+      for (int v = lane; v < n; v += 32) {
+        const int sz = (int)s_size[v];
+        if (sz > 0) {
+          const float thr = s_int[v] - k / (float)sz;
+          if (s_wmax[v] > thr) { mt = fminf(mt, thr); cnt++; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+      minthr = mt; alive = cnt;
+    };
+    refresh();
+    float ratio = 1.0f;
     int c0 = 0;
-    bool done = false;
+    bool done = alive <= 1;
     while (!done && c0 < LW_BINS && m > 0) {
       // --- chunk boundary: bins [c0, c1) with about LW_CH / ratio entries ---
       int c1 = 0, tot = 0, bef = 0;
@@ -1056,15 +1087,9 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
             merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
           }
         }
-        float mt = 3.0e38f;
-        for (int v = lane; v < n; v += 32) {
-          const int sz = (int)s_size[v];
-          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-        minthr = mt;
-        if (nseg <= 1 || below) done = true;
+        __syncwarp();
+        refresh();
+        if (nseg <= 1 || below || alive <= 1) done = true;
       }
       ratio = fminf(1.0f, fmaxf(1.25f * (float)(kept + 2) / (float)(tot + 2), 1.0f / 256.0f));
       c0 = c1;
@@ -1150,6 +1175,51 @@ __global__ void __launch_bounds__(128) k_closest_round(const uint32_t* __restric
     if (w_ab >= best) { best = w_ab; bi = (int)c; }
   }
   if (bi != attach[i]) { attach[i] = bi; *changed = 1u; }
+}
+
+// units whose list is {self} after the mutual filter and that have enough neighbours (VS.h:2199-2201)
+__global__ void __launch_bounds__(256) k_collect_singles(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1, int64_t nu,
+                                                       int adjacency_min, uint32_t* __restrict__ list, uint32_t* __restrict__ counts /* [0]=eligible [1]=all singles */) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nu || cnt1[i] != 1u) return;
+  atomicAdd(&counts[1], 1u);
+  const int n = (int)(adj_off[i + 1] - adj_off[i]);
+  if (!(n + 1 > adjacency_min)) return;
+  list[atomicAdd(&counts[0], 1u)] = (uint32_t)i;
+}
+// one warp per single unit: lanes evaluate the candidates; the winner is the LAST candidate with the
+// largest weight (`>=` in VS.h:2281), candidates in the order slot 0 (= the COUNT), then the neighbours
+__global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __restrict__ list, uint32_t nlist, const uint32_t* __restrict__ adj_off,
+                                                          const int32_t* __restrict__ adj_idx, const uint32_t* __restrict__ cnt1,
+                                                          const float* __restrict__ rec, int64_t nu, PairParams pp, int32_t* attach,
+                                                          uint32_t* __restrict__ changed) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (li >= nlist) return;
+  const int64_t i = list[li];
+  const uint32_t off = adj_off[i];
+  const int n = (int)(adj_off[i + 1] - off);
+  float ri[REC_FLOATS], rc[REC_FLOATS];
+  for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
+  float best = 0.f;
+  int bj = -1, bi = -1;
+  for (int j = lane; j <= n; j += 32) {
+    const int64_t c = (j == 0) ? (int64_t)n : (int64_t)adj_idx[off + j - 1];
+    if (c < 0 || c >= nu) continue;
+    const uint32_t cc = cnt1[c];
+    if (!(cc > 1u || (cc == 1u && c < i && ((volatile int32_t*)attach)[c] >= 0))) continue;
+    for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
+    float w_ab, w_ba;
+    pair_weights(ri, rc, pp, w_ab, w_ba);
+    if (w_ab >= best) { best = w_ab; bj = j; bi = (int)c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ow = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oj >= 0 && (bj < 0 || ow > best || (ow == best && oj > bj))) { best = ow; bj = oj; bi = oi; }
+  }
+  if (lane == 0 && bi != attach[i]) { attach[i] = bi; *changed = 1u; }
 }
 
 // ---- stage 5d: connected components by lock-free union-find, root = smallest unit id ----
