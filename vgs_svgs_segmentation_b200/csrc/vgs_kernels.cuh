@@ -806,7 +806,7 @@ constexpr int LW_WARPS = 4;     // units per CTA
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   (void)mcap;   // the bin-ordered entry list lives in a global scratch slice (written once, read once: L2)
-  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 16 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -828,8 +828,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
   float* s_int = C_w + LW_CS;                                        // ncap
   int* s_gid = reinterpret_cast<int*>(s_int + ncap);                 // ncap
   int* s_key = s_gid + ncap;                                         // ncap: (dx+64) | (dy+64)<<8 | (dz+64)<<16 relative to the centre
-  float* s_wmax = reinterpret_cast<float*>(s_key + ncap);           // ncap: largest weight incident to the segment (by label)
-  unsigned* s_hist = reinterpret_cast<unsigned*>(s_wmax + ncap);    // 256: histogram, then inclusive prefix sums
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
   unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
   unsigned short* C_f = reinterpret_cast<unsigned short*>(s_cur + 256);   // LW_CS
   // global scratch slice of this unit (written once, read once: L2): mcap entry codes ordered by bin,
@@ -857,7 +856,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       s_gid[i] = (int)g;
       // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
       s_key[i] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
-      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f; s_wmax[i] = 0.f;
+      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
     if (us) s_ul[nv + __popc(bal & lt)] = (unsigned char)i;
@@ -902,10 +901,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
       for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
-      if (lane == 0) {
-        s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0;
-        s_wmax[keepl] = fmaxf(s_wmax[keepl], s_wmax[drop]);
-      }
+      if (lane == 0) { s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0; }
       nseg--;
       __syncwarp();
       todo &= ~((2u << Lm) - 1u);
@@ -927,11 +923,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
         if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
         if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
         reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
-        const float wm = fmaxf(w_ab > lb ? w_ab : 0.f, w_ba > lb ? w_ba : 0.f);   // NaN-free: NaN fails w > lb
-        if (wm > 0.f) {
-          atomicMax(reinterpret_cast<int*>(&s_wmax[s_ul[ia]]), __float_as_int(wm));
-          atomicMax(reinterpret_cast<int*>(&s_wmax[s_ul[ia + 1 + rem]]), __float_as_int(wm));
-        }
+
         rem += 32; p += 32;
         while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
@@ -968,47 +960,28 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
     }
     __syncwarp();
     const int m = (int)s_hist[255];
-    // A segment whose largest incident weight does not exceed its threshold can never merge again (its
-    // threshold only changes when it merges), so it is dead: only ALIVE segments count for the two exact
-    // termination tests (at most one alive segment left; next weight <= smallest alive threshold).
-    float minthr = 0.f;
-    int alive = 0;
-    auto refresh = [&]() {
-      float mt = 3.0e38f;
-      int cnt = 0;
-      for (int v = lane; v < n; v += 32) {
-        const int sz = (int)s_size[v];
-        if (sz > 0) {
-          const float thr = s_int[v] - k / (float)sz;
-          if (s_wmax[v] > thr) { mt = fminf(mt, thr); cnt++; }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-      minthr = mt; alive = cnt;
-    };
-    refresh();
-    float ratio = 1.0f;
+    float ratio = 1.0f, minthr = 1.0f - k / 1.0f;
     int c0 = 0;
-    bool done = alive <= 1;
+    bool done = false;
     while (!done && c0 < LW_BINS && m > 0) {
       // --- chunk boundary: bins [c0, c1) with about LW_CH / ratio entries ---
-      int c1 = 0, tot = 0, bef = 0;
-      if (lane == 0) {
-        const int before = c0 > 0 ? (int)s_hist[c0 - 1] : 0;
-        const int budget = before + min(LW_CS, max(1, (int)((float)LW_CH / ratio)));   // never more than the staging buffer
-        int lo = c0, hi = LW_BINS;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)s_hist[mid - 1] <= budget) lo = mid; else hi = mid - 1; }
-        c1 = lo;
-        if (c1 <= c0 || (int)s_hist[c1 - 1] == before) {
-          int l2 = c0 + 1, h2 = LW_BINS;   // smallest c1 with prefix[c1-1] > before
-          while (l2 < h2) { int mid = (l2 + h2) >> 1; if ((int)s_hist[mid - 1] > before) h2 = mid; else l2 = mid + 1; }
-          c1 = l2;
-        }
-        tot = (int)s_hist[c1 - 1] - before;
-        bef = before;
+      // (prefix sums are monotone: a boundary is a count of bins, found by all lanes together)
+      const int bef = c0 > 0 ? (int)s_hist[c0 - 1] : 0;
+      const int budget = bef + min(LW_CS, max(1, (int)((float)LW_CH / ratio)));   // never more than the staging buffer
+      int nA = 0, nB = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int bq = lane * 8 + q;
+        const int pv = (int)s_hist[bq];
+        const bool in = bq >= c0 && bq < LW_BINS;
+        nA += (in && pv <= budget) ? 1 : 0;     // bins whose cumulative count still fits the budget
+        nB += (in && pv <= bef) ? 1 : 0;        // leading empty bins
       }
-      c1 = __shfl_sync(0xffffffffu, c1, 0); tot = __shfl_sync(0xffffffffu, tot, 0); bef = __shfl_sync(0xffffffffu, bef, 0);
+      nA = __reduce_add_sync(0xffffffffu, nA);
+      nB = __reduce_add_sync(0xffffffffu, nB);
+      int c1 = c0 + nA;
+      if (nA <= nB) c1 = min(LW_BINS, c0 + nB + 1);   // the next non-empty bin alone exceeds the budget: take it alone
+      const int tot = (int)s_hist[c1 - 1] - bef;
       if (tot == 0) break;                 // nothing left
       if (tot > LW_CS) { to_fallback = true; break; }   // one bin alone overflows the staging buffer
       const int cntE = tot;               // the chunk is the contiguous id range [bef, bef + tot)
@@ -1087,9 +1060,15 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
             merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
           }
         }
-        __syncwarp();
-        refresh();
-        if (nseg <= 1 || below || alive <= 1) done = true;
+        float mt = 3.0e38f;
+        for (int v = lane; v < n; v += 32) {
+          const int sz = (int)s_size[v];
+          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        minthr = mt;
+        if (nseg <= 1 || below) done = true;
       }
       ratio = fminf(1.0f, fmaxf(1.25f * (float)(kept + 2) / (float)(tot + 2), 1.0f / 256.0f));
       c0 = c1;
