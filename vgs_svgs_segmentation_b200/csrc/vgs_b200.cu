@@ -92,12 +92,15 @@ struct vgs_context {
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
   DBuf stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
   int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
+  int lw_chunk = LW_CH;             // target useful entries per chunk (tuning knob VGS_B200_LW_CHUNK)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
 
   vgs_timings tm{};
   cudaEvent_t ev[32] = {};
+  float* tm_slot[16] = {};
+  unsigned tm_pending = 0;
 
   vgs_status fail(vgs_status s, const std::string& m) { err = m; return s; }
   vgs_status fail_cuda(cudaError_t e, const char* what, int line) {
@@ -245,20 +248,32 @@ vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* 
   return VGS_OK;
 }
 
+// Stage timers: CUDA events recorded on the handle's stream WITHOUT a host synchronisation (a sync per
+// stage costs a host round trip and exposes the step to host scheduling noise); the elapsed times are
+// read when somebody asks for them (vgs_stage_timings, end of vgs_run), after one synchronisation.
 struct StageTimer {
-  vgs_handle h; float* slot; cudaEvent_t a, b;
-  StageTimer(vgs_handle h_, float* slot_, int idx) : h(h_), slot(slot_) {
+  vgs_handle h; int idx; cudaEvent_t a, b;
+  StageTimer(vgs_handle h_, float* slot_, int idx_) : h(h_), idx(idx_) {
     a = h->ev[idx * 2]; b = h->ev[idx * 2 + 1];
+    h->tm_slot[idx] = slot_;
     cudaEventRecord(a, h->stream);
   }
   void stop() {
     cudaEventRecord(b, h->stream);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    *slot = ms;
+    h->tm_pending |= 1u << idx;
   }
 };
+
+void resolve_timers(vgs_handle h) {
+  if (!h->tm_pending) return;
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 15; i++)
+    if ((h->tm_pending >> i) & 1u) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, h->ev[i * 2], h->ev[i * 2 + 1]) == cudaSuccess && h->tm_slot[i]) *h->tm_slot[i] = ms;
+    }
+  h->tm_pending = 0;
+}
 
 std::vector<int4> make_stencil(float voxel_size_f, float graph_size_f) {
   // integer lattice offsets whose ideal centre distance could pass the float test dist2 < (float)(r*r)
@@ -310,6 +325,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   if (const char* e_nw = getenv("VGS_B200_NO_WARP_KERNEL")) h->use_warp_kernel = (e_nw[0] == '1') ? 0 : 1;
+  if (const char* e_ch = getenv("VGS_B200_LW_CHUNK")) { int v = atoi(e_ch); if (v >= 1 && v <= LW_CS) h->lw_chunk = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
   {
     auto optin = [&](const void* fn, size_t want_total) -> cudaError_t {
@@ -363,6 +379,7 @@ vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_
   h->n = n; h->stride = stride_bytes / 4;
   h->voxelized = h->have_units = h->have_features = h->have_adj = h->have_segments = false;
   h->d_labels = nullptr;
+  h->tm_pending = 0;
   h->tm = vgs_timings{};
   if (on_device) { h->d_xyz = xyz; }
   else {
@@ -810,7 +827,10 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
   // ---- stage 4+5a: local graphs ----
   {
     StageTimer t(h, &h->tm.graph_ms, 5);
-    CK(h->class_count.reserve(256)); CK(h->class_list.reserve((size_t)N_CLASSES * nu * 4));
+    CK(h->class_count.reserve(256));
+    CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
+    CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
+    LAUNCH(k_class_init, (unsigned)cdiv(nu, 256), 256, 0, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), nu);
     unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
     float* d_wempty = h->small.as<float>() + 160;
     uint32_t* d_maxn = h->class_count.as<uint32_t>() + 16;
@@ -827,7 +847,15 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     }
     LAUNCH(k_bin_classes, (unsigned)cdiv((last - first) * 32 + 1, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
            h->uflags.as<uint8_t>(), nu, first, last, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
-           d_maxn, h->class_list.as<uint32_t>(), d_stats, d_need);
+           d_maxn, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), d_stats, d_need);
+    // class lists ordered by unit id (deterministic, and consecutive CTAs work on neighbouring voxels, which
+    // keeps the pair-table rows they share in L2): one stable 8-bit radix pass on (class, unit id)
+    uint64_t* cls_keys; uint32_t* cls_sorted;
+    {
+      vgs_status s_ = radix_sort(h, nu, 8, &cls_keys, &cls_sorted, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(),
+                                 h->cvalsA.as<uint32_t>(), h->cvalsB.as<uint32_t>());
+      if (s_) return s_;
+    }
     uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
     unsigned long long stats[3];
     CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
@@ -890,24 +918,27 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     }
     uint32_t max_n_all = 0;
     for (int c = 0; c < N_CLASSES; c++) max_n_all = std::max(max_n_all, cc[c] ? cmaxn[c] : 0u);
+    size_t class_off[N_CLASSES + 1];
+    class_off[0] = 0;
+    for (int c = 0; c < N_CLASSES; c++) class_off[c + 1] = class_off[c] + cc[c];
     for (int c = 0; c < N_CLASSES; c++) {
       if (!cc[c]) continue;
       const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
       if (use_warp && CLASS_N_HOST[c] <= 128) {
         const size_t slice = lw_slice_bytes(ncap, mcap);
-        const uint32_t* wlist = h->class_list.as<uint32_t>() + (size_t)c * nu;
+        const uint32_t* wlist = cls_sorted + class_off[c];
         unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
         scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
         LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->uflags.as<uint8_t>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
-               h->fallback.as<uint32_t>(), d_fb_count, scratch, d_dbg);
+               h->fallback.as<uint32_t>(), d_fb_count, scratch, h->lw_chunk, d_dbg);
         continue;
       }
       size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (2 * LG_BINS + 2) * 4 + 64;
       const int bucketed = (smem + (size_t)mcap * 2 <= 220 * 1024) ? 1 : 0;   // bin-ordered pool index if it fits
       if (bucketed) smem += (size_t)mcap * 2;
-      const uint32_t* list = h->class_list.as<uint32_t>() + (size_t)c * nu;
+      const uint32_t* list = cls_sorted + class_off[c];
 #define LG(TT, CC)                                                                                                  \
   do {                                                                                                              \
     auto kfn = k_local_graph2<TT, CC>;                                                                              \
@@ -1055,6 +1086,7 @@ vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, i
     StageTimer t2(h, &h->tm.d2h_ms, 10);
     CK(cudaMemcpyAsync(labels, d_out, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
     t2.stop();
+    CK(cudaStreamSynchronize(h->stream));   // the caller's host buffer is valid on return
   }
   return VGS_OK;
 }
@@ -1113,6 +1145,7 @@ vgs_status vgs_run(vgs_handle h, const vgs_params* p, int32_t* labels, int on_de
   cudaEventRecord(b, h->stream);
   cudaEventSynchronize(b);
   cudaEventElapsedTime(&h->tm.total_ms, a, b);
+  resolve_timers(h);
   return VGS_OK;
 }
 
@@ -1128,6 +1161,8 @@ vgs_status vgs_get_counts(vgs_handle h, vgs_counts* out) {
 
 vgs_status vgs_stage_timings(vgs_handle h, vgs_timings* out) {
   if (!h || !out) return VGS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  resolve_timers(h);
   *out = h->tm;
   out->kernel_launches = h->launches;
   return VGS_OK;

@@ -342,7 +342,8 @@ __global__ void k_wempty(PairParams pp, float* __restrict__ out) {
 __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
                                                    const uint8_t* __restrict__ uflags, int64_t nu, int64_t first, int64_t last, float cut,
                                                    int svgs, const float* __restrict__ wempty, uint32_t* __restrict__ class_count,
-                                                   uint32_t* __restrict__ class_maxn, uint32_t* __restrict__ class_list,
+                                                   uint32_t* __restrict__ class_maxn, uint64_t* __restrict__ class_key,
+                                                   uint32_t* __restrict__ class_val,
                                                    unsigned long long* __restrict__ stats /* [0]=sum n(n-1) [1]=max n [2]=overflow */,
                                                    uint8_t* __restrict__ need_rows) {
   const int lane = threadIdx.x & 31;
@@ -371,8 +372,14 @@ __global__ void __launch_bounds__(128) k_bin_classes(const uint32_t* __restrict_
   if (c >= N_CLASSES || n > 255) { atomicAdd(&stats[2], 1ull); return; }
   atomicAdd(&stats[0], (unsigned long long)n * (unsigned long long)(n - 1));
   atomicMax(&class_maxn[c], (uint32_t)n);
-  uint32_t pos = atomicAdd(&class_count[c], 1u);
-  class_list[(int64_t)c * nu + pos] = (uint32_t)u;
+  atomicAdd(&class_count[c], 1u);
+  class_key[u] = (uint64_t)c;      // one stable radix pass on this key orders every class list by unit id
+  (void)class_val;
+}
+// (key, value) = (255 = not in any class, unit id) for every unit
+__global__ void __launch_bounds__(256) k_class_init(uint64_t* __restrict__ class_key, uint32_t* __restrict__ class_val, int64_t nu) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < nu) { class_key[u] = 255ull; class_val[u] = (uint32_t)u; }
 }
 
 // ---- stage 4 (VGS, cached): every unordered pair of USED voxels closer than two stencil radii is
@@ -817,7 +824,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
                                                                   int r2, const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
                                                                   int32_t* __restrict__ conn_idx, uint32_t* __restrict__ fallback,
                                                                   uint32_t* __restrict__ fallback_count,
-                                                                  unsigned short* __restrict__ scratch,
+                                                                  unsigned short* __restrict__ scratch, int chunk_target,
                                                                   unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -967,7 +974,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
       // --- chunk boundary: bins [c0, c1) with about LW_CH / ratio entries ---
       // (prefix sums are monotone: a boundary is a count of bins, found by all lanes together)
       const int bef = c0 > 0 ? (int)s_hist[c0 - 1] : 0;
-      const int budget = bef + min(LW_CS, max(1, (int)((float)LW_CH / ratio)));   // never more than the staging buffer
+      const int budget = bef + min(LW_CS, max(1, (int)((float)chunk_target / ratio)));   // never more than the staging buffer
       int nA = 0, nB = 0;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
