@@ -38,7 +38,15 @@ template <class PointT> struct PointCloud {
   std::size_t size() const { return points.size(); }
   void clear() { points.clear(); width = height = 0; }
 };
-struct PolygonMesh { typedef std::shared_ptr<PolygonMesh> Ptr; };
+struct Vertices { std::vector<std::uint32_t> vertices; };
+// pcl::PolygonMesh keeps its vertices as a PCLPointCloud2 blob; the shim keeps the typed cloud that
+// toPCLPointCloud2 would have serialised (the draw* members only ever put XYZRGB vertices in it).
+struct PolygonMesh {
+  typedef std::shared_ptr<PolygonMesh> Ptr;
+  PointCloud<PointXYZRGB> cloud;
+  std::vector<Vertices> polygons;
+};
+inline void toPCLPointCloud2(const PointCloud<PointXYZRGB>& src, PointCloud<PointXYZRGB>& dst) { dst = src; }
 }  // namespace pcl
 #endif
 

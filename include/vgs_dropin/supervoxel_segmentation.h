@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../vgs_b200.h"
+#include <algorithm>
+#include "mesh_export.h"
 #include "pcl_shim.h"
 
 namespace pcl {
@@ -116,6 +118,69 @@ class SuperVoxelBasedSegmentation {
       }
     }
   }
+  // ---- display exports (SV.h:424-611); colours are vgs_dropin::color_of(index), see mesh_export.h ----
+
+  // SV.h:424: one stick centroid -> centroid + seed_resolution * normal per supervoxel with more than points_min points
+  void drawNormofVoxels(pcl::PolygonMesh::Ptr output_mesh) {
+    const std::vector<float> rec = vgs_dropin::fetch<float>(h_, VGS_BLOB_RECORDS);
+    const std::vector<int64_t> off = vgs_dropin::fetch<int64_t>(h_, VGS_BLOB_UNIT_OFFSETS);
+    pcl::PointCloud<pcl::PointXYZRGB> verts;
+    uint8_t r, g, b;
+    vgs_dropin::color_of(0u, r, g, b);
+    for (int64_t i = 0; i + 1 < (int64_t)off.size(); i++) {
+      if (!((int)(off[i + 1] - off[i]) > supervoxel_point_min_)) continue;
+      const float* c = &rec[16 * i];
+      const float* nrm = c + 3;
+      verts.points.push_back(vgs_dropin::vertex(c[0], c[1], c[2], r, g, b));
+      verts.points.push_back(vgs_dropin::vertex(c[0] + seed_resolution_ * nrm[0], c[1] + seed_resolution_ * nrm[1],
+                                                c[2] + seed_resolution_ * nrm[2], r, g, b));
+      // the reference indexes the two vertices with the SUPERVOXEL id i (SV.h:489), which points past the
+      // vertex array as soon as one supervoxel was skipped; the drop-in indexes the stick it just wrote
+      const uint32_t k = (uint32_t)(verts.points.size() / 2 - 1);
+      vgs_dropin::push_poly(*output_mesh, k * 2, k * 2 + 1, k * 2);
+    }
+    pcl::toPCLPointCloud2(verts, output_mesh->cloud);
+  }
+  // SV.h:500: every point, one colour per octree voxel, voxels in leaf-iterator order (descending x-major Morton key)
+  void drawColorMapofPointsinVoxels(pcl::PointCloud<pcl::PointXYZRGB>::Ptr output_cloud) {
+    const std::vector<uint32_t> key = vgs_dropin::fetch<uint32_t>(h_, VGS_BLOB_POINT_KEY);
+    std::vector<std::pair<uint64_t, int32_t>> order;
+    order.reserve(key.size() / 3);
+    for (size_t p = 0; p < key.size() / 3; p++) {
+      if (key[3 * p] == 0xFFFFFFFFu) continue;   // non-finite point: never inserted into the octree
+      uint64_t code = 0;
+      for (int bit = 20; bit >= 0; bit--)
+        code = (code << 3) | (uint64_t)(((key[3 * p] >> bit) & 1u) << 2 | ((key[3 * p + 1] >> bit) & 1u) << 1 | ((key[3 * p + 2] >> bit) & 1u));
+      order.emplace_back(~code, (int32_t)p);
+    }
+    std::sort(order.begin(), order.end());
+    uint32_t voxel = 0;
+    for (size_t j = 0; j < order.size(); j++) {
+      if (j && order[j].first != order[j - 1].first) voxel++;
+      uint8_t r, g, b;
+      vgs_dropin::color_of(voxel, r, g, b);
+      const pcl::PointXYZ& q = points_cloud_->points[order[j].second];
+      output_cloud->points.push_back(vgs_dropin::vertex(q.x, q.y, q.z, r, g, b));
+    }
+    output_cloud->width = (uint32_t)output_cloud->points.size();
+    output_cloud->height = 1;
+  }
+  // SV.h:560: every labelled point, one colour per supervoxel, supervoxels in id order
+  void drawColorMapofPointsinSupervoxels(pcl::PointCloud<pcl::PointXYZRGB>::Ptr output_cloud) {
+    const std::vector<int64_t> off = vgs_dropin::fetch<int64_t>(h_, VGS_BLOB_UNIT_OFFSETS);
+    const std::vector<int32_t> pts = vgs_dropin::fetch<int32_t>(h_, VGS_BLOB_UNIT_POINTS);
+    for (int64_t i = 0; i + 1 < (int64_t)off.size(); i++) {
+      uint8_t r, g, b;
+      vgs_dropin::color_of((uint32_t)i, r, g, b);
+      for (int64_t j = off[i]; j < off[i + 1]; j++) {
+        const pcl::PointXYZ& q = points_cloud_->points[pts[j]];
+        output_cloud->points.push_back(vgs_dropin::vertex(q.x, q.y, q.z, r, g, b));
+      }
+    }
+    output_cloud->width = (uint32_t)output_cloud->points.size();
+    output_cloud->height = 1;
+  }
+
   std::vector<int> getPointLabels() {
     std::vector<int> lab((size_t)points_num_);
     ck(vgs_get_point_labels(h_, 0, lab.data(), 0));

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../vgs_b200.h"
+#include "mesh_export.h"
 #include "pcl_shim.h"
 
 namespace pcl {
@@ -115,6 +116,78 @@ class VoxelBasedSegmentation {
     }
   }
 
+  // ---- display exports (VS.h:424-945, 1016-1104).  Voxels are visited in voxel-id order (= the leaf
+  // iterator's order); colours are vgs_dropin::color_of(voxel or cluster index), see mesh_export.h. ----
+
+  // VS.h:424: the points of every used voxel (more than points_min points), one colour per voxel
+  void drawColorMapofPointsinVoxels(pcl::PointCloud<pcl::PointXYZRGB>::Ptr output_cloud) {
+    const VoxelTable t = voxelTable();
+    for (int64_t v = 0; v < t.n; v++) {
+      if (!(t.size(v) > voxel_points_min_)) continue;
+      uint8_t r, g, b;
+      vgs_dropin::color_of((uint32_t)v, r, g, b);
+      for (int64_t j = t.off[v]; j < t.off[v + 1]; j++) {
+        const pcl::PointXYZ& q = points_cloud_->points[t.pts[j]];
+        output_cloud->points.push_back(vgs_dropin::vertex(q.x, q.y, q.z, r, g, b));
+      }
+    }
+    output_cloud->width = (uint32_t)output_cloud->points.size();
+    output_cloud->height = 1;
+  }
+  // VS.h:510: one coloured box (8 vertices, 12 triangles) per used voxel
+  void drawColorMapofVoxels(pcl::PolygonMesh::Ptr output_mesh) { boxesOfUsedVoxels(*output_mesh, false); }
+  // VS.h:794: the same boxes as wire frames (12 degenerate triangles a-b-a per box)
+  void drawFrameMapofVoxels(pcl::PolygonMesh::Ptr output_mesh) { boxesOfUsedVoxels(*output_mesh, true); }
+  // VS.h:653: boxes of the used voxels of every cluster, one colour per cluster, clusters in cluster order
+  void drawColorMapofClusteredVoxels(pcl::PolygonMesh::Ptr output_mesh) {
+    const VoxelTable t = voxelTable();
+    const std::vector<int32_t> root = vgs_dropin::fetch<int32_t>(h_, VGS_BLOB_UNIT_ROOT);
+    const std::vector<float> ctr = vgs_dropin::fetch<float>(h_, VGS_BLOB_UNIT_CENTER);   // voxel_centers_ (VS.h:690)
+    // cluster m = m-th distinct root in ascending order; members in ascending voxel id
+    std::vector<int32_t> cluster_of_root((size_t)t.n, -1);
+    int32_t nc = 0;
+    for (int64_t v = 0; v < t.n; v++) if (root[v] == v) cluster_of_root[v] = nc++;
+    std::vector<int64_t> start((size_t)nc + 1, 0);
+    for (int64_t v = 0; v < t.n; v++) start[cluster_of_root[root[v]] + 1]++;
+    for (int32_t c = 0; c < nc; c++) start[c + 1] += start[c];
+    std::vector<int32_t> member((size_t)t.n);
+    { std::vector<int64_t> cur(start.begin(), start.end() - 1);
+      for (int64_t v = 0; v < t.n; v++) member[cur[cluster_of_root[root[v]]]++] = (int32_t)v; }
+    pcl::PointCloud<pcl::PointXYZRGB> verts;
+    uint32_t box = 0;
+    for (int32_t c = 0; c < nc; c++) {
+      uint8_t r, g, b;
+      vgs_dropin::color_of((uint32_t)c, r, g, b);
+      for (int64_t j = start[c]; j < start[c + 1]; j++) {
+        const int32_t v = member[j];
+        if (!(t.size(v) > voxel_points_min_)) continue;   // voxel_used_ (VS.h:693)
+        vgs_dropin::push_corners(verts, pcl::PointXYZ(ctr[3 * v], ctr[3 * v + 1], ctr[3 * v + 2]), voxel_resolution_, r, g, b);
+        vgs_dropin::push_box_faces(*output_mesh, box++);
+      }
+    }
+    pcl::toPCLPointCloud2(verts, output_mesh->cloud);
+  }
+  // VS.h:1016: one stick centre -> centre + voxel_resolution * normal per used voxel (degenerate triangle 0-1-0)
+  void drawNormofVoxels(pcl::PolygonMesh::Ptr output_mesh) {
+    const VoxelTable t = voxelTable();
+    const std::vector<float> rec = vgs_dropin::fetch<float>(h_, VGS_BLOB_RECORDS);
+    pcl::PointCloud<pcl::PointXYZRGB> verts;
+    uint8_t r, g, b;
+    vgs_dropin::color_of(0u, r, g, b);
+    uint32_t i = 0;
+    for (int64_t v = 0; v < t.n; v++) {
+      if (!(t.size(v) > voxel_points_min_)) continue;
+      const pcl::PointXYZ c = vgs_dropin::leaf_center(&t.key[3 * v], resolution_, t.box);
+      const float* nrm = &rec[16 * v + 3];
+      verts.points.push_back(vgs_dropin::vertex(c.x, c.y, c.z, r, g, b));
+      verts.points.push_back(vgs_dropin::vertex(c.x + voxel_resolution_ * nrm[0], c.y + voxel_resolution_ * nrm[1],
+                                                c.z + voxel_resolution_ * nrm[2], r, g, b));
+      vgs_dropin::push_poly(*output_mesh, i * 2, i * 2 + 1, i * 2);
+      i++;
+    }
+    pcl::toPCLPointCloud2(verts, output_mesh->cloud);
+  }
+
   // canonical per-point labels (not in the reference: smallest point index of the point's cluster)
   std::vector<int> getPointLabels() {
     std::vector<int> lab((size_t)points_num_);
@@ -124,6 +197,37 @@ class VoxelBasedSegmentation {
   vgs_handle handle() { return h_; }
 
  private:
+  struct VoxelTable {   // voxel-id order: keys, point lists, PCL's bounding box
+    int64_t n = 0;
+    std::vector<uint32_t> key;
+    std::vector<int64_t> off;
+    std::vector<int32_t> pts;
+    double box[6];
+    int size(int64_t v) const { return (int)(off[v + 1] - off[v]); }
+  };
+  VoxelTable voxelTable() {
+    VoxelTable t;
+    ck(vgs_voxel_count(h_, &t.n));
+    t.key = vgs_dropin::fetch<uint32_t>(h_, VGS_BLOB_UNIT_KEY);
+    t.off = vgs_dropin::fetch<int64_t>(h_, VGS_BLOB_UNIT_OFFSETS);
+    t.pts = vgs_dropin::fetch<int32_t>(h_, VGS_BLOB_UNIT_POINTS);
+    ck(vgs_get_bounding_box(h_, t.box));
+    return t;
+  }
+  void boxesOfUsedVoxels(pcl::PolygonMesh& mesh, bool frame) {
+    const VoxelTable t = voxelTable();
+    pcl::PointCloud<pcl::PointXYZRGB> verts;
+    uint32_t i = 0;
+    for (int64_t v = 0; v < t.n; v++) {
+      if (!(t.size(v) > voxel_points_min_)) continue;
+      uint8_t r, g, b;
+      vgs_dropin::color_of((uint32_t)v, r, g, b);
+      vgs_dropin::push_corners(verts, vgs_dropin::leaf_center(&t.key[3 * v], resolution_, t.box), voxel_resolution_, r, g, b);
+      if (frame) vgs_dropin::push_box_edges(mesh, i); else vgs_dropin::push_box_faces(mesh, i);
+      i++;
+    }
+    pcl::toPCLPointCloud2(verts, mesh.cloud);
+  }
   void ck(vgs_status s) { if (s != VGS_OK) throw std::runtime_error(std::string("libvgs_b200: ") + vgs_last_error(h_)); }
   vgs_handle h_ = nullptr;
   double resolution_;

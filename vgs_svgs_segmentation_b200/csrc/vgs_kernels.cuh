@@ -817,7 +817,12 @@ __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
+#if VGS_AB_ALT == 3
+#define LW_MIN_CTAS , 10
+#else
+#define LW_MIN_CTAS
+#endif
+__global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
                                                                   const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
                                                                   const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ key3,
                                                                   float k, int ncap, int mcap, const float2* __restrict__ table, int half,
@@ -923,6 +928,32 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
     {
       int ia = 0, rem = lane, p = lane;    // rem = offset inside row ia, row length nv-1-ia
       while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+#if VGS_AB_ALT == 2 || VGS_AB_ALT == 3
+      // two pairs in flight per lane: the table gathers are dependent-latency bound (ncu: long_scoreboard)
+      while (ia < nv - 1) {
+        const int a0 = s_ul[ia], c0 = s_ul[ia + 1 + rem];
+        rem += 32;
+        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+        const bool second = ia < nv - 1;
+        int a1 = a0, c1 = c0;
+        if (second) { a1 = s_ul[ia]; c1 = s_ul[ia + 1 + rem]; }
+        float w_ab, w_ba, x_ab, x_ba;
+        fetch(a0, c0, w_ab, w_ba);
+        fetch(a1, c1, x_ab, x_ba);
+        int b0 = 255, b1 = 255, d0 = 255, d1 = 255;
+        if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
+        if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
+        reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
+        if (second) {
+          if (x_ab > lb) { d0 = min(LW_BINS - 1, (int)((1.0f - x_ab) * scale)); atomicAdd(&s_hist[d0], 1u); }
+          if (x_ba > lb) { d1 = min(LW_BINS - 1, (int)((1.0f - x_ba) * scale)); atomicAdd(&s_hist[d1], 1u); }
+          reinterpret_cast<unsigned short*>(gbins)[p + 32] = (unsigned short)(d0 | (d1 << 8));
+          rem += 32;
+          while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+        }
+        p += 64;
+      }
+#else
       while (ia < nv - 1) {
         float w_ab, w_ba;
         fetch(s_ul[ia], s_ul[ia + 1 + rem], w_ab, w_ba);
@@ -934,6 +965,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32) k_local_graph_warp(const uint32
         rem += 32; p += 32;
         while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
+#endif
     }
     __syncwarp();
     {   // inclusive prefix sums over the 256 counters; cursors = exclusive starts
