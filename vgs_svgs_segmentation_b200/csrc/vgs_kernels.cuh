@@ -810,6 +810,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
 constexpr int LW_CS = 256;      // staging capacity (entries) per warp
 constexpr int LW_CH = 28;       // target number of USEFUL entries per chunk (one per lane: register sort)
 constexpr int LW_WARPS = 4;     // units per CTA
+constexpr int LW_ILP = 2;       // table gathers in flight per lane in pass A (4 measured the same)
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   (void)mcap;   // the bin-ordered entry list lives in a global scratch slice (written once, read once: L2)
@@ -817,12 +818,8 @@ __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   return (b + 15) & ~(size_t)15;
 }
 
-#if VGS_AB_ALT == 3
-#define LW_MIN_CTAS , 10
-#else
-#define LW_MIN_CTAS
-#endif
-__global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
+// min CTAs per SM = 8 caps the kernel at 64 registers; 48 registers / 10 CTAs measured 8 % slower, 6-7 CTAs the same
+__global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uint32_t* __restrict__ list, uint32_t nlist,
                                                                   const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
                                                                   const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ key3,
                                                                   float k, int ncap, int mcap, const float2* __restrict__ table, int half,
@@ -928,44 +925,37 @@ __global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(
     {
       int ia = 0, rem = lane, p = lane;    // rem = offset inside row ia, row length nv-1-ia
       while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
-#if VGS_AB_ALT == 2 || VGS_AB_ALT == 3
-      // two pairs in flight per lane: the table gathers are dependent-latency bound (ncu: long_scoreboard)
+      // LW_ILP pairs in flight per lane: the table gathers are dependent-latency bound (ncu: long_scoreboard)
       while (ia < nv - 1) {
-        const int a0 = s_ul[ia], c0 = s_ul[ia + 1 + rem];
-        rem += 32;
-        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
-        const bool second = ia < nv - 1;
-        int a1 = a0, c1 = c0;
-        if (second) { a1 = s_ul[ia]; c1 = s_ul[ia + 1 + rem]; }
-        float w_ab, w_ba, x_ab, x_ba;
-        fetch(a0, c0, w_ab, w_ba);
-        fetch(a1, c1, x_ab, x_ba);
-        int b0 = 255, b1 = 255, d0 = 255, d1 = 255;
-        if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
-        if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
-        reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
-        if (second) {
-          if (x_ab > lb) { d0 = min(LW_BINS - 1, (int)((1.0f - x_ab) * scale)); atomicAdd(&s_hist[d0], 1u); }
-          if (x_ba > lb) { d1 = min(LW_BINS - 1, (int)((1.0f - x_ba) * scale)); atomicAdd(&s_hist[d1], 1u); }
-          reinterpret_cast<unsigned short*>(gbins)[p + 32] = (unsigned short)(d0 | (d1 << 8));
-          rem += 32;
-          while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+        int va[LW_ILP], vc[LW_ILP];
+        bool ok[LW_ILP];
+#pragma unroll
+        for (int q = 0; q < LW_ILP; q++) {
+          ok[q] = ia < nv - 1;
+          va[q] = 0; vc[q] = 0;
+          if (ok[q]) {
+            va[q] = s_ul[ia]; vc[q] = s_ul[ia + 1 + rem];
+            rem += 32;
+            while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+          }
         }
-        p += 64;
+        float wf[LW_ILP], wr[LW_ILP];
+#pragma unroll
+        for (int q = 0; q < LW_ILP; q++) {
+          wf[q] = 0.f; wr[q] = 0.f;
+          if (ok[q]) fetch(va[q], vc[q], wf[q], wr[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < LW_ILP; q++) {
+          if (ok[q]) {
+            int b0 = 255, b1 = 255;
+            if (wf[q] > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - wf[q]) * scale)); atomicAdd(&s_hist[b0], 1u); }
+            if (wr[q] > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - wr[q]) * scale)); atomicAdd(&s_hist[b1], 1u); }
+            reinterpret_cast<unsigned short*>(gbins)[p + 32 * q] = (unsigned short)(b0 | (b1 << 8));
+          }
+        }
+        p += 32 * LW_ILP;
       }
-#else
-      while (ia < nv - 1) {
-        float w_ab, w_ba;
-        fetch(s_ul[ia], s_ul[ia + 1 + rem], w_ab, w_ba);
-        int b0 = 255, b1 = 255;
-        if (w_ab > lb) { b0 = min(LW_BINS - 1, (int)((1.0f - w_ab) * scale)); atomicAdd(&s_hist[b0], 1u); }
-        if (w_ba > lb) { b1 = min(LW_BINS - 1, (int)((1.0f - w_ba) * scale)); atomicAdd(&s_hist[b1], 1u); }
-        reinterpret_cast<unsigned short*>(gbins)[p] = (unsigned short)(b0 | (b1 << 8));
-
-        rem += 32; p += 32;
-        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
-      }
-#endif
     }
     __syncwarp();
     {   // inclusive prefix sums over the 256 counters; cursors = exclusive starts
@@ -986,15 +976,18 @@ __global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(
     {
       int ia = 0, rem = lane, p = lane;
       while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
-      while (ia < nv - 1) {
+      const int np = nv * (nv - 1) / 2;
+      int bb_n = p < np ? (int)reinterpret_cast<const unsigned short*>(gbins)[p] : 0;
+      while (p < np) {   // the parked bins are read one step ahead of their use
         const int ib = ia + 1 + rem;
-        const int bb = reinterpret_cast<const unsigned short*>(gbins)[p];
-        const int b0 = bb & 255, b1 = bb >> 8;
+        const int bb = bb_n;
         const int code = (ia << 8) | (ib << 1);
+        rem += 32; p += 32;
+        bb_n = p < np ? (int)reinterpret_cast<const unsigned short*>(gbins)[p] : 0;
+        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
+        const int b0 = bb & 255, b1 = bb >> 8;
         if (b0 != 255) ids[atomicAdd(&s_cur[b0], 1u)] = (unsigned short)code;
         if (b1 != 255) ids[atomicAdd(&s_cur[b1], 1u)] = (unsigned short)(code | 1);
-        rem += 32; p += 32;
-        while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
       }
     }
     __syncwarp();
@@ -1028,25 +1021,30 @@ __global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(
       int kept = 0;
       float rw = -1.0f;
       int rf = 0xffff;
-      for (int x0 = 0; x0 < cntE; x0 += 32) {
-        const int x = x0 + lane;
-        bool keep = false;
-        float w = 0.f;
-        int f = 0;
-        if (x < cntE) {
-          const int e = ids[bef + x];
-          const int a = s_ul[e >> 8], b = s_ul[(e >> 1) & 127];
-          if (s_seg[a] != s_seg[b]) {
-            float w_ab, w_ba;
-            fetch(a, b, w_ab, w_ba);
-            keep = true;
-            // entry (row i, col j) = weight(idx[i] -> idx[j]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
-            if (e & 1) { w = w_ba; f = (a << 8) | b; } else { w = w_ab; f = (b << 8) | a; }
-          }
+      // phase 1: codes of the still-useful entries, compacted; the entry list is read one step ahead
+      {
+        int e_nxt = lane < cntE ? (int)ids[bef + lane] : 0;
+        for (int x0 = 0; x0 < cntE; x0 += 32) {
+          const int e = e_nxt;
+          const int xn = x0 + 32 + lane;
+          e_nxt = xn < cntE ? (int)ids[bef + xn] : 0;
+          const bool keep = (x0 + lane < cntE) && s_seg[s_ul[e >> 8]] != s_seg[s_ul[(e >> 1) & 127]];
+          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) C_f[kept + __popc(bal & lt)] = (unsigned short)e;
+          kept += __popc(bal);
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) { const int pos = kept + __popc(bal & lt); C_w[pos] = w; C_f[pos] = (unsigned short)f; }
-        kept += __popc(bal);
+      }
+      __syncwarp();
+      // phase 2: one dense gather of their weights (instead of one dependent gather per 32 visited entries).
+      // entry (row i, col j) = weight(idx[i] -> idx[j]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
+      for (int i = lane; i < kept; i += 32) {
+        const int e = C_f[i];
+        const int a = s_ul[e >> 8], b = s_ul[(e >> 1) & 127];
+        float w_ab, w_ba;
+        fetch(a, b, w_ab, w_ba);
+        float w; int f;
+        if (e & 1) { w = w_ba; f = (a << 8) | b; } else { w = w_ab; f = (b << 8) | a; }
+        if (kept <= 32) { rw = w; rf = f; } else { C_w[i] = w; C_f[i] = (unsigned short)f; }
       }
       __syncwarp();
       if (kept > 0) {
@@ -1055,7 +1053,6 @@ __global__ void __launch_bounds__(LW_WARPS * 32 LW_MIN_CTAS) k_local_graph_warp(
         bool below;
         if (kept <= 32) {
           // one entry per lane: bitonic sort across the warp with shuffles, (w desc, packed index asc)
-          if (lane < kept) { rw = C_w[lane]; rf = C_f[lane]; }
 #pragma unroll
           for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll

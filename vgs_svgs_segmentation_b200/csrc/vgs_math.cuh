@@ -251,14 +251,9 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
         // acos(-x) = pi - acos(x) is evaluated in double and rounded once, i.e. the same correctly
         // rounded float as (float)acos(-(double)x) (the 1-ulp double error of the subtraction moves a float
         // with probability ~2^-28) — two double acos per pair instead of four.
-#if VGS_AB_ALT == 1
-        a1 = (double)cr_acosf(c1d); a2 = (double)cr_acosf(c2d);
-        b1 = (double)cr_acosf(-c2d); b2 = (double)cr_acosf(-c1d);
-#else
         const double ad1 = acos((double)c1d), ad2 = acos((double)c2d);
         a1 = (double)(float)ad1; a2 = (double)(float)ad2;
         b1 = (double)(float)(3.14159265358979323846 - ad2); b2 = (double)(float)(3.14159265358979323846 - ad1);
-#endif
         ads1 = (double)cr_acosf(cds);
         ads2 = PI - ads1;
       }
