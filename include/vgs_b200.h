@@ -112,6 +112,16 @@ vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* label_per_poin
 /* Stand-in for createSupervoxels when no VCCS labels are supplied: one supervoxel per occupied cell of a
  * seed_size grid anchored at the octree origin (deterministic; NOT PCL's VCCS, whose parity is unpinned). */
 vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size);
+/* createSupervoxels SV.h:245-284: the supervoxel generator itself.  The reference calls PCL's VCCS
+ * (pcl::SupervoxelClustering(voxel_resolution, seed_resolution), setColor/Spatial/NormalImportance SV.h:269-271,
+ * extract SV.h:277, refineSupervoxels(5) SV.h:278, getLabeledCloud / getMaxLabel SV.h:283-284).  This restates that
+ * algorithm with synchronous expansion rounds (deterministic, order independent); voxel_resolution is the size given
+ * to vgs_voxelize.  Third-party algorithm: parity with PCL is unpinned, the CPU restatement is oracle/vccs_oracle.cpp.
+ * Installs the labels exactly as vgs_set_supervoxel_labels(labels, getMaxLabel()) would. */
+vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float color_importance, float spatial_importance,
+                                     float normal_importance, int refine_iterations);
+/* labels currently installed (label_per_point may be NULL) and their max_label */
+vgs_status vgs_get_supervoxel_labels(vgs_handle h, int32_t* label_per_point, int32_t* max_label, int on_device);
 vgs_status vgs_unit_count(vgs_handle h, int64_t* n_units);              /* getSuperVoxelNum SV.h:118 */
 
 /* -- stage 2: calcualteVoxelCloudAttributes VS.h:290-369 / calcualteSupervoxelCloudAttributes SV.h:1238 -- */

@@ -3,10 +3,10 @@
 // test:138-160), forwarded to the C ABI of libvgs_b200.so in SVGS mode.
 //
 // The reference obtains its supervoxels from PCL's VCCS (pcl::SupervoxelClustering, SV.h:265-284 — third-party
-// code).  Here the per-point supervoxel labels are either supplied (setSupervoxelLabels: what
-// getLabeledCloud()/getMaxLabel() returned, SV.h:283-284) or, if none were supplied, made by the built-in
-// seed-grid stand-in (vgs_make_supervoxels_grid).  Everything downstream of the labels is the reference's
-// algorithm on the GPU.
+// code).  Here createSupervoxels runs the library's own restatement of that generator
+// (vgs_make_supervoxels_vccs) unless per-point labels were supplied (setSupervoxelLabels: what
+// getLabeledCloud()/getMaxLabel() returned, SV.h:283-284) or the plain seed grid was asked for
+// (useSeedGridSupervoxels).  Everything downstream of the labels is the reference's algorithm on the GPU.
 #pragma once
 #include <cstdint>
 #include <stdexcept>
@@ -78,16 +78,35 @@ class SuperVoxelBasedSegmentation {
     labels_ = label_per_point; max_label_ = max_label; have_labels_ = true;
   }
 
-  // SV.h:362.  sig_a/sig_b/sig_l are the VCCS colour/spatial/normal importances (SV.h:366-369): they only
-  // matter inside the supervoxel generator.
-  void segmentSupervoxelCloudWithGraphModel(float /*sig_a*/, float /*sig_b*/, float /*sig_l*/, float cut_thred, float sig_p,
-                                            float sig_n, float sig_o, float sig_e, float sig_c, float sig_w) {
+  // extension: one supervoxel per occupied seed_resolution grid cell instead of VCCS
+  void useSeedGridSupervoxels(bool on) { seed_grid_ = on; }
+
+  // SV.h:245 createSupervoxels: VCCS with the colour / spatial / normal importances set by
+  // segmentSupervoxelCloudWithGraphModel (SV.h:366-369) and refineSupervoxels(5) (SV.h:278)
+  void createSupervoxels() {
     if (have_labels_) {
       if ((int)labels_.size() != points_num_) throw std::runtime_error("setSupervoxelLabels: one label per input point expected");
       ck(vgs_set_supervoxel_labels(h_, labels_.data(), max_label_, 0));
-    } else {
+    } else if (seed_grid_) {
       ck(vgs_make_supervoxels_grid(h_, seed_resolution_));
+    } else {
+      ck(vgs_make_supervoxels_vccs(h_, seed_resolution_, color_impt_, spatial_impt_, normal_impt_, 5));
     }
+  }
+  // labels of the supervoxel generator (getLabeledCloud / getMaxLabel, SV.h:283-284); not available for the seed grid
+  std::vector<int> getSupervoxelLabels(int* max_label = nullptr) {
+    std::vector<int> lab((size_t)points_num_);
+    int32_t ml = 0;
+    ck(vgs_get_supervoxel_labels(h_, lab.data(), &ml, 0));
+    if (max_label) *max_label = ml;
+    return lab;
+  }
+
+  // SV.h:362.  sig_a/sig_b/sig_l are the VCCS colour/spatial/normal importances (SV.h:366-369).
+  void segmentSupervoxelCloudWithGraphModel(float sig_a, float sig_b, float sig_l, float cut_thred, float sig_p,
+                                            float sig_n, float sig_o, float sig_e, float sig_c, float sig_w) {
+    color_impt_ = sig_a; spatial_impt_ = sig_b; normal_impt_ = sig_l;
+    createSupervoxels();                                       // SV.h:372
     ck(vgs_compute_features(h_, supervoxel_point_min_));       // calcualteSupervoxelCloudAttributes SV.h:1238
     int64_t nsv = 0;
     ck(vgs_unit_count(h_, &nsv));
@@ -196,7 +215,8 @@ class SuperVoxelBasedSegmentation {
   PCXYZPtr points_cloud_;
   std::vector<int> labels_;
   int max_label_ = 0;
-  bool have_labels_ = false;
+  bool have_labels_ = false, seed_grid_ = false;
+  float color_impt_ = 0, spatial_impt_ = 0, normal_impt_ = 0;
   int points_num_ = 0, voxels_num_ = 0, supervoxels_num_ = 0, clusters_num_ = 0;
   int voxel_points_min_ = 0, supervoxel_voxel_min_ = 0, supervoxel_point_min_ = 0, supervoxel_adjacency_min_ = 0;
   float voxel_resolution_ = 0, seed_resolution_ = 0, graph_resolution_ = 0, adjacent_resolution_ = 0;

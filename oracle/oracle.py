@@ -81,6 +81,9 @@ def lib():
         L.vgso_features.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int64, C.c_void_p]
         L.vgso_cut.restype = C.c_int
         L.vgso_cut.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+        L.vgso_vccs.restype = C.c_int
+        L.vgso_vccs.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.POINTER(VccsParams), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -156,6 +159,36 @@ def features(xyz, **kw):
     out = np.zeros(14, np.float32)
     L.vgso_features(C.byref(p), x.ctypes.data, x.shape[0], out.ctypes.data)
     return out[:3], out[3:6], out[6:]
+
+
+class VccsParams(C.Structure):
+    _fields_ = [("voxel_res", C.c_float), ("seed_res", C.c_float), ("color_importance", C.c_float),
+                ("spatial_importance", C.c_float), ("normal_importance", C.c_float), ("refine_iterations", C.c_int32),
+                ("schedule", C.c_int32)]
+
+
+def vccs(xyz, voxel_res=0.05, seed_res=0.25, color_importance=0.0, spatial_importance=0.25, normal_importance=0.75,
+         refine_iterations=5, schedule=1, leaf_order=0) -> Result:
+    """Supervoxel generator restatement (vccs_oracle.cpp) on the oracle's own voxel table.  Defaults are
+    Task_File_SVGS.txt's.  Returns point_label, max_label, n_seeds, vox_normal (initial), vox_label and the voxel table."""
+    L = lib()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    # voxel table only: no voxel is "used" and the graph radius reaches nobody, so the later stages are empty
+    base = run(xyz, mode=0, voxel_size=voxel_res, graph_size=voxel_res * 0.5, points_min=2 ** 30, leaf_order=leaf_order, math=1)
+    V = int(base.stats["n_units"])
+    p = VccsParams(voxel_res, seed_res, color_importance, spatial_importance, normal_importance, refine_iterations, schedule)
+    key = np.ascontiguousarray(base.unit_key, dtype=np.uint32)
+    off = np.ascontiguousarray(base.unit_offsets, dtype=np.int64)
+    pts = np.ascontiguousarray(base.unit_points, dtype=np.int32)
+    origin = np.ascontiguousarray(base.bbox[:3], dtype=np.float64)
+    lab = np.zeros(xyz.shape[0], np.int32)
+    ml = C.c_int32(0)
+    vn = np.zeros((V, 3), np.float32)
+    vl = np.zeros(V, np.int32)
+    ns = L.vgso_vccs(xyz.ctypes.data, xyz.shape[0], xyz.shape[1], V, key.ctypes.data, off.ctypes.data, pts.ctypes.data,
+                     origin.ctypes.data, C.byref(p), lab.ctypes.data, C.byref(ml), vn.ctypes.data, vl.ctypes.data)
+    return Result(point_label=lab, max_label=int(ml.value), n_seeds=int(ns), vox_normal=vn, vox_label=vl, unit_key=key,
+                  unit_offsets=off, unit_points=pts, bbox=base.bbox, point_unit=base.point_unit)
 
 
 def cut(w, cut_thred):

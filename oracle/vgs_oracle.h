@@ -93,6 +93,22 @@ void vgso_features(const vgso_params* p, const float* xyz, int64_t n, float* out
  * members (local ids ascending) into out */
 int vgso_cut(float cut_thred, const float* w, int n, int32_t* out);
 
+/* ---- supervoxel generator (vccs_oracle.cpp): restatement of pcl::SupervoxelClustering as the reference
+ *      drives it in createSupervoxels (supervoxel_segmentation.h:245-284).  Third-party algorithm, PARITY
+ *      UNPINNED (see the header of vccs_oracle.cpp). ---- */
+typedef struct vgso_vccs_params {
+  float voxel_res, seed_res;                                   /* SV.h:266 */
+  float color_importance, spatial_importance, normal_importance; /* SV.h:269-271 */
+  int32_t refine_iterations;                                   /* SV.h:278: refineSupervoxels(5, ...) */
+  int32_t schedule; /* 0 = PCL's sequential expansion, 1 = synchronous rounds + fixed-point sums (the CUDA schedule) */
+} vgso_vccs_params;
+/* Inputs: the cloud and its voxel table as vgso_run (mode 0) produced it at voxel_res (keys, CSR of point lists in
+ * voxel-id order, origin = bounding-box minimum).  Outputs: label per point (0 = none), getMaxLabel(), optionally the
+ * initial voxel normals (V x 3) and the final label per voxel.  Returns the number of seeds. */
+int vgso_vccs(const float* xyz, int64_t n, int stride, int64_t n_voxels, const uint32_t* vox_key, const int64_t* vox_off,
+              const int32_t* vox_pts, const double* origin3, const vgso_vccs_params* p, int32_t* point_label,
+              int32_t* max_label, float* vox_normal, int32_t* vox_label);
+
 #ifdef __cplusplus
 }
 #endif

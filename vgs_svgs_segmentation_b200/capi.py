@@ -55,7 +55,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
              CONN1_IDX=(16, np.int32), ATTACH=(17, np.int32), UNIT_ROOT=(19, np.int32))
 
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
-            "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_unit_count",
+            "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_make_supervoxels_vccs", "vgs_get_supervoxel_labels", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_segment_partial", "vgs_adj_range", "vgs_export_connect", "vgs_import_connect",
             "vgs_segment_finish", "vgs_cluster_count", "vgs_get_point_labels",
             "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get"]
@@ -84,6 +84,8 @@ def load():
         L.vgs_get_voxel_centers.argtypes = [C.c_void_p, C.c_void_p]
         L.vgs_set_supervoxel_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.vgs_make_supervoxels_grid.argtypes = [C.c_void_p, C.c_float]
+        L.vgs_make_supervoxels_vccs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.vgs_get_supervoxel_labels.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int]
         L.vgs_unit_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.vgs_compute_features.argtypes = [C.c_void_p, C.c_int]
         L.vgs_find_adjacency.argtypes = [C.c_void_p, C.c_float]
@@ -162,6 +164,17 @@ class Handle:
 
     def make_supervoxels_grid(self, seed_size):
         self._ck(self.L.vgs_make_supervoxels_grid(self.h, seed_size))
+
+    def make_supervoxels_vccs(self, seed_resolution=0.25, color_importance=0.0, spatial_importance=0.25, normal_importance=0.75,
+                              refine_iterations=5):
+        self._ck(self.L.vgs_make_supervoxels_vccs(self.h, seed_resolution, color_importance, spatial_importance, normal_importance,
+                                                  refine_iterations))
+
+    def supervoxel_labels(self):
+        lab = np.empty(self.n, np.int32)
+        ml = C.c_int32(0)
+        self._ck(self.L.vgs_get_supervoxel_labels(self.h, lab.ctypes.data, C.byref(ml), 0))
+        return lab, int(ml.value)
 
     # --- stages ---
     def voxelize(self, voxel_size):

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "vgs_kernels.cuh"
+#include "vgs_vccs.cuh"
 
 using namespace vgs;
 
@@ -96,6 +97,12 @@ struct vgs_context {
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
+  // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
+  struct {
+    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, owner, owner2, dist, claim;
+    DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, cnt, tk, tv, tk2, tv2;
+  } vc;
+  int64_t vccs_seeds = 0;
 
   vgs_timings tm{};
   cudaEvent_t ev[32] = {};
@@ -566,6 +573,165 @@ vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
   h->have_units = true;
   h->units_external = true;
   h->have_features = h->have_adj = h->have_segments = false;
+  return VGS_OK;
+}
+
+// createSupervoxels (SV.h:245-284): pcl::SupervoxelClustering(voxel_resolution, seed_resolution) + extract +
+// refineSupervoxels(k), restated as data-parallel kernels (vgs_vccs.cuh; CPU restatement oracle/vccs_oracle.cpp,
+// schedule 1).  Installs the per-point labels and getMaxLabel() exactly as vgs_set_supervoxel_labels would.
+vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float color_importance, float spatial_importance,
+                                     float normal_importance, int refine_iterations) {
+  if (!h) return VGS_ERR_INVALID;
+  if (h->mode != VGS_MODE_SVGS) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: handle is not in SVGS mode");
+  if (!h->voxelized) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: call vgs_voxelize first (voxel_resolution = its voxel size)");
+  if (!(seed_resolution > 0) || refine_iterations < 0) return h->fail(VGS_ERR_INVALID, "vgs_make_supervoxels_vccs: bad seed_resolution / refine_iterations");
+  CK(cudaSetDevice(h->device));
+  auto& c = h->vc;
+  const int64_t n = h->n;
+  const int desc = h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0;
+  // --- voxel table of its own (the shared sort buffers are reused by the unit builders) ---
+  CK(c.keysA.reserve((size_t)n * 8)); CK(c.keysB.reserve((size_t)n * 8));
+  CK(c.valsA.reserve((size_t)n * 4)); CK(c.valsB.reserve((size_t)n * 4));
+  LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
+         c.keysA.as<uint64_t>(), c.valsA.as<uint32_t>(), (uint32_t*)nullptr);
+  uint64_t* ks; uint32_t* vs;
+  vgs_status s = radix_sort(h, n, 3 * h->depth + 1, &ks, &vs, c.keysA.as<uint64_t>(), c.keysB.as<uint64_t>(), c.valsA.as<uint32_t>(),
+                            c.valsB.as<uint32_t>());
+  if (s) return s;
+  int64_t V = 0;
+  s = build_units(h, ks, n, &V, &c.start, &c.key, &c.pos);
+  if (s) return s;
+  {
+    uint64_t lastkey = 0;
+    CK(cudaMemcpyAsync(&lastkey, c.key.as<uint64_t>() + (V - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (lastkey >> (3 * h->depth)) V--;   // the segment of the non-finite points
+  }
+  if (V != h->n_voxels) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: voxel table differs from vgs_voxelize's");
+  CK(c.xyz.reserve((size_t)V * 12 + 16)); CK(c.key3.reserve((size_t)V * 12 + 16)); CK(c.plain.reserve((size_t)V * 8 + 16));
+  CK(c.ptvox.reserve((size_t)n * 4)); CK(c.nb.reserve((size_t)V * 27 * 4)); CK(c.nrm.reserve((size_t)V * 12 + 16));
+  CK(c.owner.reserve((size_t)V * 4)); CK(c.owner2.reserve((size_t)V * 4)); CK(c.dist.reserve((size_t)V * 4)); CK(c.claim.reserve((size_t)V * 4));
+  CK(cudaMemsetAsync(c.ptvox.p, 0xff, (size_t)n * 4, h->stream));
+  LAUNCH(k_vccs_voxels, (unsigned)cdiv(V, 256), 256, 0, h->d_xyz, h->stride, vs, c.start.as<uint32_t>(), c.key.as<uint64_t>(), V, h->depth, desc,
+         c.xyz.as<float>(), c.key3.as<uint32_t>(), c.plain.as<uint64_t>(), c.ptvox.as<int32_t>());
+  uint64_t capacity = 64;
+  while (capacity < (uint64_t)V * 2) capacity <<= 1;
+  const uint64_t vmask = capacity - 1;
+  CK(c.tk.reserve(capacity * 8)); CK(c.tv.reserve(capacity * 4));
+  CK(cudaMemsetAsync(c.tk.p, 0xff, capacity * 8, h->stream));
+  LAUNCH(k_hash_insert, (unsigned)cdiv(V, 256), 256, 0, c.plain.as<uint64_t>(), V, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask);
+  LAUNCH(k_vccs_neighbours, (unsigned)cdiv(V * 27, 256), 256, 0, c.key3.as<uint32_t>(), V, h->depth, c.tk.as<unsigned long long>(),
+         c.tv.as<uint32_t>(), vmask, c.nb.as<int32_t>());
+  LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.nrm.as<float>());
+
+  // --- seeds ---
+  const double seed_d = (double)seed_resolution;
+  CK(c.ckA.reserve((size_t)V * 8)); CK(c.ckB.reserve((size_t)V * 8)); CK(c.cvA.reserve((size_t)V * 4)); CK(c.cvB.reserve((size_t)V * 4));
+  CK(c.cell3.reserve((size_t)V * 12 + 16));
+  LAUNCH(k_vccs_cell_keys, (unsigned)cdiv(V, 256), 256, 0, c.xyz.as<float>(), V, h->box.mn[0], h->box.mn[1], h->box.mn[2], seed_d,
+         c.ckA.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cell3.as<int32_t>());
+  uint64_t* cks; uint32_t* cvs;
+  s = radix_sort(h, V, 63, &cks, &cvs, c.ckA.as<uint64_t>(), c.ckB.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cvB.as<uint32_t>());
+  if (s) return s;
+  int64_t NC = 0;
+  s = build_units(h, cks, V, &NC, &c.cstart, &c.ckey, &c.cpos);
+  if (s) return s;
+  uint64_t ccap = 64;
+  while (ccap < (uint64_t)NC * 2) ccap <<= 1;
+  const uint64_t cmask = ccap - 1;
+  CK(c.tk2.reserve(ccap * 8)); CK(c.tv2.reserve(ccap * 4));
+  CK(cudaMemsetAsync(c.tk2.p, 0xff, ccap * 8, h->stream));
+  LAUNCH(k_hash_insert, (unsigned)cdiv(NC, 256), 256, 0, c.ckey.as<uint64_t>(), NC, c.tk2.as<unsigned long long>(), c.tv2.as<uint32_t>(), cmask);
+  CK(c.best.reserve((size_t)NC * 8)); CK(c.flag.reserve((size_t)(NC + 1) * 4)); CK(c.rank.reserve((size_t)(NC + 1) * 4));
+  CK(cudaMemsetAsync(c.best.p, 0xff, (size_t)NC * 8, h->stream));
+  LAUNCH(k_vccs_seed_nearest, (unsigned)cdiv(V, 256), 256, 0, c.xyz.as<float>(), c.cell3.as<int32_t>(), V, h->box.mn[0], h->box.mn[1], h->box.mn[2],
+         seed_d, c.tk2.as<unsigned long long>(), c.tv2.as<uint32_t>(), cmask, c.best.as<unsigned long long>());
+  LAUNCH(k_vccs_reset, (unsigned)cdiv(V, 256), 256, 0, V, c.owner.as<int32_t>(), c.dist.as<float>(), c.claim.as<int32_t>());
+  LAUNCH(k_vccs_seed_claim, (unsigned)cdiv(NC, 256), 256, 0, c.best.as<unsigned long long>(), NC, c.claim.as<int32_t>());
+  const float voxel_res = h->voxel_size;
+  const float search_radius = 0.5f * seed_resolution;
+  const float min_points = 0.05f * (search_radius) * (search_radius) * 3.1415926536f / (voxel_res * voxel_res);
+  const int reach = (int)std::ceil((double)search_radius / (double)voxel_res) + 1;
+  if (reach > 40) return h->fail(VGS_ERR_LIMIT, "vgs_make_supervoxels_vccs: seed_resolution / voxel_resolution too large");
+  LAUNCH(k_vccs_seed_filter, (unsigned)cdiv(NC * 32, 128), 128, 0, c.best.as<unsigned long long>(), c.claim.as<int32_t>(), NC, c.key3.as<uint32_t>(),
+         c.xyz.as<float>(), h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, search_radius * search_radius, min_points, reach,
+         c.flag.as<uint32_t>());
+  unsigned long long Htot = 0;
+  s = scan_u32(h, c.flag.as<uint32_t>(), c.rank.as<uint32_t>(), NC, &Htot);
+  if (s) return s;
+  const int64_t H = (int64_t)Htot;
+  h->vccs_seeds = H;
+  CK(h->labels_own.reserve((size_t)n * 4));
+  if (H == 0) {
+    CK(cudaMemsetAsync(h->labels_own.p, 0, (size_t)n * 4, h->stream));
+    h->d_labels = h->labels_own.as<int32_t>(); h->max_label = 0;
+    h->units_external = false;
+    h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+    return h->fail(VGS_ERR_INVALID, "vgs_make_supervoxels_vccs: no seed survived (cloud too sparse for this seed_resolution)");
+  }
+  CK(c.hc.reserve((size_t)H * 12 + 16)); CK(c.hn.reserve((size_t)H * 12 + 16)); CK(c.alive.reserve((size_t)H + 16));
+  CK(c.acc.reserve((size_t)H * 48)); CK(c.cnt.reserve((size_t)H * 8)); CK(c.seedv.reserve((size_t)H * 4));
+  CK(cudaMemsetAsync(c.alive.p, 0, (size_t)H, h->stream));
+  LAUNCH(k_vccs_helpers, (unsigned)cdiv(NC, 256), 256, 0, c.best.as<unsigned long long>(), c.flag.as<uint32_t>(), c.rank.as<uint32_t>(), NC,
+         c.xyz.as<float>(), c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), c.owner.as<int32_t>());
+
+  // --- expandSupervoxels(depth): depth - 1 synchronous rounds, centroids after each ---
+  const int depth = (int)(1.8f * seed_resolution / voxel_res);
+  int32_t* own_a = c.owner.as<int32_t>();
+  int32_t* own_b = c.owner2.as<int32_t>();
+  auto expand = [&]() -> vgs_status {
+    for (int it = 1; it < depth; it++) {
+      LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, c.nb.as<int32_t>(), own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
+             c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
+             spatial_importance, normal_importance);
+      std::swap(own_a, own_b);
+      CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 48, h->stream));
+      CK(cudaMemsetAsync(c.cnt.p, 0, (size_t)H * 8, h->stream));
+      LAUNCH(k_vccs_accumulate, (unsigned)cdiv(V, 256), 256, 0, V, own_a, c.xyz.as<float>(), c.nrm.as<float>(), c.acc.as<unsigned long long>(),
+             c.cnt.as<unsigned long long>());
+      LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, c.acc.as<unsigned long long>(), c.cnt.as<unsigned long long>(), c.hc.as<float>(),
+             c.hn.as<float>(), c.alive.as<uint8_t>());
+    }
+    return VGS_OK;
+  };
+  s = expand();
+  if (s) return s;
+  // --- refineSupervoxels(k): normals inside each supervoxel, reseed at the voxel nearest to the centroid, expand ---
+  for (int it = 0; it < refine_iterations; it++) {
+    LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.nrm.as<float>());
+    LAUNCH(k_vccs_reseed, (unsigned)cdiv(H * 32, 128), 128, 0, H, c.hc.as<float>(), c.alive.as<uint8_t>(), h->box.mn[0], h->box.mn[1], h->box.mn[2],
+           (double)voxel_res, h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, c.xyz.as<float>(), c.seedv.as<int32_t>());
+    LAUNCH(k_vccs_reset, (unsigned)cdiv(V, 256), 256, 0, V, own_a, c.dist.as<float>(), c.claim.as<int32_t>());
+    LAUNCH(k_vccs_reseed_claim, (unsigned)cdiv(H, 256), 256, 0, H, c.seedv.as<int32_t>(), c.alive.as<uint8_t>(), c.claim.as<int32_t>());
+    LAUNCH(k_vccs_reseed_apply, (unsigned)cdiv(H, 256), 256, 0, H, c.seedv.as<int32_t>(), c.alive.as<uint8_t>(), c.claim.as<int32_t>(), own_a);
+    s = expand();
+    if (s) return s;
+  }
+  // --- getLabeledCloud / getMaxLabel, installed like vgs_set_supervoxel_labels ---
+  int32_t* d_ml = reinterpret_cast<int32_t*>(h->small.as<unsigned long long>() + 60);
+  CK(cudaMemsetAsync(d_ml, 0, 4, h->stream));
+  LAUNCH(k_vccs_max_label, (unsigned)cdiv(H, 256), 256, 0, H, c.alive.as<uint8_t>(), d_ml);
+  LAUNCH(k_vccs_point_labels, (unsigned)cdiv(n, 256), 256, 0, n, c.ptvox.as<int32_t>(), (const int32_t*)own_a, h->labels_own.as<int32_t>());
+  int32_t ml = 0;
+  CK(cudaMemcpyAsync(&ml, d_ml, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d_labels = h->labels_own.as<int32_t>();
+  h->max_label = ml;
+  h->units_external = false;
+  h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  return VGS_OK;
+}
+
+// the labels the SVGS units are built from (set by the caller or made by vgs_make_supervoxels_vccs) and max_label
+vgs_status vgs_get_supervoxel_labels(vgs_handle h, int32_t* labels, int32_t* max_label, int on_device) {
+  if (!h) return VGS_ERR_INVALID;
+  if (h->mode != VGS_MODE_SVGS || !h->d_labels) return h->fail(VGS_ERR_STATE, "vgs_get_supervoxel_labels: no supervoxel labels yet");
+  CK(cudaSetDevice(h->device));
+  if (labels) {
+    CK(cudaMemcpyAsync(labels, h->d_labels, (size_t)h->n * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (max_label) *max_label = h->max_label;
   return VGS_OK;
 }
 

@@ -80,19 +80,27 @@ class _Prims:
         cnt = np.floor(n_points * areas / areas.sum()).astype(np.int64)
         cnt[0] += n_points - cnt.sum()
         parts = [s(int(k), rng) for k, (_, s) in zip(cnt, self.items) if k > 0]
+        # ground truth for segmentation-quality metrics: index of the surface (rectangle / cylinder / blob) a point
+        # was sampled from; does not consume random numbers, so the clouds are unchanged
+        self.ids = np.concatenate([np.full(int(k), i, np.int32) for i, k in enumerate(cnt) if k > 0])
         pts = np.concatenate(parts, axis=0)
         pts += noise * rng.standard_normal(pts.shape)
         return pts
 
 
-def _finish(pts, rng, shuffle):
-    if shuffle:
-        pts = pts[rng.permutation(pts.shape[0])]
-    return np.ascontiguousarray(pts, dtype=np.float32)
+def _finish(pts, rng, shuffle, prims=None, return_ids=False):
+    perm = rng.permutation(pts.shape[0]) if shuffle else None
+    if perm is not None:
+        pts = pts[perm]
+    out = np.ascontiguousarray(pts, dtype=np.float32)
+    if return_ids:
+        ids = prims.ids if perm is None else prims.ids[perm]
+        return out, np.ascontiguousarray(ids)
+    return out
 
 
 def construction_site(n_points=10_000_000, seed=1, extent=70.0, noise=0.005, shuffle=True,
-                      offset=(0.0, 0.0, 0.0)):
+                      offset=(0.0, 0.0, 0.0), return_ids=False):
     """BASELINE.json config 3: slab + boxes (walls/containers, random yaw) + vertical/horizontal
     cylinders + scaffolding planes.  `extent` scales the whole site; the default 70 m with 10 M
     points gives ~1 500 pts/m^2 (~30 points per 0.15 m voxel)."""
@@ -120,7 +128,7 @@ def construction_site(n_points=10_000_000, seed=1, extent=70.0, noise=0.005, shu
         for lvl in range(3):
             P.rect([cx, cy, (2.0 + 2.0 * lvl) * k], ex, np.array([-np.sin(yaw), np.cos(yaw), 0.0]) * 1.2 * k)
     pts = P.sample(n_points, rng, noise) + np.asarray(offset, dtype=np.float64)
-    return _finish(pts, rng, shuffle)
+    return _finish(pts, rng, shuffle, P, return_ids)
 
 
 def town(n_points=2_000_000, seed=20170610, extent=60.0, noise=0.005, shuffle=True, offset=(0.0, 0.0, 0.0)):
@@ -176,7 +184,7 @@ def urban(n_points=100_000_000, seed=2, extent=320.0, noise=0.005, shuffle=True,
     return _finish(pts, rng, shuffle)
 
 
-def two_planes(n_points=40_000, seed=7, noise=0.004, shuffle=True):
+def two_planes(n_points=40_000, seed=7, noise=0.004, shuffle=True, return_ids=False):
     """Small parity-test scene: a floor patch, a wall and a 30-degree ramp meeting it."""
     rng = np.random.Generator(np.random.Philox(key=seed))
     P = _Prims()
@@ -184,7 +192,7 @@ def two_planes(n_points=40_000, seed=7, noise=0.004, shuffle=True):
     P.rect([0.3, 3.2, 0.1], [4.0, 0, 0], [0, 0, 2.5])
     P.rect([4.3, 0.2, 0.1], [2.0, 0, 1.1547], [0, 3.0, 0])
     pts = P.sample(n_points, rng, noise)
-    return _finish(pts, rng, shuffle)
+    return _finish(pts, rng, shuffle, P, return_ids)
 
 
 def supervoxel_labels_grid(xyz, seed_size=0.25):
