@@ -156,3 +156,33 @@ inline void saveColoredClusters(const std::string& fileoutpath_name, PCXYZPtr in
   }
   std::fclose(f);
 }
+
+// IO.cpp:73-76 — an already coloured cloud (the draw* members' output) as a binary XYZRGB PCD
+inline void saveColoredClusters(const std::string& fileoutpath_name, pcl::PointCloud<pcl::PointXYZRGB>::Ptr colored_cloud) {
+  FILE* f = std::fopen(fileoutpath_name.c_str(), "wb");
+  if (!f) throw std::runtime_error("saveColoredClusters: cannot open " + fileoutpath_name);
+  const size_t total = colored_cloud->points.size();
+  std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\n"
+                  "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", total, total);
+  for (const auto& p : colored_cloud->points) {
+    float xyz[3] = {p.x, p.y, p.z};
+    std::uint32_t rgb = ((std::uint32_t)p.r << 16) | ((std::uint32_t)p.g << 8) | (std::uint32_t)p.b;
+    std::fwrite(xyz, 4, 3, f);
+    std::fwrite(&rgb, 4, 1, f);
+  }
+  std::fclose(f);
+}
+
+// IO.h:100-108 — plain XYZ cloud as a binary PCD
+inline void outputPointCloudData(const std::string& outName, PCXYZPtr dataCloud) {
+  FILE* f = std::fopen(outName.c_str(), "wb");
+  if (!f) throw std::runtime_error("outputPointCloudData: cannot open " + outName);
+  const size_t total = dataCloud->points.size();
+  std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
+                  "WIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", total, total);
+  for (const auto& p : dataCloud->points) {
+    float xyz[3] = {p.x, p.y, p.z};
+    std::fwrite(xyz, 4, 3, f);
+  }
+  std::fclose(f);
+}

@@ -104,3 +104,40 @@ def test_driver_end_to_end(built_lib, tmp_path, mode):
         assert len(g) == len(exp)
         a = np.stack([g["x"], g["y"], g["z"]], 1)
         assert np.array_equal(a[np.lexsort(a.T)], exp[np.lexsort(exp.T)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["vgs", "svgs"])
+def test_driver_display_exports(built_lib, tmp_path, mode):
+    """VGS_DRIVER_EXPORT_DIR: the meshes / coloured clouds the snippet declares (test:42-47, 131-135) are written; SVGS runs
+    without external labels, i.e. through the built-in supervoxel generator"""
+    from oracle import oracle
+    from vgs_svgs_segmentation_b200 import scenes
+    from test_mesh_exports import read_ply
+    _compile()
+    xyz = scenes.two_planes(40_000)
+    write_pcd_binary(tmp_path / "in.pcd", xyz, extra_field=False)
+    write_task_file(tmp_path / "task.txt", VGS_VALUES if mode == "vgs" else SVGS_VALUES, str(tmp_path) + "/", "in.pcd", "out.pcd")
+    exp = tmp_path / "exports"
+    exp.mkdir()
+    r = subprocess.run([EXE, str(tmp_path / "task.txt")], capture_output=True, text=True, env={**os.environ, "VGS_DRIVER_EXPORT_DIR": str(exp)})
+    assert r.returncode == 0, r.stderr
+    print(r.stdout)
+    if mode == "vgs":
+        ref = oracle.run(xyz, math=1)
+        nu = int(ref.used.sum())
+        for name, per_box in (("colored_voxels", 12), ("frames_voxels", 12), ("clustered_voxels", 12)):
+            v, _, f = read_ply(exp / f"{name}.ply")
+            assert len(v) == 8 * nu and len(f) == per_box * nu
+        v, _, f = read_ply(exp / "normals_voxels.ply")
+        assert len(v) == 2 * nu and len(f) == nu
+        off = ref.unit_offsets
+        assert len(read_colored_pcd(exp / "points_in_voxels.pcd")) == int((off[1:] - off[:-1])[ref.used > 0].sum())
+    else:
+        sv = oracle.vccs(xyz, schedule=1)
+        rec = read_colored_pcd(exp / "points_in_supervoxels.pcd")
+        # createSupervoxels drops label max_label (SV.h:313 loops k < max_label)
+        assert len(rec) == int(((sv.point_label > 0) & (sv.point_label < sv.max_label)).sum())
+        assert len(read_colored_pcd(exp / "points_in_voxels.pcd")) == len(xyz)
+        v, _, f = read_ply(exp / "normals_supervoxels.ply")
+        assert len(f) > 0 and len(v) == 2 * len(f)

@@ -3,6 +3,8 @@
 // Task_File_VGS.txt:24-25) and runs segmentationVGS / segmentationSVGS exactly as the reference's usage
 // snippet does (test:9-86, 91-170) on the drop-in classes.  Usage:
 //   vgs_driver <task_file> [input.pcd] [output.pcd] [supervoxel_labels.i32]
+// With VGS_DRIVER_EXPORT_DIR=<dir> the display exports the snippet declares but never saves (test:42-47, 131-135:
+// coloured voxels, frames, normals, clustered voxels) are written there as PLY / PCD files.
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -44,6 +46,23 @@ static int segmentationVGS(const string& out_name, PCXYZPtr input_cloud, const s
   std::printf(" In total %d\n", voxel_structure.getClusterNum());            // VS.h:2086
   std::printf("VGS: %zu points, %d voxels, %zu segments written\n", input_cloud->size(), nv, clusters_points_idx.size());
   saveColoredClusters(out_name, input_cloud, clusters_points_idx);          // test:80
+  if (const char* dir = std::getenv("VGS_DRIVER_EXPORT_DIR")) {
+    const string d = string(dir) + "/";
+    pcl::PointCloud<pcl::PointXYZRGB>::Ptr colored_cloud(new PCXYZRGB);                                   // test:42
+    pcl::PolygonMesh::Ptr colored_voxels(new pcl::PolygonMesh), frames_voxels(new pcl::PolygonMesh);     // test:44-47
+    pcl::PolygonMesh::Ptr Normes_voxels(new pcl::PolygonMesh), clustered_voxels(new pcl::PolygonMesh);
+    voxel_structure.drawColorMapofPointsinVoxels(colored_cloud);
+    voxel_structure.drawColorMapofVoxels(colored_voxels);
+    voxel_structure.drawFrameMapofVoxels(frames_voxels);
+    voxel_structure.drawNormofVoxels(Normes_voxels);
+    voxel_structure.drawColorMapofClusteredVoxels(clustered_voxels);
+    saveColoredClusters(d + "points_in_voxels.pcd", colored_cloud);
+    if (vgs_dropin::savePolygonMeshPLY(d + "colored_voxels.ply", *colored_voxels) || vgs_dropin::savePolygonMeshPLY(d + "frames_voxels.ply", *frames_voxels) ||
+        vgs_dropin::savePolygonMeshPLY(d + "normals_voxels.ply", *Normes_voxels) ||
+        vgs_dropin::savePolygonMeshPLY(d + "clustered_voxels.ply", *clustered_voxels))
+      throw std::runtime_error("cannot write the display exports to " + d);
+    std::printf("display exports written to %s\n", d.c_str());
+  }
   return 0;
 }
 
@@ -86,6 +105,18 @@ static int segmentationSVGS(const string& out_name, PCXYZPtr input_cloud, const 
   std::printf("SVGS: %zu points, %d voxels, %d supervoxels, %zu segments written\n", input_cloud->size(), nv,
               supervoxel_structure.getSuperVoxelNum(), clusters_points_idx.size());
   saveColoredClusters(out_name, input_cloud, clusters_points_idx);
+  if (const char* dir = std::getenv("VGS_DRIVER_EXPORT_DIR")) {
+    const string d = string(dir) + "/";
+    pcl::PointCloud<pcl::PointXYZRGB>::Ptr colored_voxels(new PCXYZRGB), colored_supervoxels(new PCXYZRGB);   // test:131-133
+    pcl::PolygonMesh::Ptr normes_spvoxels(new pcl::PolygonMesh);                                              // test:135
+    supervoxel_structure.drawColorMapofPointsinVoxels(colored_voxels);
+    supervoxel_structure.drawColorMapofPointsinSupervoxels(colored_supervoxels);
+    supervoxel_structure.drawNormofVoxels(normes_spvoxels);
+    saveColoredClusters(d + "points_in_voxels.pcd", colored_voxels);
+    saveColoredClusters(d + "points_in_supervoxels.pcd", colored_supervoxels);
+    if (vgs_dropin::savePolygonMeshPLY(d + "normals_supervoxels.ply", *normes_spvoxels)) throw std::runtime_error("cannot write the display exports to " + d);
+    std::printf("display exports written to %s\n", d.c_str());
+  }
   return 0;
 }
 
