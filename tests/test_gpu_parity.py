@@ -168,6 +168,18 @@ def test_vgs_without_pair_cache(built_lib, monkeypatch):
     _compare_vgs(xyz, g2, r)
 
 
+def test_vgs_adjacency_two_pass(built_lib, monkeypatch):
+    """VGS_B200_ADJ_TWO_PASS=1: count / scan / probe-again adjacency (used when the staging rows of the one-pass
+    variant would not fit) gives the same lists as the default one-pass build."""
+    monkeypatch.setenv("VGS_B200_ADJ_TWO_PASS", "1")
+    xyz = _scene("site")
+    g = gpu_stages(xyz)
+    monkeypatch.delenv("VGS_B200_ADJ_TWO_PASS")
+    g2 = gpu_stages(xyz)
+    assert np.array_equal(g["adj_offsets"], g2["adj_offsets"]) and np.array_equal(g["adj_idx"], g2["adj_idx"])
+    _compare_vgs(xyz, g, oracle.run(xyz, math=1))
+
+
 def test_vgs_large_cut_keeps_zero_weights(built_lib):
     """cut_thred > 0.5 makes the cut bound negative: zero-weight entries (pairs with unused voxels)
     stay in play and may merge (SURVEY.md A.5 last bullet)."""

@@ -25,6 +25,6 @@ for it in range(9):
         h.run(p, lab.data_ptr(), on_device=True)
         torch.cuda.synchronize()
         if it >= 2:
-            res[v].append(h.timings()["graph_ms"])
+            res[v].append(h.timings()[os.environ.get("AB_KEY", "graph_ms")])
 for v in values:
-    print(knob, v, "graph_ms median", round(statistics.median(res[v]), 2), "min", round(min(res[v]), 2), "max", round(max(res[v]), 2))
+    print(knob, v, os.environ.get("AB_KEY", "graph_ms"), "median", round(statistics.median(res[v]), 2), "min", round(min(res[v]), 2), "max", round(max(res[v]), 2))

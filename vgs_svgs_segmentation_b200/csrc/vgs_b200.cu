@@ -85,7 +85,7 @@ struct vgs_context {
   // device buffers
   DBuf keysA, keysB, valsA, valsB, hist, tiles, flags, scan, small;
   DBuf ustart, ukey, pos_unit, rec, key3, center, plainm, tk, tv, stencil;
-  DBuf adj_cnt, adj_off, adj_idx, class_count, class_list;
+  DBuf adj_cnt, adj_off, adj_idx, adj_stage, class_count, class_list;
   DBuf conn0_cnt, conn0_idx, conn1_cnt, conn1_idx, attach, parent, root, csize, cminpt, labels_out, tmp;
   uint64_t* d_keys = nullptr;   // sorted keys (points to keysA or keysB)
   uint32_t* d_perm = nullptr;   // sorted point indices
@@ -97,6 +97,8 @@ struct vgs_context {
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
+  int cc_jumps = 6;                 // pointer-jumping rounds over the initial component forest
+  int adj_two_pass = 0;             // 1 = count / scan / probe again instead of staging rows (VGS_B200_ADJ_TWO_PASS)
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
     DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, owner, owner2, dist, claim;
@@ -331,6 +333,8 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
+  if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
+  if (const char* e_tp = getenv("VGS_B200_ADJ_TWO_PASS")) h->adj_two_pass = (e_tp[0] == '1') ? 1 : 0;
   if (const char* e_nw = getenv("VGS_B200_NO_WARP_KERNEL")) h->use_warp_kernel = (e_nw[0] == '1') ? 0 : 1;
   if (const char* e_ch = getenv("VGS_B200_LW_CHUNK")) { int v = atoi(e_ch); if (v >= 1 && v <= LW_CS) h->lw_chunk = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
@@ -890,9 +894,12 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   double r = (double)graph_size;
   float r2 = (float)(r * r);
   CK(h->adj_cnt.reserve((size_t)(nu + 1) * 4)); CK(h->adj_off.reserve((size_t)(nu + 1) * 4));
+  // one probing pass when the fixed-stride staging rows fit (nu * nst ids); otherwise count, scan, probe again
+  const bool one_pass = !h->adj_two_pass && (size_t)nu * (size_t)nst * 4 <= ((size_t)8 << 30);
+  if (one_pass) CK(h->adj_stage.reserve((size_t)nu * (size_t)nst * 4 + 16));
   LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
-         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 0,
-         h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, (int32_t*)nullptr, nst);
+         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, one_pass ? 2 : 0,
+         h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, one_pass ? h->adj_stage.as<int32_t>() : (int32_t*)nullptr, nst);
   unsigned long long total = 0;
   vgs_status s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, &total);
   if (s) return s;
@@ -901,10 +908,13 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, &tot32, 4, cudaMemcpyHostToDevice, h->stream));
   h->n_adj = (int64_t)total;
   CK(h->adj_idx.reserve((size_t)total * 4 + 16));
-  LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
-         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
-         h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), nst);
-  CK(cudaStreamSynchronize(h->stream));
+  if (one_pass)
+    LAUNCH(k_adjacency_compact, (unsigned)cdiv(nu * 32, 256), 256, 0, h->adj_stage.as<int32_t>(), nst, h->adj_off.as<uint32_t>(), nu,
+           h->adj_idx.as<int32_t>());
+  else
+    LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
+           h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
+           h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), nst);
   h->have_adj = true;
   t.stop();
   return VGS_OK;
@@ -1195,7 +1205,9 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
   // ---- stage 5d: components ----
   {
     StageTimer t(h, &h->tm.components_ms, 8);
-    LAUNCH(k_iota, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu);
+    LAUNCH(k_cc_init, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>(),
+           h->attach.as<int32_t>(), nu, h->parent.as<int>());
+    for (int r = 0; r < h->cc_jumps; r++) LAUNCH(k_cc_jump, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu);
     LAUNCH(k_cc_hook, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(),
            h->conn1_idx.as<int32_t>(), h->attach.as<int32_t>(), nu, h->parent.as<int>());
     LAUNCH(k_cc_flatten, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu, h->root.as<int>());

@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(256) k_plain_morton(const uint32_t* __restrict
 // ---- stage 3 (VGS): FLANN radius search over voxel centres == lattice stencil probed through the
 //      hash table, then the float test dist2 < (float)(r*r) and ordering by (dist2, id)
 //      (VS.h:223-265, FLANN L2_Simple + RadiusResultSet).  One warp per voxel.
-//      fill == 0: write the neighbour count; fill == 1: write the ordered list at adj_off[v]. ----
+//      fill == 0: write the neighbour count; fill == 1: write the ordered list at adj_off[v];
+//      fill == 2 (one probing pass instead of two): write the count AND the ordered list into a fixed-stride
+//      staging row (adj_idx + v * cap); k_adjacency_compact moves the rows to their CSR offsets after the scan. ----
 __global__ void __launch_bounds__(128) k_adjacency(const uint32_t* __restrict__ key3, const float* __restrict__ center, int64_t nv,
                                                  int depth, const int4* __restrict__ stencil, int nst,
                                                  const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
@@ -226,10 +228,12 @@ __global__ void __launch_bounds__(128) k_adjacency(const uint32_t* __restrict__ 
     }
     count += __popc(bal);
   }
-  if (!fill) { if (lane == 0) adj_cnt[v] = (uint32_t)count; return; }
+  if (fill != 1 && lane == 0) adj_cnt[v] = (uint32_t)count;
+  if (!fill) return;
   __syncwarp();
   if (count > cap) count = cap;
-  const uint32_t off = adj_off[v];
+  if (fill == 2) adj_idx += v * cap;
+  const uint32_t off = fill == 2 ? 0u : adj_off[v];
   for (int e = lane; e < count; e += 32) {
     float d = sd2[e]; int id = sid[e];
     int rank = 0;
@@ -239,6 +243,16 @@ __global__ void __launch_bounds__(128) k_adjacency(const uint32_t* __restrict__ 
     }
     adj_idx[off + rank] = id;
   }
+}
+
+__global__ void __launch_bounds__(256) k_adjacency_compact(const int32_t* __restrict__ stage, int cap, const uint32_t* __restrict__ adj_off,
+                                                         int64_t nv, int32_t* __restrict__ adj_idx) {
+  const int lane = threadIdx.x & 31;
+  int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= nv) return;
+  const uint32_t off = adj_off[v];
+  const int c = (int)(adj_off[v + 1] - off);
+  for (int e = lane; e < c; e += 32) adj_idx[off + e] = stage[v * cap + e];
 }
 
 // ---- stage 3 (SVGS): radius search over supervoxel centroids (SV.h:1477-1521).  Uniform grid of
@@ -1238,9 +1252,15 @@ __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __re
 }
 
 // ---- stage 5d: connected components by lock-free union-find, root = smallest unit id ----
+// find with path halving: a non-root's pointer only ever moves to one of its ancestors (roots are hooked under
+// smaller roots only), so the plain store races benignly with the CAS in uf_union, which touches roots only
 __device__ __forceinline__ int uf_find(int* parent, int x) {
   int p = ((volatile int*)parent)[x];
-  while (p != x) { x = p; p = ((volatile int*)parent)[x]; }
+  while (p != x) {
+    const int gp = ((volatile int*)parent)[p];
+    if (gp != p) ((volatile int*)parent)[x] = gp;
+    x = p; p = gp;
+  }
   return x;
 }
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
@@ -1254,6 +1274,33 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 __global__ void __launch_bounds__(256) k_iota(int* __restrict__ p, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int)i;
+}
+// initial forest: every unit points at its smallest linked unit with a smaller id (connect list / closest-check
+// partner), which already performs one union per unit without any atomics.  One warp per unit.
+__global__ void __launch_bounds__(128) k_cc_init(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1,
+                                               const int32_t* __restrict__ idx1, const int32_t* __restrict__ attach, int64_t nu,
+                                               int* __restrict__ parent) {
+  const int lane = threadIdx.x & 31;
+  int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= nu) return;
+  const uint32_t off = adj_off[u];
+  const int c = (int)cnt1[u];
+  int p = (int)u;
+  for (int e = lane; e < c; e += 32) p = min(p, idx1[off + e]);
+  p = __reduce_min_sync(0xffffffffu, p);
+  if (lane == 0) {
+    const int a = attach[u];
+    if (a >= 0) p = min(p, a);
+    parent[u] = p;
+  }
+}
+// pointer jumping over the initial forest (parents only move to ancestors, so in-place updates are safe)
+__global__ void __launch_bounds__(256) k_cc_jump(int* parent, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = ((volatile int*)parent)[i];
+  const int gp = ((volatile int*)parent)[p];
+  if (gp != p) ((volatile int*)parent)[i] = gp;
 }
 __global__ void __launch_bounds__(128) k_cc_hook(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1,
                                                const int32_t* __restrict__ idx1, const int32_t* __restrict__ attach, int64_t nu,
