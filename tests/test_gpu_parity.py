@@ -168,6 +168,16 @@ def test_vgs_without_pair_cache(built_lib, monkeypatch):
     _compare_vgs(xyz, g2, r)
 
 
+def test_vgs_pair_cache_without_bitmap(built_lib, monkeypatch):
+    """VGS_B200_NO_BITMAP=1: the pair cache finds partners by hash probes of every stencil offset (the path taken for
+    octrees deeper than 11 levels) instead of reading z-runs of the occupancy bitmap; same lists and labels."""
+    monkeypatch.setenv("VGS_B200_NO_BITMAP", "1")
+    xyz = _scene("site")
+    g = gpu_stages(xyz)
+    monkeypatch.delenv("VGS_B200_NO_BITMAP")
+    _compare_vgs(xyz, g, oracle.run(xyz, math=1))
+
+
 def test_vgs_adjacency_two_pass(built_lib, monkeypatch):
     """VGS_B200_ADJ_TWO_PASS=1: count / scan / probe-again adjacency (used when the staging rows of the one-pass
     variant would not fit) gives the same lists as the default one-pass build."""

@@ -91,12 +91,13 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  DBuf stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
+  DBuf bitmap, stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
   int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
   int lw_chunk = LW_CH;             // target useful entries per chunk (tuning knob VGS_B200_LW_CHUNK)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
+  int use_bitmap = 1;               // pair-cache partner search on an occupancy bitmap (0: hash probes; VGS_B200_NO_BITMAP)
   int cc_jumps = 6;                 // pointer-jumping rounds over the initial component forest
   int adj_two_pass = 0;             // 1 = count / scan / probe again instead of staging rows (VGS_B200_ADJ_TWO_PASS)
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
@@ -333,6 +334,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
+  if (const char* e_bm = getenv("VGS_B200_NO_BITMAP")) h->use_bitmap = (e_bm[0] == '1') ? 0 : 1;
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
   if (const char* e_tp = getenv("VGS_B200_ADJ_TWO_PASS")) h->adj_two_pass = (e_tp[0] == '1') ? 1 : 0;
   if (const char* e_nw = getenv("VGS_B200_NO_WARP_KERNEL")) h->use_warp_kernel = (e_nw[0] == '1') ? 0 : 1;
@@ -373,8 +375,14 @@ void vgs_destroy(vgs_handle h) {
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
                  &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin};
+                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin,
+                 &h->adj_stage, &h->bitmap};
   for (DBuf* b : all) b->release();
+  auto& c = h->vc;
+  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm,
+                 &c.owner, &c.owner2, &c.dist, &c.claim, &c.ckA, &c.ckB, &c.cvA, &c.cvB, &c.cstart, &c.ckey, &c.cpos, &c.cell3, &c.best,
+                 &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.cnt, &c.tk, &c.tv, &c.tk2, &c.tv2};
+  for (DBuf* b : vcb) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1066,12 +1074,33 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
             st2.push_back(make_int4(dx, dy, dz, code - half - 1));
           }
         CK(h->pair_table.reserve(bytes));
-        CK(h->stencil2.reserve(st2.size() * sizeof(int4)));
-        CK(cudaMemcpyAsync(h->stencil2.p, st2.data(), st2.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
-        LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
-               h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
-               h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
+        if (h->use_bitmap && h->depth <= 11 && r2 <= 15 && half < 65536) {
+          // partner search on an occupancy bitmap of the used voxels: stencil columns (dx, dy, mask of dz)
+          std::vector<int4> cols;
+          for (const int4& o : st2) {
+            if (cols.empty() || cols.back().x != o.x || cols.back().y != o.y) {
+              bool found = false;
+              for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + r2); found = true; break; }
+              if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + r2), 0));
+            } else cols.back().z |= 1 << (o.z + r2);
+          }
+          const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
+          CK(h->bitmap.reserve(bm_bytes));
+          CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
+          LAUNCH(k_bitmap_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, h->depth, h->bitmap.as<uint32_t>());
+          CK(h->stencil2.reserve(cols.size() * sizeof(int4)));
+          CK(cudaMemcpyAsync(h->stencil2.p, cols.data(), cols.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+          LAUNCH(k_pair_cache_bm, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
+                 h->stencil2.as<int4>(), (int)cols.size(), r2, h->bitmap.as<uint32_t>(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(),
+                 h->hmask, gp.pp, h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
+        } else {
+          CK(h->stencil2.reserve(st2.size() * sizeof(int4)));
+          CK(cudaMemcpyAsync(h->stencil2.p, st2.data(), st2.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+          LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
+                 h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
+                 h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
+        }
         tpc.stop();
         cached = true;
       }
