@@ -356,6 +356,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, false>, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_local_graph_warp, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
+    if (r == cudaSuccess) r = optin((const void*)k_adjacency_bm, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
       cudaGetLastError();
@@ -905,6 +906,26 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   // one probing pass when the fixed-stride staging rows fit (nu * nst ids); otherwise count, scan, probe again
   const bool one_pass = !h->adj_two_pass && (size_t)nu * (size_t)nst * 4 <= ((size_t)8 << 30);
   if (one_pass) CK(h->adj_stage.reserve((size_t)nu * (size_t)nst * 4 + 16));
+  int rho_s = 0;
+  for (const int4& o : st) rho_s = std::max(rho_s, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
+  if (one_pass && h->use_bitmap && h->depth <= 11 && rho_s <= 15 && nst < 65536 && (size_t)wpb * nst * 10 <= 200 * 1024) {
+    // lattice search on the all-voxel occupancy bitmap: stencil columns (dx, dy, mask of dz)
+    std::vector<int4> cols;
+    for (const int4& o : st) {
+      bool found = false;
+      for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + rho_s); found = true; break; }
+      if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + rho_s), 0));
+    }
+    const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
+    CK(h->bitmap.reserve(bm_bytes));
+    CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
+    LAUNCH(k_bitmap_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), (const uint8_t*)nullptr, nu, h->depth, h->bitmap.as<uint32_t>());
+    CK(h->stencil2.reserve(cols.size() * sizeof(int4)));
+    CK(cudaMemcpyAsync(h->stencil2.p, cols.data(), cols.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_adjacency_bm, (unsigned)cdiv(nu, wpb), wpb * 32, (size_t)wpb * nst * 10, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
+           h->stencil2.as<int4>(), (int)cols.size(), rho_s, h->bitmap.as<uint32_t>(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(),
+           h->hmask, r2, h->adj_cnt.as<uint32_t>(), h->adj_stage.as<int32_t>(), nst);
+  } else
   LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
          h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, one_pass ? 2 : 0,
          h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, one_pass ? h->adj_stage.as<int32_t>() : (int32_t*)nullptr, nst);

@@ -469,9 +469,92 @@ __global__ void __launch_bounds__(128) k_pair_cache(const uint32_t* __restrict__
 __global__ void __launch_bounds__(256) k_bitmap_set(const uint32_t* __restrict__ key3, const uint8_t* __restrict__ uflags, int64_t nv,
                                                   int depth, uint32_t* __restrict__ bm) {
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nv || !(uflags[v] & F_USED)) return;
+  if (v >= nv || (uflags && !(uflags[v] & F_USED))) return;   // uflags == null: every voxel
   const uint64_t b = ((((uint64_t)key3[3 * v] << depth) | key3[3 * v + 1]) << depth) | key3[3 * v + 2];
   atomicOr(&bm[b >> 5], 1u << (b & 31));
+}
+
+// k_adjacency (fill == 2) with the lattice search done on the all-voxel bitmap: one load per stencil column,
+// hash lookups only for occupied cells.  Same float test, same (dist2, id) order.
+__global__ void __launch_bounds__(128) k_adjacency_bm(const uint32_t* __restrict__ key3, const float* __restrict__ center, int64_t nv,
+                                                    int depth, const int4* __restrict__ cols, int ncol, int rho, const uint32_t* __restrict__ bm,
+                                                    const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
+                                                    uint64_t mask, float r2, uint32_t* __restrict__ adj_cnt, int32_t* __restrict__ stage, int cap) {
+  extern __shared__ unsigned char smraw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* sd2 = reinterpret_cast<float*>(smraw) + (size_t)w * cap;
+  int* sid = reinterpret_cast<int*>(smraw + (size_t)wpb * cap * sizeof(float)) + (size_t)w * cap;
+  unsigned short* q = reinterpret_cast<unsigned short*>(smraw + (size_t)wpb * cap * 8) + (size_t)w * cap;
+  int64_t v = (int64_t)blockIdx.x * wpb + w;
+  if (v >= nv) return;
+  const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
+  const float qx = center[3 * v], qy = center[3 * v + 1], qz = center[3 * v + 2];
+  const int lim = 1 << depth;
+  const int S = 2 * rho + 1;
+  int nq = 0;
+  for (int base = 0; base < ncol; base += 32) {
+    const int ci = base + lane;
+    uint32_t hits = 0;
+    int cbase = 0;
+    if (ci < ncol) {
+      const int4 o = cols[ci];
+      const int x = kx + o.x, y = ky + o.y;
+      if (x >= 0 && y >= 0 && x < lim && y < lim) {
+        const int z0 = max(kz - rho, 0), z1 = min(kz + rho, lim - 1);
+        const uint64_t b0 = ((((uint64_t)x << depth) | (uint64_t)y) << depth) | (uint64_t)z0;
+        const uint64_t two = (uint64_t)__ldg(bm + (b0 >> 5)) | ((uint64_t)__ldg(bm + (b0 >> 5) + 1) << 32);
+        uint32_t run = (uint32_t)(two >> (b0 & 31)) & (uint32_t)((1ull << (z1 - z0 + 1)) - 1ull);
+        run <<= (z0 - (kz - rho));
+        hits = run & (uint32_t)o.z;
+        cbase = ((o.x + rho) * S + (o.y + rho)) * S;
+      }
+    }
+    const int cnt = __popc(hits);
+    const int incl = (int)warp_incl_scan((unsigned)cnt, lane);
+    int pos = nq + incl - cnt;
+    while (hits) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      q[pos++] = (unsigned short)(cbase + j);
+    }
+    nq += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  int count = 0;
+  for (int b = 0; b < nq; b += 32) {
+    const int e = b + lane;
+    int id = -1;
+    float d2 = 0.f;
+    if (e < nq) {
+      const int c = q[e];
+      const int dz = c % S - rho, dy = (c / S) % S - rho, dx = c / (S * S) - rho;
+      id = hash_lookup(tk, tv, mask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+      if (id >= 0) {
+        float ex = qx - center[3 * (int64_t)id], ey = qy - center[3 * (int64_t)id + 1], ez = qz - center[3 * (int64_t)id + 2];
+        d2 = 0.f; d2 += ex * ex; d2 += ey * ey; d2 += ez * ez;
+        if (!(d2 < r2)) id = -1;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
+    if (id >= 0) {
+      const int pos = count + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) { sd2[pos] = d2; sid[pos] = id; }
+    }
+    count += __popc(bal);
+  }
+  if (lane == 0) adj_cnt[v] = (uint32_t)count;
+  __syncwarp();
+  if (count > cap) count = cap;
+  stage += v * cap;
+  for (int e = lane; e < count; e += 32) {
+    const float d = sd2[e]; const int id = sid[e];
+    int rank = 0;
+    for (int j = 0; j < count; j++) {
+      const float dj = sd2[j]; const int ij = sid[j];
+      rank += (dj < d || (dj == d && ij < id)) ? 1 : 0;
+    }
+    stage[rank] = id;
+  }
 }
 
 // k_pair_cache with the partner search done on the bitmap: the stencil is stored as columns (dx, dy, 13-bit mask
