@@ -1012,8 +1012,8 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
   if (li >= nlist) return;
   unsigned char* base = smraw + (size_t)wq * lw_slice_bytes(ncap, mcap);
   float* C_w = reinterpret_cast<float*>(base);                       // LW_CS
-  float* s_int = C_w + LW_CS;                                        // ncap
-  int* s_gid = reinterpret_cast<int*>(s_int + ncap);                 // ncap
+  float* s_thr = C_w + LW_CS;                                        // ncap: merge threshold Int(C) - k/|C| of segment C
+  int* s_gid = reinterpret_cast<int*>(s_thr + ncap);                 // ncap
   int* s_key = s_gid + ncap;                                         // ncap: (dx+64) | (dy+64)<<8 | (dz+64)<<16 relative to the centre
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + ncap);      // 256: histogram, then inclusive prefix sums
   unsigned* s_cur = s_hist + 256;                                    // 256: scatter cursors
@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
       s_gid[i] = (int)g;
       // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
       s_key[i] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
-      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_int[i] = 1.0f;
+      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_thr[i] = 1.0f - k / 1.0f;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
     if (us) s_ul[nv + __popc(bal & lt)] = (unsigned char)i;
@@ -1075,8 +1075,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
       if ((todo >> lane) & 1u) {
         sa = s_seg[v1]; sb = s_seg[v2];
         if (sa != sb) {
-          const float m1 = s_int[sa] - k / (float)(int)s_size[sa];
-          const float m2 = s_int[sb] - k / (float)(int)s_size[sb];
+          const float m1 = s_thr[sa], m2 = s_thr[sb];     // Int(C) - k / |C|, kept up to date at every merge
           a_wins = (m1 >= m2);
           pred = w > (a_wins ? m1 : m2);
         }
@@ -1088,7 +1087,10 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
       const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
       for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
-      if (lane == 0) { s_int[keepl] = wl; s_size[keepl] = (unsigned char)(s_size[keepl] + s_size[drop]); s_size[drop] = 0; }
+      if (lane == 0) {
+        const int nsz = (int)s_size[keepl] + (int)s_size[drop];
+        s_thr[keepl] = wl - k / (float)nsz; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
+      }
       nseg--;
       __syncwarp();
       todo &= ~((2u << Lm) - 1u);
@@ -1277,7 +1279,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
         float mt = 3.0e38f;
         for (int v = lane; v < n; v += 32) {
           const int sz = (int)s_size[v];
-          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
+          if (sz > 0) mt = fminf(mt, s_thr[v]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
