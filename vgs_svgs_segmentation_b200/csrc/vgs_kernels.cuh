@@ -992,7 +992,7 @@ constexpr int LW_ILP = 2;       // table gathers in flight per lane in pass A (4
 constexpr int LW_BINS = 255;    // real bins 0..254; bin value 255 marks a dropped entry
 __host__ __device__ inline size_t lw_slice_bytes(int ncap, int mcap) {
   (void)mcap;   // the bin-ordered entry list lives in a global scratch slice (written once, read once: L2)
-  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 3 + 16;
+  size_t b = (size_t)LW_CS * 4 + (size_t)ncap * 12 + 512 * 4 + (size_t)LW_CS * 2 + (size_t)ncap * 2 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -1024,7 +1024,6 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
   unsigned char* gbins = reinterpret_cast<unsigned char*>(ids + mcap);
   unsigned char* s_seg = reinterpret_cast<unsigned char*>(C_f + LW_CS);   // ncap
   unsigned char* s_size = s_seg + ncap;                              // ncap
-  unsigned char* s_ul = s_size + ncap;                               // ncap: local ids of the used vertices
   const uint32_t lt = (1u << lane) - 1u;
 
   const uint32_t u = list[li];
@@ -1034,19 +1033,25 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
   for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
   const int S = 2 * r2 + 1;
   int nv = 0;
-  for (int b0 = 0; b0 < n; b0 += 32) {   // vertex table + ordered list of the used vertices
+  // vertex table of the USED neighbours only, in adjacency order (local vertex 0 = the unit itself): unused voxels
+  // cannot merge (their weight is w_empty <= cut bound, else the unit goes to the general kernel), and the
+  // tie-break order (col * n + row over all neighbours, VS.h:1922) is preserved by the monotone renumbering
+  for (int b0 = 0; b0 < n; b0 += 32) {
     const int i = b0 + lane;
     bool us = false;
+    int64_t g = 0;
     if (i < n) {
-      const int64_t g = adj_idx[off + i];
+      g = adj_idx[off + i];
       us = (__ldg(uflags + g) & F_USED) != 0;
-      s_gid[i] = (int)g;
-      // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
-      s_key[i] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
-      s_seg[i] = (unsigned char)i; s_size[i] = us ? 1 : 0; s_thr[i] = 1.0f - k / 1.0f;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
-    if (us) s_ul[nv + __popc(bal & lt)] = (unsigned char)i;
+    if (us) {
+      const int j = nv + __popc(bal & lt);
+      s_gid[j] = (int)g;
+      // mixed-radix lattice code of the offset to the centre: code(b) - code(a) orders pairs lexicographically
+      s_key[j] = (((int)key3[3 * g] - cx) * S + ((int)key3[3 * g + 1] - cy)) * S + ((int)key3[3 * g + 2] - cz);
+      s_seg[j] = (unsigned char)j; s_size[j] = 1; s_thr[j] = 1.0f - k / 1.0f;
+    }
     nv += __popc(bal);
   }
   __syncwarp();
@@ -1086,7 +1091,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
       const int keepl = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
       const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
-      for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
+      for (int v = lane; v < nv; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
       if (lane == 0) {
         const int nsz = (int)s_size[keepl] + (int)s_size[drop];
         s_thr[keepl] = wl - k / (float)nsz; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
@@ -1114,7 +1119,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
           ok[q] = ia < nv - 1;
           va[q] = 0; vc[q] = 0;
           if (ok[q]) {
-            va[q] = s_ul[ia]; vc[q] = s_ul[ia + 1 + rem];
+            va[q] = ia; vc[q] = ia + 1 + rem;
             rem += 32;
             while (ia < nv - 1 && rem >= nv - 1 - ia) { rem -= nv - 1 - ia; ia++; }
           }
@@ -1208,7 +1213,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
           const int e = e_nxt;
           const int xn = x0 + 32 + lane;
           e_nxt = xn < cntE ? (int)ids[bef + xn] : 0;
-          const bool keep = (x0 + lane < cntE) && s_seg[s_ul[e >> 8]] != s_seg[s_ul[(e >> 1) & 127]];
+          const bool keep = (x0 + lane < cntE) && s_seg[e >> 8] != s_seg[(e >> 1) & 127];
           const uint32_t bal = __ballot_sync(0xffffffffu, keep);
           if (keep) C_f[kept + __popc(bal & lt)] = (unsigned short)e;
           kept += __popc(bal);
@@ -1219,7 +1224,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
       // entry (row i, col j) = weight(idx[i] -> idx[j]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
       for (int i = lane; i < kept; i += 32) {
         const int e = C_f[i];
-        const int a = s_ul[e >> 8], b = s_ul[(e >> 1) & 127];
+        const int a = e >> 8, b = (e >> 1) & 127;
         float w_ab, w_ba;
         fetch(a, b, w_ab, w_ba);
         float w; int f;
@@ -1277,7 +1282,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
           }
         }
         float mt = 3.0e38f;
-        for (int v = lane; v < n; v += 32) {
+        for (int v = lane; v < nv; v += 32) {
           const int sz = (int)s_size[v];
           if (sz > 0) mt = fminf(mt, s_thr[v]);
         }
@@ -1299,9 +1304,9 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
   // --- emit the segment that contains local vertex 0 (the unit itself) ---
   const int s0 = s_seg[0];
   int cnt = 0;
-  for (int b = 0; b < n; b += 32) {
+  for (int b = 0; b < nv; b += 32) {
     const int v = b + lane;
-    const bool in = v < n && s_seg[v] == s0;
+    const bool in = v < nv && s_seg[v] == s0;
     const uint32_t bal = __ballot_sync(0xffffffffu, in);
     if (in) conn_idx[off + cnt + __popc(bal & lt)] = s_gid[v];
     cnt += __popc(bal);
