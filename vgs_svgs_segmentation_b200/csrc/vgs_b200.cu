@@ -91,6 +91,11 @@ struct vgs_context {
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
+  // derived stencil tables, rebuilt only when (voxel_size, graph_size) change: columns of the radius stencil, the
+  // pair-cache stencil (differences of two offsets, lexicographically positive half) and its columns
+  std::vector<int4> adj_cols_host, st2_host, pc_cols_host;
+  int st_rho = 0, st_r2 = 0, st_half = 0;
+  float st_vs = -1.f, st_gs = -1.f;
   DBuf bitmap, stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
   int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
   int lw_chunk = LW_CH;             // target useful entries per chunk (tuning knob VGS_B200_LW_CHUNK)
@@ -126,6 +131,18 @@ struct vgs_context {
     cudaError_t e_ = (x);                                                     \
     if (e_ != cudaSuccess) return h->fail_cuda(e_, #x, __LINE__);             \
   } while (0)
+// In-step host synchronisation.  Default: cudaStreamSynchronize.  VGS_B200_SPIN_SYNC=1 polls the stream instead of
+// sleeping (lower wake-up latency on an idle host, worse on an oversubscribed one: measured both ways on shared boxes).
+static int g_spin_sync = -1;
+static inline cudaError_t stream_wait(cudaStream_t st) {
+  if (g_spin_sync < 0) { const char* e = getenv("VGS_B200_SPIN_SYNC"); g_spin_sync = (e && e[0] == '1') ? 1 : 0; }
+  if (!g_spin_sync) return cudaStreamSynchronize(st);
+  for (;;) {
+    const cudaError_t r = cudaStreamQuery(st);
+    if (r != cudaErrorNotReady) return r;
+  }
+}
+
 #define LAUNCH(kernel, grid, block, smem, ...)                                \
   do {                                                                        \
     kernel<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__);              \
@@ -147,7 +164,7 @@ vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, 
   LAUNCH(k_scan_down, (unsigned)nt, SC_THREADS, 0, in, out, n, h->tiles.as<uint32_t>());
   if (total_host) {
     CK(cudaMemcpyAsync(total_host, d_total, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
   }
   return VGS_OK;
 }
@@ -250,7 +267,7 @@ vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* 
     LAUNCH(k_find_outside, (unsigned)blocks, 256, 0, h->d_xyz, h->stride, s, e, b, st.defined ? 1 : 0, d_found, nullptr);
     unsigned long long r = 0;
     CK(cudaMemcpyAsync(&r, d_found, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     if (r != ~0ull) { *found = (int64_t)r; return VGS_OK; }
     s = e;
     window *= 8;
@@ -458,7 +475,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
       if (idx >= n) break;
       float p[3];
       CK(cudaMemcpyAsync(p, h->d_xyz + idx * h->stride, 12, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       st.adopt(p);
       if (st.depth > 21) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: octree depth > 21 bits per axis (extent / voxel_size too large)");
       if (ep.n >= MAX_EPOCHS) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: too many bounding-box growth epochs");
@@ -502,7 +519,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     uint64_t lastkey = 0; uint32_t laststart = 0;
     CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     int64_t n_fin = n;
     if (lastkey >> (3 * h->depth)) { n_fin = laststart; nunits--; }
     h->n_finite = n_fin;
@@ -549,7 +566,7 @@ static vgs_status build_svgs_units(vgs_handle h) {
   uint64_t lastkey = 0; uint32_t laststart = 0;
   CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   int64_t nval = n;
   if (lastkey >> 32) { nval = laststart; nunits--; }
   h->d_keys = ks; h->d_perm = vs;
@@ -578,7 +595,7 @@ vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
   uint64_t lastkey = 0; uint32_t laststart = 0;
   CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   int64_t nval = n;
   if (lastkey >> 63) { nval = laststart; nunits--; }
   h->d_keys = ks; h->d_perm = vs;
@@ -617,7 +634,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   {
     uint64_t lastkey = 0;
     CK(cudaMemcpyAsync(&lastkey, c.key.as<uint64_t>() + (V - 1), 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     if (lastkey >> (3 * h->depth)) V--;   // the segment of the non-finite points
   }
   if (V != h->n_voxels) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: voxel table differs from vgs_voxelize's");
@@ -727,7 +744,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   LAUNCH(k_vccs_point_labels, (unsigned)cdiv(n, 256), 256, 0, n, c.ptvox.as<int32_t>(), (const int32_t*)own_a, h->labels_own.as<int32_t>());
   int32_t ml = 0;
   CK(cudaMemcpyAsync(&ml, d_ml, 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   h->d_labels = h->labels_own.as<int32_t>();
   h->max_label = ml;
   h->units_external = false;
@@ -742,7 +759,7 @@ vgs_status vgs_get_supervoxel_labels(vgs_handle h, int32_t* labels, int32_t* max
   CK(cudaSetDevice(h->device));
   if (labels) {
     CK(cudaMemcpyAsync(labels, h->d_labels, (size_t)h->n * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
   }
   if (max_label) *max_label = h->max_label;
   return VGS_OK;
@@ -776,7 +793,7 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
          h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->uflags.as<uint8_t>(), d_used);
   unsigned long long used = 0;
   CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   h->n_used = (int64_t)used;
   h->have_features = true;
   t.stop();
@@ -810,7 +827,7 @@ vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz) {
   CK(cudaSetDevice(h->device));
   { vgs_status s = ensure_geometry(h); if (s) return s; }
   CK(cudaMemcpyAsync(xyz, h->center.p, (size_t)h->nu * 12, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   return VGS_OK;
 }
 
@@ -865,7 +882,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, &total);
     if (s) return s;
     CK(cudaMemcpyAsync(&over, d_over, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     if (over) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: a supervoxel has more than 255 neighbours within graph_size");
     uint32_t tot32 = (uint32_t)total;
     CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, &tot32, 4, cudaMemcpyHostToDevice, h->stream));
@@ -874,7 +891,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     LAUNCH(k_adjacency_svgs, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
            h->cstart.as<uint32_t>(), vs, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
            h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), cap, d_over);
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     h->have_adj = true;
     t.stop();
     return VGS_OK;
@@ -892,8 +909,39 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(cudaMemsetAsync(h->tk.p, 0xff, capacity * 8, h->stream));
   LAUNCH(k_plain_morton, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, h->plainm.as<uint64_t>());
   LAUNCH(k_hash_insert, (unsigned)cdiv(nu, 256), 256, 0, h->plainm.as<uint64_t>(), nu, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask);
-  std::vector<int4> st = make_stencil(h->voxel_size, graph_size);
-  h->stencil_host = st;
+  if (h->st_vs != h->voxel_size || h->st_gs != graph_size) {
+    h->stencil_host = make_stencil(h->voxel_size, graph_size);
+    int rho = 0;
+    for (const int4& o : h->stencil_host) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
+    auto columns = [](const std::vector<int4>& offs, int reach) {
+      std::vector<int4> cols;
+      for (const int4& o : offs) {
+        bool found = false;
+        for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + reach); found = true; break; }
+        if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + reach), 0));
+      }
+      return cols;
+    };
+    h->st_rho = rho;
+    h->adj_cols_host = rho <= 15 ? columns(h->stencil_host, rho) : std::vector<int4>();
+    const int r2 = 2 * rho, S = 2 * r2 + 1;
+    h->st_r2 = r2;
+    h->st_half = (S * S * S - 1) / 2;
+    std::vector<char> seen((size_t)S * S * S, 0);
+    h->st2_host.clear();
+    for (const int4& p1 : h->stencil_host)
+      for (const int4& p2 : h->stencil_host) {
+        int dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+        if (!(dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0))))) continue;
+        int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2);
+        if (seen[code]) continue;
+        seen[code] = 1;
+        h->st2_host.push_back(make_int4(dx, dy, dz, code - h->st_half - 1));
+      }
+    h->pc_cols_host = r2 <= 15 ? columns(h->st2_host, r2) : std::vector<int4>();
+    h->st_vs = h->voxel_size; h->st_gs = graph_size;
+  }
+  const std::vector<int4>& st = h->stencil_host;
   const int nst = (int)st.size();
   const int wpb = 4;
   size_t smem = (size_t)wpb * nst * 8;
@@ -906,16 +954,10 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   // one probing pass when the fixed-stride staging rows fit (nu * nst ids); otherwise count, scan, probe again
   const bool one_pass = !h->adj_two_pass && (size_t)nu * (size_t)nst * 4 <= ((size_t)8 << 30);
   if (one_pass) CK(h->adj_stage.reserve((size_t)nu * (size_t)nst * 4 + 16));
-  int rho_s = 0;
-  for (const int4& o : st) rho_s = std::max(rho_s, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
+  const int rho_s = h->st_rho;
   if (one_pass && h->use_bitmap && h->depth <= 11 && rho_s <= 15 && nst < 65536 && (size_t)wpb * nst * 10 <= 200 * 1024) {
     // lattice search on the all-voxel occupancy bitmap: stencil columns (dx, dy, mask of dz)
-    std::vector<int4> cols;
-    for (const int4& o : st) {
-      bool found = false;
-      for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + rho_s); found = true; break; }
-      if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + rho_s), 0));
-    }
+    const std::vector<int4>& cols = h->adj_cols_host;
     const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
     CK(h->bitmap.reserve(bm_bytes));
     CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
@@ -981,7 +1023,7 @@ vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, in
   uint32_t a = 0, b = 0;
   CK(cudaMemcpyAsync(&a, h->adj_off.as<uint32_t>() + first_unit, 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&b, h->adj_off.as<uint32_t>() + last_unit, 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   *e_first = a; *e_last = b;
   return VGS_OK;
 }
@@ -1004,7 +1046,7 @@ static vgs_status connect_copy(vgs_handle h, int64_t first, int64_t last, int32_
     CK(cudaMemcpyAsync(i, idx_dev, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
     h->have_graph = true;
   }
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   return VGS_OK;
 }
 vgs_status vgs_export_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, int32_t* cnt_dev, int32_t* idx_dev) {
@@ -1066,46 +1108,29 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(cmaxn, d_maxn, sizeof(cmaxn), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
     if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a local graph has more than 181 enumerated (or 255 total) units (graph_size / unit spacing too large)");
     // pair-weight cache (VGS lattice): each unordered pair of used voxels evaluated once
     bool cached = false;
     int half = 0, r2 = 0;
     if (h->mode == VGS_MODE_VGS && h->use_pair_cache && !h->stencil_host.empty()) {
-      int rho = 0;
-      for (const int4& o : h->stencil_host) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
-      r2 = 2 * rho;
-      const int S = 2 * r2 + 1;
-      half = (S * S * S - 1) / 2;
+      r2 = h->st_r2;
+      half = h->st_half;
       size_t bytes = (size_t)nu * (size_t)half * sizeof(float2);
-      size_t free_b = 0, total_b = 0;
-      CK(cudaMemGetInfo(&free_b, &total_b));
-      if (bytes <= h->pair_table.cap || bytes < free_b / 2) {
-        // offsets that are differences of two stencil offsets, lexicographically positive half
-        std::vector<char> seen((size_t)S * S * S, 0);
-        std::vector<int4> st2;
-        for (const int4& p1 : h->stencil_host)
-          for (const int4& p2 : h->stencil_host) {
-            int dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
-            if (!(dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0))))) continue;
-            int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2);
-            if (seen[code]) continue;
-            seen[code] = 1;
-            st2.push_back(make_int4(dx, dy, dz, code - half - 1));
-          }
+      bool fits = bytes <= h->pair_table.cap;
+      if (!fits) {   // only when the table has to grow: cudaMemGetInfo is a slow driver call
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        fits = bytes < (free_b + h->pair_table.cap) / 2;
+      }
+      if (fits) {
+        const std::vector<int4>& st2 = h->st2_host;
         CK(h->pair_table.reserve(bytes));
         StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
         if (h->use_bitmap && h->depth <= 11 && r2 <= 15 && half < 65536) {
           // partner search on an occupancy bitmap of the used voxels: stencil columns (dx, dy, mask of dz)
-          std::vector<int4> cols;
-          for (const int4& o : st2) {
-            if (cols.empty() || cols.back().x != o.x || cols.back().y != o.y) {
-              bool found = false;
-              for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + r2); found = true; break; }
-              if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + r2), 0));
-            } else cols.back().z |= 1 << (o.z + r2);
-          }
+          const std::vector<int4>& cols = h->pc_cols_host;
           const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
           CK(h->bitmap.reserve(bm_bytes));
           CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
@@ -1179,7 +1204,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     if (d_dbg) {
       unsigned long long dd[8];
       CK(cudaMemcpyAsync(dd, d_dbg, 64, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       fprintf(stderr, "[vgs debug] units %llu chunks %llu (%.2f/unit) scanned %llu (%.1f/unit) kept %llu (%.1f/unit) m/unit %.1f final_nseg/unit %.2f nv/unit %.1f\n",
               dd[3], dd[0], (double)dd[0] / (double)std::max(1ull, dd[3]), dd[1], (double)dd[1] / (double)std::max(1ull, dd[3]), dd[2],
               (double)dd[2] / (double)std::max(1ull, dd[3]), (double)dd[4] / (double)std::max(1ull, dd[3]),
@@ -1188,7 +1213,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     if (use_warp) {   // units the warp kernel handed back: general CTA kernel sized for the largest neighbourhood
       uint32_t nfb = 0;
       CK(cudaMemcpyAsync(&nfb, d_fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       h->n_fallback = nfb;
       if (nfb) {
         const int ncap = (int)((max_n_all + 3u) & ~3u), mcap = CLASS_N_HOST[N_CLASSES - 1] * (CLASS_N_HOST[N_CLASSES - 1] - 1);
@@ -1233,7 +1258,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
            h->singles.as<uint32_t>(), d_scnt);
     uint32_t scnt[2] = {0, 0};
     CK(cudaMemcpyAsync(scnt, d_scnt, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     int rounds = 0;
     while (scnt[0] > 0) {
       CK(cudaMemsetAsync(d_changed, 0, 4, h->stream));
@@ -1242,7 +1267,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
              h->attach.as<int32_t>(), d_changed);
       uint32_t changed = 0;
       CK(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       rounds++;
       if (!changed) break;
       if (rounds > 100000) return h->fail(VGS_ERR_LIMIT, "vgs_segment: closest-check did not converge");
@@ -1282,7 +1307,7 @@ static vgs_status ensure_cluster_stats(vgs_handle h, int voxels_min) {
   LAUNCH(k_cluster_count, (unsigned)cdiv(nu, 256), 256, 0, h->root.as<int>(), h->csize.as<uint32_t>(), nu, min_excl, d_cnt);
   unsigned long long c2[2];
   CK(cudaMemcpyAsync(c2, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   h->n_clusters_all = (int64_t)c2[0]; h->n_clusters_exp = (int64_t)c2[1];
   h->have_cluster_stats = true; h->last_voxels_min = min_excl;
   return VGS_OK;
@@ -1314,7 +1339,7 @@ vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, i
     StageTimer t2(h, &h->tm.d2h_ms, 10);
     CK(cudaMemcpyAsync(labels, d_out, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
     t2.stop();
-    CK(cudaStreamSynchronize(h->stream));   // the caller's host buffer is valid on return
+    CK(stream_wait(h->stream));   // the caller's host buffer is valid on return
   }
   return VGS_OK;
 }
@@ -1328,7 +1353,7 @@ vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_cluster
   // Output formatting of a finished result: canonical labels come from the device; grouping the
   // point indices by label into the reference's vector<vector<int>> layout is done here.
   const int64_t n = h->n;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(stream_wait(h->stream));
   // cluster order of the reference = ascending smallest voxel id (clusteringVoxels seeds, VS.h:2064);
   // root ids are exactly those seeds.  Fetch per-point unit + per-unit root to order clusters.
   std::vector<int32_t> root((size_t)h->nu);
@@ -1403,7 +1428,7 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
   auto copy_out = [&](const void* src, size_t nbytes) -> vgs_status {
     if (!dst) { *bytes = nbytes; return VGS_OK; }
     if (*bytes < nbytes) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h->stream));
     CK(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost));
     *bytes = nbytes;
     return VGS_OK;
@@ -1438,7 +1463,7 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
       if (!dst) { *bytes = (size_t)(nu + 1) * 8; return VGS_OK; }
       if (*bytes < (size_t)(nu + 1) * 8) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
       std::vector<uint32_t> t32((size_t)nu + 1);
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       CK(cudaMemcpy(t32.data(), h->ustart.p, ((size_t)nu + 1) * 4, cudaMemcpyDeviceToHost));
       for (int64_t i = 0; i <= nu; i++) ((int64_t*)dst)[i] = t32[i];
       *bytes = (size_t)(nu + 1) * 8;
@@ -1451,7 +1476,7 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
       if (!dst) { *bytes = (size_t)(nu + 1) * 8; return VGS_OK; }
       if (*bytes < (size_t)(nu + 1) * 8) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
       std::vector<uint32_t> t32((size_t)nu + 1);
-      CK(cudaStreamSynchronize(h->stream));
+      CK(stream_wait(h->stream));
       CK(cudaMemcpy(t32.data(), h->adj_off.p, ((size_t)nu + 1) * 4, cudaMemcpyDeviceToHost));
       for (int64_t i = 0; i <= nu; i++) ((int64_t*)dst)[i] = t32[i];
       *bytes = (size_t)(nu + 1) * 8;
