@@ -40,11 +40,11 @@ out += [f"Same build, `python bench.py --steps {bench['steps']} --warmup {bench[
         f"through host buffers, {bench['gpu_launches']} launches in {bench['steps']} steps), stage timers (ms): {json.dumps(st)}.",
         f"Share check: graph stage (k_pair_cache + k_bin_classes + k_rs_* of the class lists + k_local_graph_*) = "
         f"{100 * st['graph'] / sum(st.values()):.1f}% of the CUDA-event stage sum; the same kernels are "
-        f"{100 * sum(a[1] for k, a in agg.items() if k in ('k_local_graph_warp', 'k_local_graph2', 'k_pair_cache', 'k_bin_classes', 'k_class_init')) / total:.1f}% "
+        f"{100 * sum(a[1] for k, a in agg.items() if k in ('k_local_graph_warp', 'k_local_graph2', 'k_pair_cache', 'k_pair_cache_bm', 'k_bitmap_set', 'k_bin_classes', 'k_class_init')) / total:.1f}% "
         "of the ncu total."]
 open(os.path.join(ROOT, "profiles", f"{tag}_launches_10M_final.md"), "w").write("\n".join(out) + "\n")
-dom = ("k_local_graph_warp", "k_local_graph2", "k_pair_cache", "k_bin_classes")
-json.dump({"kernel": "stage 4+5a: k_pair_cache + k_bin_classes + k_local_graph_warp / k_local_graph2 (all launches of one pipeline pass, 10 M-point construction site)",
+dom = ("k_local_graph_warp", "k_local_graph2", "k_pair_cache", "k_pair_cache_bm", "k_bitmap_set", "k_bin_classes", "k_class_init")
+json.dump({"kernel": "stage 4+5a: k_pair_cache_bm + k_bin_classes + k_local_graph_warp / k_local_graph2 (all launches of one pipeline pass, 10 M-point construction site)",
            "launches": sum(agg[k][0] for k in dom if k in agg),
            "dram_bytes_read": sum(agg[k][2] for k in dom if k in agg), "dram_bytes_write": sum(agg[k][3] for k in dom if k in agg),
            "gpu_time_ms_ncu": sum(agg[k][1] for k in dom if k in agg),
