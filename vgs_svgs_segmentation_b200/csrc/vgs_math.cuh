@@ -20,8 +20,18 @@
 
 namespace vgs {
 
+// double acos / exp behind a call on the device: pair_weights uses them seven times, and inlining every copy makes
+// the pair kernels exceed the instruction cache (ncu: no_instruction stalls)
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ double vgs_dacos(double x) { return acos(x); }
+static __device__ __noinline__ double vgs_dexp(double x) { return exp(x); }
+#else
+VGS_HD double vgs_dacos(double x) { return acos(x); }
+VGS_HD double vgs_dexp(double x) { return exp(x); }
+#endif
+
 // ---- correctly rounded float libm (double evaluation, one rounding) ----
-VGS_HD float cr_acosf(float x) { return (float)acos((double)x); }
+VGS_HD float cr_acosf(float x) { return (float)vgs_dacos((double)x); }
 VGS_HD float cr_sinf(float x) { return (float)sin((double)x); }
 VGS_HD float cr_cosf(float x) { return (float)cos((double)x); }
 VGS_HD float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
@@ -251,7 +261,7 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
         // acos(-x) = pi - acos(x) is evaluated in double and rounded once, i.e. the same correctly
         // rounded float as (float)acos(-(double)x) (the 1-ulp double error of the subtraction moves a float
         // with probability ~2^-28) — two double acos per pair instead of four.
-        const double ad1 = acos((double)c1d), ad2 = acos((double)c2d);
+        const double ad1 = vgs_dacos((double)c1d), ad2 = vgs_dacos((double)c2d);
         a1 = (double)(float)ad1; a2 = (double)(float)ad2;
         b1 = (double)(float)(3.14159265358979323846 - ad2); b2 = (double)(float)(3.14159265358979323846 - ad1);
         ads1 = (double)cr_acosf(cds);
@@ -260,7 +270,7 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
     }
     if (!P.svgs) {
       double max_singular = PI / 2;
-      float thr = (float)((double)(float)max_singular / (1 + exp(-1 * 0.5 * (a12 - PI / 6))));
+      float thr = (float)((double)(float)max_singular / (1 + vgs_dexp(-1 * 0.5 * (a12 - PI / 6))));
       double ads = ads1;
       if (ads1 > ads2) ads = ads2;
       if (ads > (double)thr) { C_ab = (float)fabs(a1 - a2); C_ba = (float)fabs(b1 - b2); }
@@ -283,17 +293,17 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
     double ee = (double)qe * (double)qe;
     float qc = C_ab / P.sig_c;
     float sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-    w_ab = (float)exp(-0.5 * (double)sd / w2);
+    w_ab = (float)vgs_dexp(-0.5 * (double)sd / w2);
     if (f2u(C_ba) == f2u(C_ab)) { w_ba = w_ab; }
     else {
       qc = C_ba / P.sig_c;
       sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-      w_ba = (float)exp(-0.5 * (double)sd / w2);
+      w_ba = (float)vgs_dexp(-0.5 * (double)sd / w2);
     }
   } else {
     float sd = (float)sqrt((double)S * (double)S / (double)P.sig_p + (double)A * (double)A / (double)P.sig_n +
                            (double)E * (double)E / (double)P.sig_e + (double)T * (double)T / (double)P.sig_o);
-    w_ab = (float)exp(-0.5 * (double)sd / w2);
+    w_ab = (float)vgs_dexp(-0.5 * (double)sd / w2);
     w_ba = w_ab;
   }
 }
