@@ -16,7 +16,7 @@ hs = []
 for path in paths:
     capi._lib, capi.SO_PATH = None, os.path.abspath(path)
     hs.append(capi.Handle(stream=torch.cuda.current_stream().cuda_stream))
-keys = ("total_ms", "graph_ms", "pair_cache_ms", "adjacency_ms", "components_ms", "voxelize_ms")
+keys = ("total_ms", "graph_ms", "pair_cache_ms", "adjacency_ms", "mutual_ms", "components_ms", "labels_ms", "voxelize_ms")
 res = [{k: [] for k in keys} for _ in paths]
 for it in range(13):
     for i, h in enumerate(hs):

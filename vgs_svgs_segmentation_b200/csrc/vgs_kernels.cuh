@@ -1497,10 +1497,17 @@ __global__ void __launch_bounds__(256) k_cluster_stats(const int* __restrict__ r
                                                      const uint32_t* __restrict__ perm, int64_t nu, uint32_t* __restrict__ csize,
                                                      uint32_t* __restrict__ cminpt) {
   int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= nu) return;
-  int r = root[u];
-  atomicAdd(&csize[r], 1u);
-  atomicMin(&cminpt[r], perm[ustart[u]]);  // the unit's points ascend by index
+  const bool ok = u < nu;
+  const int lane = threadIdx.x & 31;
+  const int r = ok ? root[u] : -1 - lane;              // out-of-range lanes form singleton groups
+  const uint32_t mp = ok ? perm[ustart[u]] : 0xffffffffu;   // the unit's points ascend by index
+  // neighbouring units mostly share their cluster: one atomic pair per distinct root and warp
+  const uint32_t peers = __match_any_sync(0xffffffffu, r);
+  const uint32_t mn = __reduce_min_sync(peers, mp);
+  if (ok && lane == __ffs(peers) - 1) {
+    atomicAdd(&csize[r], (uint32_t)__popc(peers));
+    atomicMin(&cminpt[r], mn);
+  }
 }
 __global__ void __launch_bounds__(256) k_cluster_count(const int* __restrict__ root, const uint32_t* __restrict__ csize, int64_t nu,
                                                      int min_size_excl, unsigned long long* __restrict__ out2) {
