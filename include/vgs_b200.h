@@ -140,6 +140,9 @@ vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* s, float cut_thred, int a
  *    adjacency slots [e_first, e_last) of vgs_adj_range. -- */
 vgs_status vgs_segment_partial(vgs_handle h, const vgs_sigmas* s, float cut_thred, int64_t first_unit, int64_t last_unit);
 vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, int64_t* e_first, int64_t* e_last);
+/* balanced partition for `parts` ranks: contiguous unit-id ranges with ~equal sum of (neighbourhood size)^2 and the
+ * adjacency slots they cover; both arrays have parts + 1 entries (identical on every rank) */
+vgs_status vgs_unit_ranges(vgs_handle h, int parts, int64_t* first_unit, int64_t* first_slot);
 vgs_status vgs_export_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, int32_t* cnt_dev, int32_t* idx_dev);
 vgs_status vgs_import_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, const int32_t* cnt_dev, const int32_t* idx_dev);
 vgs_status vgs_segment_finish(vgs_handle h, const vgs_sigmas* s, float cut_thred, int adjacency_min);

@@ -80,3 +80,21 @@ def test_partitioned_two_gpus_equals_single(built_lib, tmp_path):
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "MULTIGPU_OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_library_unit_ranges_equal_python_rule(built_lib):
+    """vgs_unit_ranges (evaluated inside the library, no numpy on the step path) = unit_ranges() on the same offsets"""
+    from vgs_svgs_segmentation_b200 import capi, scenes
+    from vgs_svgs_segmentation_b200.multigpu import unit_ranges
+    xyz = scenes.construction_site(150_000, seed=4, extent=9.0)
+    h = capi.Handle()
+    h.set_points(xyz)
+    h.voxelize(0.15)
+    h.compute_features(10)
+    h.find_adjacency(0.5)
+    off = h.blob("ADJ_OFFSETS")
+    for world in (1, 2, 3, 8):
+        ranges, slots = h.unit_ranges(world)
+        assert ranges == unit_ranges(off, world)
+        assert slots == [(int(off[a]), int(off[b])) for a, b in ranges]

@@ -112,6 +112,7 @@ struct vgs_context {
   } vc;
   int64_t vccs_seeds = 0;
 
+  std::vector<uint32_t> host_u32;   // host staging of small index arrays
   vgs_timings tm{};
   cudaEvent_t ev[32] = {};
   float* tm_slot[16] = {};
@@ -1025,6 +1026,35 @@ vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, in
   CK(cudaMemcpyAsync(&b, h->adj_off.as<uint32_t>() + last_unit, 4, cudaMemcpyDeviceToHost, h->stream));
   CK(stream_wait(h->stream));
   *e_first = a; *e_last = b;
+  return VGS_OK;
+}
+
+// Contiguous unit-id ranges with ~equal sum of n^2 (n = neighbourhood size, the pair-work proxy) for `parts` ranks,
+// and the adjacency slots they cover: first_unit / first_slot have parts + 1 entries.  Deterministic, identical on
+// every rank (all ranks hold the same adjacency).
+vgs_status vgs_unit_ranges(vgs_handle h, int parts, int64_t* first_unit, int64_t* first_slot) {
+  if (!h || !first_unit || !first_slot || parts < 1) return VGS_ERR_INVALID;
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_unit_ranges: call vgs_find_adjacency first");
+  CK(cudaSetDevice(h->device));
+  const int64_t nu = h->nu;
+  h->host_u32.resize((size_t)nu + 1);
+  CK(cudaMemcpyAsync(h->host_u32.data(), h->adj_off.p, (size_t)(nu + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(stream_wait(h->stream));
+  const uint32_t* off = h->host_u32.data();
+  double total = 0;
+  for (int64_t u = 0; u < nu; u++) { const double n = (double)(off[u + 1] - off[u]); total += n * n; }
+  first_unit[0] = 0;
+  int r = 1;
+  double acc = 0;
+  for (int64_t u = 0; u < nu && r < parts; u++) {
+    // cut before the first unit whose prefix sum reaches r/parts of the total (numpy.searchsorted(w, t, 'left'))
+    while (r < parts && acc >= total * (double)r / (double)parts) first_unit[r++] = u;
+    const double n = (double)(off[u + 1] - off[u]);
+    acc += n * n;
+  }
+  while (r < parts) first_unit[r++] = nu;
+  first_unit[parts] = nu;
+  for (int i = 0; i <= parts; i++) first_slot[i] = (int64_t)off[first_unit[i]];
   return VGS_OK;
 }
 

@@ -58,17 +58,27 @@ def segment_partitioned(h, params, rank: int, world: int, labels_out=None, on_de
     if world == 1:
         h.segment(sig, p.cut_thred, p.adjacency_min)
     else:
-        adj_off = h.blob("ADJ_OFFSETS")
-        ranges = unit_ranges(adj_off, world)
-        slots = [(int(adj_off[a]), int(adj_off[b])) for a, b in ranges]
+        ranges, slots = h.unit_ranges(world)      # same rule as unit_ranges() below, evaluated by the library
         a, b = ranges[rank]
         h.segment_partial(sig, p.cut_thred, a, b)
         dev = torch.device("cuda", torch.cuda.current_device())
+        pool = h.__dict__.setdefault("_exchange_pool", {})   # exchange buffers are reused across steps
+
+        counter = [0]
+
+        def new_tensor(n):
+            k = counter[0]
+            counter[0] += 1
+            t = pool.get(k)
+            if t is None or t.numel() < n or t.device != dev:
+                t = torch.empty(max(int(n) + int(n) // 8, 1), dtype=torch.int32, device=dev)
+                pool[k] = t
+            return t[:max(int(n), 1)]
         exchange_connect(
             ranges, slots, rank,
             export_fn=lambda f, l, c, i: h.export_connect(f, l, c.data_ptr(), i.data_ptr()),
             import_fn=lambda f, l, c, i: h.import_connect(f, l, c.data_ptr(), i.data_ptr()),
-            new_tensor=lambda n: torch.empty(max(int(n), 1), dtype=torch.int32, device=dev),
+            new_tensor=new_tensor,
             broadcast=lambda t, src: dist.broadcast(t, src=src))
         h.segment_finish(sig, p.cut_thred, p.adjacency_min)
     if labels_out is None:
