@@ -178,6 +178,16 @@ def test_vgs_pair_cache_without_bitmap(built_lib, monkeypatch):
     _compare_vgs(xyz, g, oracle.run(xyz, math=1))
 
 
+def test_vgs_single_stream_classes(built_lib, monkeypatch):
+    """VGS_B200_CLASS_STREAMS=1: all size-class launches on the handle's stream (default: 6 streams, forked / joined with
+    events); the connect lists do not depend on how the launches overlap."""
+    monkeypatch.setenv("VGS_B200_CLASS_STREAMS", "1")
+    xyz = _scene("site")
+    g = gpu_stages(xyz)
+    monkeypatch.delenv("VGS_B200_CLASS_STREAMS")
+    _compare_vgs(xyz, g, oracle.run(xyz, math=1))
+
+
 def test_vgs_adjacency_two_pass(built_lib, monkeypatch):
     """VGS_B200_ADJ_TWO_PASS=1: count / scan / probe-again adjacency (used when the staging rows of the one-pass
     variant would not fit) gives the same lists as the default one-pass build."""

@@ -115,6 +115,12 @@ struct vgs_context {
   std::vector<uint32_t> host_u32;   // host staging of small index arrays
   vgs_timings tm{};
   cudaEvent_t ev[32] = {};
+  // the size-class launches of the local graph stage are independent: they run on the handle's stream plus these,
+  // forked / joined with events, so that the small classes of big units fill the tails of the large ones
+  static constexpr int N_AUX = 7;
+  cudaStream_t aux[N_AUX] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {};
+  int class_streams = 6;            // VGS_B200_CLASS_STREAMS (1 = everything on the handle's stream; measured flat from 4 to 8)
   float* tm_slot[16] = {};
   unsigned tm_pending = 0;
 
@@ -147,6 +153,13 @@ static inline cudaError_t stream_wait(cudaStream_t st) {
 #define LAUNCH(kernel, grid, block, smem, ...)                                \
   do {                                                                        \
     kernel<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__);              \
+    h->launches++;                                                            \
+    CK(cudaGetLastError());                                                   \
+  } while (0)
+
+#define LAUNCH_ON(st, kernel, grid, block, smem, ...)                        \
+  do {                                                                        \
+    kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                   \
     h->launches++;                                                            \
     CK(cudaGetLastError());                                                   \
   } while (0)
@@ -351,6 +364,12 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     h->own_stream = true;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  for (int i = 0; i < vgs_context::N_AUX; i++) {
+    cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (const char* e_cs = getenv("VGS_B200_CLASS_STREAMS")) { int v = atoi(e_cs); if (v >= 1 && v <= 1 + vgs_context::N_AUX) h->class_streams = v; }
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   if (const char* e_bm = getenv("VGS_B200_NO_BITMAP")) h->use_bitmap = (e_bm[0] == '1') ? 0 : 1;
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
@@ -403,6 +422,8 @@ void vgs_destroy(vgs_handle h) {
                  &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.cnt, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < vgs_context::N_AUX; i++) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1202,7 +1223,14 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     size_t class_off[N_CLASSES + 1];
     class_off[0] = 0;
     for (int c = 0; c < N_CLASSES; c++) class_off[c + 1] = class_off[c] + cc[c];
-    for (int c = 0; c < N_CLASSES; c++) {
+    // classes of big units first (few units, long per-unit time), spread over the class streams
+    const int nstreams = use_warp ? h->class_streams : 1;
+    if (nstreams > 1) {
+      CK(cudaEventRecord(h->ev_fork, h->stream));
+      for (int i = 0; i < nstreams - 1; i++) CK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
+    }
+    int launch_no = 0;
+    for (int c = N_CLASSES - 1; c >= 0; c--) {
       if (!cc[c]) continue;
       const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
       if (use_warp && CLASS_N_HOST[c] <= 128) {
@@ -1210,7 +1238,9 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         const uint32_t* wlist = cls_sorted + class_off[c];
         unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
         scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
-        LAUNCH(k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
+        const int si = launch_no++ % nstreams;
+        cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
+        LAUNCH_ON(st, k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->uflags.as<uint8_t>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
                h->fallback.as<uint32_t>(), d_fb_count, scratch, h->lw_chunk, d_dbg);
@@ -1231,6 +1261,11 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else LG(256, false); }
 #undef LG
     }
+    if (nstreams > 1)
+      for (int i = 0; i < nstreams - 1; i++) {
+        CK(cudaEventRecord(h->ev_join[i], h->aux[i]));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
+      }
     if (d_dbg) {
       unsigned long long dd[8];
       CK(cudaMemcpyAsync(dd, d_dbg, 64, cudaMemcpyDeviceToHost, h->stream));
