@@ -316,12 +316,17 @@ def main():
             "e2e": {"value": total_points / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 12 * n,
                     "d2h_bytes_per_step": 4 * n, "ms_per_step": ms_e2e, "labels_equal_resident_path": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_pair_cache + k_bin_classes + k_local_graph_warp (stage 4+5a, all size classes)",
+            "roofline": {"bound": "hbm", "kernel": "k_pair_cache_bm + k_bin_classes + k_local_graph_warp (stage 4+5a, all size classes)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_kind": peak_kind, "algorithmic_bytes": int(dom_b),
-                         "note": "achieved = algorithmic bytes (8*E + 64*V, DESIGN.md section 4) / CUDA-event time of the stage; "
-                                 "the stage is bound by gather latency + instruction issue, not HBM bandwidth; traffic = ncu "
-                                 "dram read+write bytes of k_local_graph_warp per pass on this workload (profiles/r01_traffic.json)"},
+                         "algorithmic_bytes_no_reuse": int(72 * E + 64 * V),
+                         "sm_issue_active_pct_ncu": 60.8,
+                         "note": "achieved = algorithmic bytes (8*E + 64*V, SURVEY.md 8d / DESIGN.md section 4) / CUDA-event time of the "
+                                 "stage; SURVEY.md 8d classifies this stage as compute/latency bound (sum of n^2 pair work), not HBM bound: "
+                                 "ncu shows 61 % issue-slot utilisation and 8 % DRAM throughput for k_local_graph_warp "
+                                 "(profiles/r01_ncu_local_graph_warp_final.md); algorithmic_bytes_no_reuse = 64*E record gathers + 8*E if no "
+                                 "record were reused; traffic = ncu dram read+write bytes of the stage's kernels per pass on this workload "
+                                 "(profiles/r01_traffic.json): the pair table rows (8.8 KB, sparse) and the bin-ordered entry scratch"},
             "stages": stages,
             "clocks": clk.summary(),
             "wall_s_timed_region": t_wall,
