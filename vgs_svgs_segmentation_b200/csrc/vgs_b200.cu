@@ -1224,7 +1224,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     class_off[0] = 0;
     for (int c = 0; c < N_CLASSES; c++) class_off[c + 1] = class_off[c] + cc[c];
     // classes of big units first (few units, long per-unit time), spread over the class streams
-    const int nstreams = use_warp ? h->class_streams : 1;
+    const int nstreams = h->class_streams;
     if (nstreams > 1) {
       CK(cudaEventRecord(h->ev_fork, h->stream));
       for (int i = 0; i < nstreams - 1; i++) CK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
@@ -1233,13 +1233,13 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     for (int c = N_CLASSES - 1; c >= 0; c--) {
       if (!cc[c]) continue;
       const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
+      const int si = launch_no++ % nstreams;
+      cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
       if (use_warp && CLASS_N_HOST[c] <= 128) {
         const size_t slice = lw_slice_bytes(ncap, mcap);
         const uint32_t* wlist = cls_sorted + class_off[c];
         unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
         scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
-        const int si = launch_no++ % nstreams;
-        cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
         LAUNCH_ON(st, k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->uflags.as<uint8_t>(), h->key3.as<uint32_t>(), cut_thred, ncap,
                mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
@@ -1253,7 +1253,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
 #define LG(TT, CC)                                                                                                  \
   do {                                                                                                              \
     auto kfn = k_local_graph2<TT, CC>;                                                                              \
-    LAUNCH(kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),                  \
+    LAUNCH_ON(st, kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),           \
            h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2,        \
            d_wempty, bucketed, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
   } while (0)

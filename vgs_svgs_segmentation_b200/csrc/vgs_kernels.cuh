@@ -1347,35 +1347,7 @@ __global__ void __launch_bounds__(128) k_mutual(const uint32_t* __restrict__ adj
 // ---- stage 5c: closestCheck (VS.h:2181-2303) as a fixed-point iteration.  The reference visits
 //      units in id order and links in place, so a single unit i may attach to a smaller-id single
 //      that already attached.  attach[i] depends only on attach[c], c < i, hence iterating to a
-//      fixed point reproduces the sequential result.  One thread per single unit. ----
-__global__ void __launch_bounds__(128) k_closest_round(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
-                                                     const uint32_t* __restrict__ cnt1, const float* __restrict__ rec, int64_t nu,
-                                                     int adjacency_min, PairParams pp, int32_t* attach, uint32_t* __restrict__ changed,
-                                                     unsigned long long* __restrict__ n_singles) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nu) return;
-  if (cnt1[i] != 1u) return;
-  if (n_singles) atomicAdd(n_singles, 1ull);
-  const uint32_t off = adj_off[i];
-  const int n = (int)(adj_off[i + 1] - off);
-  if (!(n + 1 > adjacency_min)) return;   // voxels_adjacency_idx_[i].size() = count + 1 (VS.h:2201)
-  float ri[REC_FLOATS], rc[REC_FLOATS];
-  for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
-  float best = 0.f;
-  int bi = -1;
-  for (int j = 0; j <= n; j++) {
-    int64_t c = (j == 0) ? (int64_t)n : (int64_t)adj_idx[off + j - 1];  // slot 0 is the COUNT (VS.h:2243)
-    if (c < 0 || c >= nu) continue;
-    uint32_t cc = cnt1[c];
-    bool q = cc > 1u || (cc == 1u && c < i && ((volatile int32_t*)attach)[c] >= 0);
-    if (!q) continue;
-    for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
-    float w_ab, w_ba;
-    pair_weights(ri, rc, pp, w_ab, w_ba);
-    if (w_ab >= best) { best = w_ab; bi = (int)c; }
-  }
-  if (bi != attach[i]) { attach[i] = bi; *changed = 1u; }
-}
+//      fixed point reproduces the sequential result.  One warp per single unit (k_closest_round_warp). ----
 
 // units whose list is {self} after the mutual filter and that have enough neighbours (VS.h:2199-2201)
 __global__ void __launch_bounds__(256) k_collect_singles(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1, int64_t nu,
