@@ -150,3 +150,39 @@ def test_gpu_vccs_state_errors(built_lib):
         h.make_supervoxels_vccs()          # not voxelised yet
     with pytest.raises(capi.VgsError):
         h.supervoxel_labels()
+
+
+@pytest.mark.gpu
+def test_gpu_vccs_nonfinite_points_and_tiny_clouds(built_lib):
+    """non-finite points never enter the octree: label 0, everything else as the oracle; a cloud of a few points still
+    yields labels (or a clean VGS_ERR_INVALID when no seed survives) instead of a crash"""
+    from oracle import oracle
+    from vgs_svgs_segmentation_b200 import capi
+    xyz, _ = _scene("planes")
+    xyz = xyz.copy()
+    bad = np.arange(0, len(xyz), 97)
+    xyz[bad[0::3], 0] = np.nan
+    xyz[bad[1::3], 1] = np.inf
+    xyz[bad[2::3], 2] = -np.inf
+    h = capi.Handle(mode=capi.VGS_MODE_SVGS)
+    h.set_points(xyz)
+    h.voxelize(0.05)
+    h.make_supervoxels_vccs()
+    lab, ml = h.supervoxel_labels()
+    ref = oracle.vccs(xyz, schedule=1)
+    assert (lab[bad] == 0).all()
+    assert ml == ref.max_label
+    np.testing.assert_array_equal(lab, ref.point_label)
+    for n in (1, 5, 60):
+        tiny = np.ascontiguousarray(xyz[np.isfinite(xyz).all(axis=1)][:n])
+        h = capi.Handle(mode=capi.VGS_MODE_SVGS)
+        h.set_points(tiny)
+        h.voxelize(0.05)
+        try:
+            h.make_supervoxels_vccs()
+        except capi.VgsError as e:
+            assert e.status == 1, e          # VGS_ERR_INVALID: no seed survived
+            continue
+        lab, ml = h.supervoxel_labels()
+        r = oracle.vccs(tiny, schedule=1)
+        assert ml == r.max_label and np.array_equal(lab, r.point_label)
