@@ -79,6 +79,8 @@ def lib():
         L.vgso_pair.argtypes = [C.POINTER(Params)] + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] * 2 + [C.c_void_p]
         L.vgso_eigen33.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.vgso_features.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int64, C.c_void_p]
+        L.vgso_set_threads.argtypes = [C.c_int]
+        L.vgso_set_threads.restype = C.c_int
         L.vgso_cut.restype = C.c_int
         L.vgso_cut.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         L.vgso_vccs.restype = C.c_int
@@ -86,6 +88,11 @@ def lib():
                                 C.POINTER(VccsParams), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def set_threads(n: int):
+    """threads of the per-unit local-graph loop (1 = as the reference runs; results do not depend on it)"""
+    return int(lib().vgso_set_threads(int(n)))
 
 
 def make_params(**kw) -> Params:

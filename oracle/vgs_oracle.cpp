@@ -28,6 +28,13 @@
 #include <unordered_map>
 #include <vector>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <array>
+
+static int g_threads = 1;   // vgso_set_threads
+
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -742,29 +749,51 @@ int vgso_handle_s::run(const float* xyz, int64_t N, int stride, const int32_t* l
   Sig sg{p.sig_p, p.sig_n, p.sig_o, p.sig_e, p.sig_c, p.sig_w};
   float near_tol = p.near_tol > 0 ? p.near_tol : 1e-5f;
   conn.assign((size_t)V, {});
+  // The units are independent of each other; the reference runs them one after the other on one thread.  With
+  // vgso_set_threads(n > 1) (bench.py --impl reference: "all the host threads it can use") the loop is split over
+  // OpenMP threads — same arithmetic per unit, counters and near-threshold records merged afterwards in unit order.
   {
-    std::vector<float> W;
-    std::vector<int> members;
-    for (int64_t i = 0; i < V; i++) {
-      if (!used[i]) continue;
-      const int nn = adj[i][0];
-      const int* gid = adj[i].data() + 1;
-      W.assign((size_t)nn * nn, 0.f);
-      for (int a = 0; a < nn; a++)
-        for (int b = 0; b < nn; b++) {
-          if (a != b) {
-            float d5[5];
-            measuring_distance<MATH>(attr[gid[a]], attr[gid[b]], svgs, d5, &stats[7]);
-            float w = distance_weight(d5, sg, svgs);
-            if (std::isnan(w)) stats[6]++;
-            W[(size_t)a * nn + b] = w;
-            stats[5]++;
-          } else W[(size_t)a * nn + b] = 1.f;
-        }
-      cut_graph(p.cut_thred, W.data(), nn, members, near_tol, &stats[8], &near, (int)i, gid);
-      conn[i].resize(members.size());
-      for (size_t j = 0; j < members.size(); j++) conn[i][j] = gid[members[j]];
+    const int nthreads = std::max(1, g_threads);
+    std::vector<std::array<int64_t, 4>> tstats((size_t)nthreads, std::array<int64_t, 4>{0, 0, 0, 0});
+    std::vector<std::vector<NearRec>> tnear((size_t)nthreads);
+#pragma omp parallel num_threads(nthreads)
+    {
+#ifdef _OPENMP
+      const int tid = omp_get_thread_num();
+#else
+      const int tid = 0;
+#endif
+      std::vector<float> W;
+      std::vector<int> members;
+      int64_t* st = tstats[(size_t)tid].data();   // [0] pair evals  [1] NaN weights  [2] ub corner  [3] near threshold
+#pragma omp for schedule(dynamic, 64)
+      for (int64_t i = 0; i < V; i++) {
+        if (!used[i]) continue;
+        const int nn = adj[i][0];
+        const int* gid = adj[i].data() + 1;
+        W.assign((size_t)nn * nn, 0.f);
+        for (int a = 0; a < nn; a++)
+          for (int b = 0; b < nn; b++) {
+            if (a != b) {
+              float d5[5];
+              measuring_distance<MATH>(attr[gid[a]], attr[gid[b]], svgs, d5, &st[2]);
+              float w = distance_weight(d5, sg, svgs);
+              if (std::isnan(w)) st[1]++;
+              W[(size_t)a * nn + b] = w;
+              st[0]++;
+            } else W[(size_t)a * nn + b] = 1.f;
+          }
+        cut_graph(p.cut_thred, W.data(), nn, members, near_tol, &st[3], &tnear[(size_t)tid], (int)i, gid);
+        conn[i].resize(members.size());
+        for (size_t j = 0; j < members.size(); j++) conn[i][j] = gid[members[j]];
+      }
     }
+    for (int t = 0; t < nthreads; t++) {
+      stats[5] += tstats[(size_t)t][0]; stats[6] += tstats[(size_t)t][1]; stats[7] += tstats[(size_t)t][2]; stats[8] += tstats[(size_t)t][3];
+      near.insert(near.end(), tnear[(size_t)t].begin(), tnear[(size_t)t].end());
+    }
+    if (nthreads > 1)
+      std::stable_sort(near.begin(), near.end(), [](const NearRec& a, const NearRec& b) { return a.centre < b.centre; });
   }
   c_conn0.from(conn, true);
 
@@ -866,6 +895,16 @@ int vgso_handle_s::run(const float* xyz, int64_t N, int stride, const int32_t* l
 }
 
 extern "C" {
+
+int vgso_set_threads(int n) {
+#ifdef _OPENMP
+  g_threads = n > 0 ? n : 1;
+#else
+  (void)n;
+  g_threads = 1;   // built without OpenMP
+#endif
+  return g_threads;
+}
 
 vgso_handle vgso_create(const vgso_params* p) {
   vgso_handle h = new vgso_handle_s();

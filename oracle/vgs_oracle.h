@@ -92,6 +92,9 @@ void vgso_features(const vgso_params* p, const float* xyz, int64_t n, float* out
 /* cutGraphSegmentation on a dense n x n matrix (row-major W[row*n+col]); returns member count,
  * members (local ids ascending) into out */
 int vgso_cut(float cut_thred, const float* w, int n, int32_t* out);
+/* threads for the per-unit local-graph loop of vgso_run (default 1 = as the reference runs it).  Results do not
+ * depend on the value.  Returns the number in effect (1 when the oracle was built without OpenMP). */
+int vgso_set_threads(int n);
 
 /* ---- supervoxel generator (vccs_oracle.cpp): restatement of pcl::SupervoxelClustering as the reference
  *      drives it in createSupervoxels (supervoxel_segmentation.h:245-284).  Third-party algorithm, PARITY

@@ -204,3 +204,20 @@ def test_mutual_filter_and_labels_are_canonical():
     lab = r.point_label
     for l in np.unique(lab[lab >= 0]):
         assert np.flatnonzero(lab == l).min() == l              # label = smallest point index of the cluster
+
+
+def test_threaded_oracle_equals_single_thread():
+    """vgso_set_threads only splits the per-unit loop (bench.py --impl reference): every output is unchanged"""
+    from vgs_svgs_segmentation_b200 import scenes
+    xyz = scenes.two_planes(40_000)
+    a = oracle.run(xyz, math=0)
+    n = oracle.set_threads(4)
+    try:
+        b = oracle.run(xyz, math=0)
+    finally:
+        oracle.set_threads(1)
+    assert n in (1, 4)          # 1 when the oracle was built without OpenMP
+    assert a.stats == b.stats
+    for k in a:
+        if k != "stats":
+            np.testing.assert_array_equal(a[k], b[k])
