@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--points", type=int, default=10_000_000)
-    ap.add_argument("--ref-points", type=int, default=400_000)
+    ap.add_argument("--ref-points", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--mode", default="tiles", choices=["tiles", "partitioned"],
