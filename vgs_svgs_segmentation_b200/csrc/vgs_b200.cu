@@ -1134,7 +1134,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     uint32_t* d_maxn = h->class_count.as<uint32_t>() + 16;
     CK(cudaMemsetAsync(h->class_count.p, 0, 256, h->stream));
     CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
-    CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));
+    CK(cudaMemsetAsync(h->conn0_cnt.as<uint32_t>() + first, 0, (size_t)(last - first) * 4, h->stream));   // own range only: other ranges are imported / computed by other calls
     LAUNCH(k_wempty, 1, 1, 0, gp.pp, d_wempty);
     const bool partial = !(first == 0 && last == nu);
     uint8_t* d_need = nullptr;
