@@ -1179,7 +1179,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         const std::vector<int4>& st2 = h->st2_host;
         CK(h->pair_table.reserve(bytes));
         StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
-        if (h->use_bitmap && h->depth <= 11 && r2 <= 15 && half < 65536) {
+        if (h->use_bitmap && h->depth <= 11 && 2 * r2 + 1 <= 13 && half < 65536) {   // PC_QCAP holds 13 hits per column and lane
           // partner search on an occupancy bitmap of the used voxels: stencil columns (dx, dy, mask of dz)
           const std::vector<int4>& cols = h->pc_cols_host;
           const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
