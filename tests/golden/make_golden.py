@@ -21,6 +21,14 @@ CASES = {
 }
 
 
+# supervoxel generator (oracle/vccs_oracle.cpp): Task_File_SVGS.txt values, both schedules
+VCCS_CASES = {
+    "vccs_two_planes_20k": dict(scene=("two_planes", dict(n_points=20_000, seed=3)),
+                                params=dict(voxel_res=0.05, seed_res=0.25, color_importance=0.0, spatial_importance=0.25,
+                                            normal_importance=0.75, refine_iterations=5)),
+}
+
+
 def make_scene(spec):
     name, kw = spec
     return getattr(scenes, name)(**kw)
@@ -40,6 +48,17 @@ def main():
             unit_cluster=r.unit_cluster, point_label=r.point_label,
             stats=np.array([r.stats[k] for k in oracle.STAT_NAMES], np.int64))
         print(name, r.stats)
+    for name, case in VCCS_CASES.items():
+        xyz = make_scene(case["scene"])
+        seq = oracle.vccs(xyz, schedule=0, **case["params"])
+        syn = oracle.vccs(xyz, schedule=1, **case["params"])
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            xyz_sha=np.frombuffer(__import__("hashlib").sha256(xyz.tobytes()).digest(), np.uint8),
+            label_sequential=seq.point_label, max_label_sequential=np.int32(seq.max_label),
+            label_synchronous=syn.point_label, max_label_synchronous=np.int32(syn.max_label),
+            vox_normal=syn.vox_normal, n_seeds=np.int32(syn.n_seeds))
+        print(name, "seeds", syn.n_seeds, "max label", seq.max_label, syn.max_label)
 
 
 if __name__ == "__main__":
