@@ -5,6 +5,7 @@
 //   saveColoredClusters   : PCD writer (binary, x y z rgb), one deterministic colour per cluster
 // The reference's PCLVisualizer windows (showColoredClusters) are out of scope (GUI).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -136,6 +137,100 @@ inline int inputPointCloudData(const std::string& name, PCXYZPtr cloud) {
   return 0;
 }
 
+// IO.h:83-97 inputPointCloudData2 — PLY point cloud (pcl::io::loadPLYFile): header-driven reader for `format ascii`,
+// `binary_little_endian` and `binary_big_endian`; the vertex element's x, y, z may be float or double and may be
+// surrounded by any scalar properties (colours, normals, intensity ...); list properties inside the vertex element
+// and elements before it are skipped by size; everything after the vertex element (faces) is ignored.
+// Returns 0, or a negative code (-1 cannot open, -2 not a PLY / bad header, -3 no x/y/z, -4 truncated data).
+inline int inputPointCloudData2(const std::string& name, PCXYZPtr cloud) {
+  std::ifstream f(name, std::ios::binary);
+  if (!f) return -1;
+  struct Prop { std::string type, list_count; bool is_list = false; int role = -1; };
+  struct Elem { std::string name; long count = 0; std::vector<Prop> props; };
+  auto type_size = [](const std::string& t) -> int {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+  };
+  std::string line;
+  if (!std::getline(f, line) || vgs_rstrip(line) != "ply") return -2;
+  int fmt = -1;   // 0 ascii, 1 little endian, 2 big endian
+  std::vector<Elem> elems;
+  bool ended = false;
+  while (std::getline(f, line)) {
+    line = vgs_rstrip(line);
+    std::istringstream ss(line);
+    std::string tok;
+    ss >> tok;
+    if (tok == "format") {
+      std::string kind; ss >> kind;
+      fmt = kind == "ascii" ? 0 : kind == "binary_little_endian" ? 1 : kind == "binary_big_endian" ? 2 : -1;
+    } else if (tok == "element") {
+      Elem e; ss >> e.name >> e.count; elems.push_back(e);
+    } else if (tok == "property") {
+      if (elems.empty()) return -2;
+      Prop p; std::string t; ss >> t;
+      if (t == "list") { p.is_list = true; ss >> p.list_count >> p.type; }
+      else p.type = t;
+      std::string pname; ss >> pname;
+      if (!p.is_list) p.role = pname == "x" ? 0 : pname == "y" ? 1 : pname == "z" ? 2 : -1;
+      elems.back().props.push_back(p);
+    } else if (tok == "end_header") { ended = true; break; }
+  }
+  if (!ended || fmt < 0) return -2;
+  auto read_scalar = [&](const std::string& t, double& v) -> bool {   // binary scalar -> double
+    unsigned char b[8];
+    const int sz = type_size(t);
+    if (sz == 0) return false;
+    f.read(reinterpret_cast<char*>(b), sz);
+    if (f.gcount() != sz) return false;
+    if (fmt == 2) for (int i = 0; i < sz / 2; i++) std::swap(b[i], b[sz - 1 - i]);
+    if (t == "float" || t == "float32") { float x; std::memcpy(&x, b, 4); v = x; }
+    else if (t == "double" || t == "float64") { double x; std::memcpy(&x, b, 8); v = x; }
+    else if (t == "char" || t == "int8") { signed char x; std::memcpy(&x, b, 1); v = x; }
+    else if (t == "uchar" || t == "uint8") { v = b[0]; }
+    else if (t == "short" || t == "int16") { std::int16_t x; std::memcpy(&x, b, 2); v = x; }
+    else if (t == "ushort" || t == "uint16") { std::uint16_t x; std::memcpy(&x, b, 2); v = x; }
+    else if (t == "int" || t == "int32") { std::int32_t x; std::memcpy(&x, b, 4); v = x; }
+    else { std::uint32_t x; std::memcpy(&x, b, 4); v = x; }
+    return true;
+  };
+  cloud->points.clear();
+  for (const Elem& e : elems) {
+    const bool is_vertex = e.name == "vertex";
+    if (is_vertex) {
+      bool have[3] = {false, false, false};
+      for (const Prop& p : e.props) if (p.role >= 0) have[p.role] = true;
+      if (!(have[0] && have[1] && have[2])) return -3;
+      cloud->points.reserve((size_t)e.count);
+    }
+    for (long i = 0; i < e.count; i++) {
+      float xyz[3] = {0, 0, 0};
+      if (fmt == 0) {
+        if (!std::getline(f, line)) return -4;
+        std::istringstream ss(line);
+        for (const Prop& p : e.props) {
+          double v = 0;
+          if (p.is_list) { double c = 0; if (!(ss >> c)) return -4; for (long k = 0; k < (long)c; k++) if (!(ss >> v)) return -4; }
+          else { if (!(ss >> v)) return -4; if (is_vertex && p.role >= 0) xyz[p.role] = (float)v; }
+        }
+      } else {
+        for (const Prop& p : e.props) {
+          double v = 0;
+          if (p.is_list) { double c = 0; if (!read_scalar(p.list_count, c)) return -4; for (long k = 0; k < (long)c; k++) if (!read_scalar(p.type, v)) return -4; }
+          else { if (!read_scalar(p.type, v)) return -4; if (is_vertex && p.role >= 0) xyz[p.role] = (float)v; }
+        }
+      }
+      if (is_vertex) cloud->points.push_back(pcl::PointXYZ(xyz[0], xyz[1], xyz[2]));
+    }
+    if (is_vertex) break;   // faces and later elements are not needed
+  }
+  cloud->width = (std::uint32_t)cloud->points.size(); cloud->height = 1;
+  return 0;
+}
+
 // IO.cpp:22-71 — coloured copy of the clustered points (points outside every cluster are not written)
 inline void saveColoredClusters(const std::string& fileoutpath_name, PCXYZPtr input_cloud,
                                 const std::vector<std::vector<int>>& clusters_points_idx) {
@@ -173,10 +268,10 @@ inline void saveColoredClusters(const std::string& fileoutpath_name, pcl::PointC
   std::fclose(f);
 }
 
-// IO.h:100-108 — plain XYZ cloud as a binary PCD
-inline void outputPointCloudData(const std::string& outName, PCXYZPtr dataCloud) {
+// IO.h:100-108 — plain XYZ cloud as a binary PCD; 0, or -1 when the file cannot be written (as the reference)
+inline int outputPointCloudData(const std::string& outName, PCXYZPtr dataCloud) {
   FILE* f = std::fopen(outName.c_str(), "wb");
-  if (!f) throw std::runtime_error("outputPointCloudData: cannot open " + outName);
+  if (!f) return -1;
   const size_t total = dataCloud->points.size();
   std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
                   "WIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", total, total);
@@ -184,5 +279,5 @@ inline void outputPointCloudData(const std::string& outName, PCXYZPtr dataCloud)
     float xyz[3] = {p.x, p.y, p.z};
     std::fwrite(xyz, 4, 3, f);
   }
-  std::fclose(f);
+  return std::fclose(f) == 0 ? 0 : -1;
 }

@@ -112,3 +112,63 @@ def test_task_file_lines_are_positional(exe, tmp_path):
     r = subprocess.run([exe, "task", str(p)], capture_output=True, text=True)
     got = r.stdout.splitlines()
     assert got[0] == str(len(lines)) and got[1:] == [f"[{l}]" for l in lines]
+
+
+def _ply_header(fmt, n, props, nfaces=0, crlf=False):
+    lines = ["ply", f"format {fmt} 1.0", "comment test", f"element vertex {n}"] + [f"property {t} {name}" for t, name in props]
+    if nfaces:
+        lines += [f"element face {nfaces}", "property list uchar int vertex_indices"]
+    lines.append("end_header")
+    return (("\r\n" if crlf else "\n").join(lines) + ("\r\n" if crlf else "\n")).encode()
+
+
+def _read_ply(exe, path, tmp_path):
+    out = tmp_path / "out.f32"
+    r = subprocess.run([exe, "ply", str(path), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return np.fromfile(out, np.float32).reshape(-1, 3)
+
+
+def test_ply_ascii_with_colour_and_faces(exe, tmp_path):
+    """inputPointCloudData2 (IO.h:83-97): x y z taken from among other scalar properties; faces ignored"""
+    xyz = _cloud(400)
+    body = "\n".join(f"{x:.9g} {y:.9g} {z:.9g} 10 20 30" for x, y, z in xyz.tolist()) + "\n3 0 1 2\n"
+    p = tmp_path / "a.ply"
+    p.write_bytes(_ply_header("ascii", len(xyz), [("float", "x"), ("float", "y"), ("float", "z"), ("uchar", "red"),
+                                                   ("uchar", "green"), ("uchar", "blue")], nfaces=1) + body.encode())
+    np.testing.assert_array_equal(_read_ply(exe, p, tmp_path), xyz)
+
+
+@pytest.mark.parametrize("endian", ["little", "big"])
+def test_ply_binary_mixed_properties(exe, tmp_path, endian):
+    """binary PLY, both byte orders: an intensity before x, double z, a uchar after; CRLF header"""
+    xyz = _cloud(1000)
+    e = "<" if endian == "little" else ">"
+    rec = np.zeros(len(xyz), dtype=[("intensity", e + "f4"), ("x", e + "f4"), ("y", e + "f4"), ("z", e + "f8"), ("cls", "u1")])
+    rec["intensity"], rec["x"], rec["y"], rec["z"], rec["cls"] = 7.0, xyz[:, 0], xyz[:, 1], xyz[:, 2].astype(np.float64), 3
+    p = tmp_path / "b.ply"
+    p.write_bytes(_ply_header(f"binary_{endian}_endian", len(xyz), [("float", "intensity"), ("float", "x"), ("float", "y"),
+                                                                   ("double", "z"), ("uchar", "cls")], crlf=True) + rec.tobytes())
+    np.testing.assert_array_equal(_read_ply(exe, p, tmp_path), xyz)
+
+
+def test_ply_errors(exe, tmp_path):
+    p = tmp_path / "bad.ply"
+    p.write_bytes(b"plx\n")
+    assert subprocess.run([exe, "ply", str(p), str(tmp_path / "o")], capture_output=True, text=True).stderr.strip() == "rc -2"
+    p.write_bytes(_ply_header("ascii", 2, [("float", "x"), ("float", "y")]) + b"1 2\n3 4\n")
+    assert subprocess.run([exe, "ply", str(p), str(tmp_path / "o")], capture_output=True, text=True).stderr.strip() == "rc -3"
+    p.write_bytes(_ply_header("binary_little_endian", 5, [("float", "x"), ("float", "y"), ("float", "z")]) + b"\0" * 20)
+    assert subprocess.run([exe, "ply", str(p), str(tmp_path / "o")], capture_output=True, text=True).stderr.strip() == "rc -4"
+    assert subprocess.run([exe, "ply", str(tmp_path / "missing.ply"), str(tmp_path / "o")], capture_output=True, text=True).stderr.strip() == "rc -1"
+
+
+def test_output_point_cloud_data_roundtrip(exe, tmp_path):
+    """outputPointCloudData (IO.h:100-108) writes a binary XYZ PCD that inputPointCloudData reads back"""
+    xyz = _cloud(700)
+    a = tmp_path / "a.pcd"
+    a.write_bytes(_header(len(xyz), "binary", with_intensity=False) + xyz.tobytes())
+    b = tmp_path / "b.pcd"
+    r = subprocess.run([exe, "xyzpcd", str(a), str(b)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    np.testing.assert_array_equal(_read_back(exe, b, tmp_path), xyz)

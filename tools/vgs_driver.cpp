@@ -128,7 +128,8 @@ int main(int argc, char** argv) {
   string out_name = argc > 3 ? argv[3] : vgs_rstrip(input_vector[18]) + vgs_rstrip(input_vector[21]);
   int method = std::atoi(input_vector[24].c_str());
   PCXYZPtr input_cloud(new PCXYZ);
-  int rc = inputPointCloudData(in_name, input_cloud);
+  const bool is_ply = in_name.size() >= 4 && (in_name.compare(in_name.size() - 4, 4, ".ply") == 0 || in_name.compare(in_name.size() - 4, 4, ".PLY") == 0);
+  int rc = is_ply ? inputPointCloudData2(in_name, input_cloud) : inputPointCloudData(in_name, input_cloud);   // IO.h:64 / IO.h:83
   if (rc != 0) { std::fprintf(stderr, "cannot read %s (rc %d)\n", in_name.c_str(), rc); return 3; }
   try {
     if (method == 2) return segmentationVGS(out_name, input_cloud, input_vector);
