@@ -47,6 +47,7 @@ class SuperVoxelBasedSegmentation {
     ck(vgs_get_bounding_box(h_, b));
     min_x = b[0]; min_y = b[1]; min_z = b[2]; max_x = b[3]; max_y = b[4]; max_z = b[5];
   }
+  void getTaskVector(std::vector<std::string> input_vector) { task_vector_ = input_vector; }   // SV.h:96 (stored, never read)
   int getCloudPointNum(PCXYZPtr input_data) {                                        // SV.h:101
     points_num_ = (int)input_data->points.size();
     points_cloud_ = input_data;
@@ -214,6 +215,7 @@ class SuperVoxelBasedSegmentation {
   PointCloudConstPtr input_;
   PCXYZPtr points_cloud_;
   std::vector<int> labels_;
+  std::vector<std::string> task_vector_;
   int max_label_ = 0;
   bool have_labels_ = false, seed_grid_ = false;
   float color_impt_ = 0, spatial_impt_ = 0, normal_impt_ = 0;

@@ -81,8 +81,25 @@ class VoxelBasedSegmentation {
     return out;
   }
 
+  // VS.h:198, 211: internal bookkeeping of calcualteVoxelCloudAttributes in the reference (they APPEND one flag per call,
+  // VS.h:351-361); the used / clustered state lives on the device here, so calling them from outside has no effect
+  void setVoxelChosen(int /*voxel_idx*/, int /*chosen_ornot*/) {}
+  void setVoxelClustered(int /*voxel_idx*/, int /*clustered_ornot*/) {}
+  // VS.h:269: ids of the voxels within graph_size of voxel_id, nearest first, the voxel itself first (FLANN radius order)
+  std::vector<int> getOneVoxelAdjacency(int voxel_id) {
+    if (adj_off_cache_.empty()) {
+      adj_off_cache_ = vgs_dropin::fetch<int64_t>(h_, VGS_BLOB_ADJ_OFFSETS);
+      adj_idx_cache_ = vgs_dropin::fetch<int32_t>(h_, VGS_BLOB_ADJ_IDX);
+    }
+    if (voxel_id < 0 || (size_t)voxel_id + 1 >= adj_off_cache_.size()) throw std::runtime_error("getOneVoxelAdjacency: voxel id out of range");
+    return std::vector<int>(adj_idx_cache_.begin() + adj_off_cache_[voxel_id], adj_idx_cache_.begin() + adj_off_cache_[voxel_id + 1]);
+  }
+
   void calcualteVoxelCloudAttributes(PCXYZPtr /*input_cloud*/) { ck(vgs_compute_features(h_, voxel_points_min_)); }  // VS.h:290 [sic]
-  void findAllVoxelAdjacency(float graph_size) { ck(vgs_find_adjacency(h_, graph_size)); }                            // VS.h:223
+  void findAllVoxelAdjacency(float graph_size) {                                                                      // VS.h:223
+    adj_off_cache_.clear(); adj_idx_cache_.clear();
+    ck(vgs_find_adjacency(h_, graph_size));
+  }
   void segmentVoxelCloudWithGraphModel(float cut_thred, float sig_p, float sig_n, float sig_o, float sig_e, float sig_c,
                                        float sig_w) {  // VS.h:372
     vgs_sigmas s{sig_p, sig_n, sig_o, sig_e, sig_c, sig_w};
@@ -237,6 +254,8 @@ class VoxelBasedSegmentation {
   int voxel_points_min_ = 0, voxel_adjacency_min_ = 0, cluster_voxels_min_ = 0;
   float voxel_resolution_ = 0;
   std::vector<std::vector<int>> clusters_point_idx_;
+  std::vector<int64_t> adj_off_cache_;
+  std::vector<int32_t> adj_idx_cache_;
 };
 
 }  // namespace pcl

@@ -46,6 +46,10 @@ int main(int argc, char** argv) {
     // features, adjacency, segmentation (test:65-71)
     voxel_structure.calcualteVoxelCloudAttributes(input_cloud);
     voxel_structure.findAllVoxelAdjacency(graph_size);
+    {   // VS.h:269: the radius neighbours of a voxel, itself first
+      std::vector<int> a0 = voxel_structure.getOneVoxelAdjacency(0), al = voxel_structure.getOneVoxelAdjacency(nvox - 1);
+      if (a0.empty() || a0[0] != 0 || al.empty() || al[0] != nvox - 1) { fprintf(stderr, "getOneVoxelAdjacency: self is not first\n"); return 4; }
+    }
     voxel_structure.segmentVoxelCloudWithGraphModel(cut_thred, sig_p, sig_n, sig_o, sig_e, sig_c, sig_w);
     // output (test:74-76)
     voxel_structure.drawColorMapofPointsinClusters(clustered_cloud);
