@@ -5,8 +5,9 @@
  * This is the drop-in boundary: the C++ classes in include/vgs_dropin/ (same class and member names
  * as the reference's voxel_segmentation.h / supervoxel_segmentation.h) forward to these entry
  * points; INTEGRATION.md shows the binding.  Plain C, opaque handle, int status, caller-owned
- * buffers, no torch / CUDA types in the signatures.  One handle = one CUDA device + one stream;
- * a handle is not thread-safe, different handles are independent.
+ * buffers, no torch / CUDA types in the signatures.  One handle = one CUDA device + one stream (work forked onto
+ * the handle's internal side streams — the independent size-class launches of vgs_segment — is joined back into that
+ * stream before the call returns); a handle is not thread-safe, different handles are independent.
  *
  * There is NO CPU fallback: every entry point fails with VGS_ERR_NO_DEVICE / VGS_ERR_CUDA when
  * no sm_100 device is usable.
