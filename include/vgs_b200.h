@@ -93,7 +93,9 @@ vgs_status vgs_device_count(int* n);            /* VGS_ERR_NO_DEVICE when none *
 
 /* -- input: replaces setInputCloud + getCloudPointNum (VS.h:94-102, test:52-53).  xyz = n points,
  *    stride_bytes 12 (packed) or 16 (pcl::PointXYZ).  on_device != 0: xyz is a device pointer that
- *    must stay valid until the run ends (no copy is made); else a host pointer, copied H2D. -- */
+ *    must stay valid until the run ends (no copy is made); else a host pointer, copied H2D on the handle's stream:
+ *    asynchronously when the buffer is pinned, so it must stay valid and unchanged until the next call that
+ *    synchronises (vgs_voxelize and every later stage do; vgs_run does before it returns). -- */
 vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_bytes, int on_device);
 
 /* -- stage 0+1: replaces OctreePointCloud(res) + addPointsFromInputCloud + setVoxelCenters

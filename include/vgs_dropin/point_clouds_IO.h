@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <limits>
+#include <cstdlib>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -90,8 +92,15 @@ inline int inputPointCloudData(const std::string& name, PCXYZPtr cloud) {
   if (data == "ascii") {
     for (long p = 0; p < npoints; p++) {
       if (!std::getline(f, line)) break;
-      std::istringstream ss(line); std::vector<double> v; double t;
-      while (ss >> t) v.push_back(t);
+      // strtod per token: accepts the "nan" / "inf" tokens PCL writes for non-finite points (operator>> does not,
+      // which would turn such a row into a ghost point at the origin)
+      std::istringstream ss(line); std::vector<double> v; std::string tok;
+      while (ss >> tok) {
+        char* endp = nullptr;
+        double t = std::strtod(tok.c_str(), &endp);
+        if (endp == tok.c_str()) t = std::numeric_limits<double>::quiet_NaN();
+        v.push_back(t);
+      }
       int col = 0; float xyz[3] = {0, 0, 0};
       for (size_t i = 0; i < fields.size(); i++) {
         if ((int)i == ix && col < (int)v.size()) xyz[0] = (float)v[col];

@@ -1,7 +1,7 @@
 """CPU model of what `k_local_graph_warp` does instead of sorting n^2 weights: drop every weight
 <= the cut bound, histogram the rest into 255 bins, walk the bins in chunks (skip entries whose endpoints already
 share a segment, sort the rest by (w desc, flat index asc), merge with re-evaluation) and stop as soon as nothing
-can merge any more.  The model must give the reference's connect list (oracle.cut = cutGraphSegmentation,
+can change the segment of local vertex 0 any more (S0 rule: the next weight is <= Int(S0) - k/|S0|).  The model must give the reference's connect list (oracle.cut = cutGraphSegmentation,
 VS.h:1913-2029) for ANY weight matrix — in particular with heavy ties and arbitrary chunk boundaries, which real
 scenes hardly exercise.  (The CUDA kernel itself is compared with the oracle by the -m gpu parity tests.)"""
 import numpy as np
@@ -28,7 +28,6 @@ def chunked_cut(W, k, rng):
     size = [1] * n
     thr = [F(1) - k / F(1)] * n
     nseg = n
-    minthr = F(1) - k / F(1)
     ent.sort(key=lambda e: e[0])
     bins = [e[0] for e in ent]
     c0 = 0
@@ -39,8 +38,8 @@ def chunked_cut(W, k, rng):
         if not chunk:
             continue
         chunk.sort(key=lambda e: (-float(e[1]), e[2]))
-        if not (chunk[0][1] > minthr):
-            break                                               # nothing at or below this weight can merge
+        if not (chunk[0][1] > thr[seg[0]]):
+            break                                               # S0 rule: the segment of vertex 0 cannot merge any more
         for _, w, _, v1, v2 in chunk:
             s1, s2 = seg[v1], seg[v2]
             if s1 == s2:
@@ -53,7 +52,6 @@ def chunked_cut(W, k, rng):
                 size[drop] = 0
                 thr[keep] = w - k / F(size[keep])
                 nseg -= 1
-        minthr = min(thr[s] for s in range(n) if size[s] > 0)
     return np.array([v for v in range(n) if seg[v] == seg[0]], np.int32)
 
 

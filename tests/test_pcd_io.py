@@ -104,6 +104,17 @@ def test_pcd_ascii(exe, tmp_path):
     np.testing.assert_array_equal(_read_back(exe, p, tmp_path), xyz)
 
 
+def test_pcd_ascii_nan_row_stays_nan(exe, tmp_path):
+    """PCL writes `nan nan nan` for non-finite points in DATA ascii files; the reader must hand them on as NaN (the octree
+    skips them, as addPointsFromInputCloud does) instead of inventing a point at the origin"""
+    p = tmp_path / "n.pcd"
+    p.write_bytes(_header(3, "ascii", with_intensity=False) + b"1 2 3\nnan nan nan\n4 5 6\n")
+    got = _read_back(exe, p, tmp_path)
+    assert got.shape == (3, 3)
+    np.testing.assert_array_equal(got[[0, 2]], np.array([[1, 2, 3], [4, 5, 6]], np.float32))
+    assert np.isnan(got[1]).all()
+
+
 def test_task_file_lines_are_positional(exe, tmp_path):
     """IO.cpp:162-165: every line (comments and blanks included) is kept; parameter k = line k; CRLF files"""
     lines = ["// header", "", "Seg", "//Tasks", "0.15", ""]

@@ -72,6 +72,7 @@ struct vgs_context {
   int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
   int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
   bool have_graph = false;       // connect lists of stage 4+5a complete (own range computed or imported)
+  int64_t graph_covered = 0;     // units whose connect lists are in place (own range + imported ranges)
   bool units_external = false;   // SVGS units made by vgs_make_supervoxels_grid (not from labels)
   bool have_units = false, have_features = false, have_adj = false, have_segments = false, have_geometry = false;
   float bb_f[6] = {0, 0, 0, 0, 0, 0};   // float-narrowed bounding box members (VS.h:1123)
@@ -1033,7 +1034,7 @@ vgs_status vgs_segment_partial(vgs_handle h, const vgs_sigmas* sg, float cut_thr
 
 vgs_status vgs_segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   if (!h || !sg) return VGS_ERR_INVALID;
-  if (!h->have_graph) return h->fail(VGS_ERR_STATE, "vgs_segment_finish: call vgs_segment_partial (and import the other ranges) first");
+  if (!h->have_graph) return h->fail(VGS_ERR_STATE, "vgs_segment_finish: connect lists incomplete — call vgs_segment_partial, then import EVERY other range");
   return segment_finish(h, sg, cut_thred, adjacency_min);
 }
 
@@ -1095,7 +1096,8 @@ static vgs_status connect_copy(vgs_handle h, int64_t first, int64_t last, int32_
   } else {
     CK(cudaMemcpyAsync(c, cnt_dev, (size_t)(last - first) * 4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(i, idx_dev, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
-    h->have_graph = true;
+    h->graph_covered += last - first;
+    h->have_graph = h->graph_covered >= h->nu;   // every range present (a lost exchange must not pass silently)
   }
   CK(stream_wait(h->stream));
   return VGS_OK;
@@ -1291,13 +1293,15 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     }
     t.stop();
   }
-  h->have_graph = true;
+  h->graph_covered = last - first;               // a new own range invalidates earlier imports
+  h->have_graph = h->graph_covered >= nu;
   return VGS_OK;
 }
 
 static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
+  h->have_cluster_stats = false;
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
   gp.cut = cut_thred;
@@ -1452,17 +1456,18 @@ vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_cluster
 
 vgs_status vgs_run(vgs_handle h, const vgs_params* p, int32_t* labels, int on_device) {
   if (!h || !p) return VGS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
   cudaEvent_t a = h->ev[30], b = h->ev[31];
-  cudaEventRecord(a, h->stream);
+  CK(cudaEventRecord(a, h->stream));
   vgs_status s;
   if ((s = vgs_voxelize(h, p->voxel_size))) return s;
   if ((s = vgs_compute_features(h, p->points_min))) return s;
   if ((s = vgs_find_adjacency(h, p->graph_size))) return s;
   if ((s = vgs_segment(h, &p->sig, p->cut_thred, p->adjacency_min))) return s;
   if (labels && (s = vgs_get_point_labels(h, p->voxels_min, labels, on_device))) return s;
-  cudaEventRecord(b, h->stream);
-  cudaEventSynchronize(b);
-  cudaEventElapsedTime(&h->tm.total_ms, a, b);
+  CK(cudaEventRecord(b, h->stream));
+  CK(cudaEventSynchronize(b));
+  CK(cudaEventElapsedTime(&h->tm.total_ms, a, b));
   resolve_timers(h);
   return VGS_OK;
 }

@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   unsigned short* B_i = s_ul + ncap;                                             // bucketed ? mcap : 0: pool indices ordered by bin
   unsigned* s_cur = s_hist + LG_BINS + 1;                                        // LG_BINS scatter cursors (layout: hist | cursors)
   __shared__ int s_m, s_cnt, s_c1, s_done, s_nseg, s_tot, s_nu, s_c0b, s_before;
-  __shared__ float s_minthr, s_wempty, s_ratio;
+  __shared__ float s_wempty, s_ratio;
 
   const int tid = threadIdx.x;
   if (blockIdx.x >= nlist) return;
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
   const uint32_t off = adj_off[u];
   const int n = (int)(adj_off[u + 1] - off);
   const float k = gp.cut;
-  if (tid == 0) { s_m = 0; s_nseg = n; s_done = (n <= 1) ? 1 : 0; s_minthr = 1.0f - k / 1.0f; s_ratio = 1.0f; }
+  if (tid == 0) { s_m = 0; s_nseg = n; s_done = (n <= 1) ? 1 : 0; s_ratio = 1.0f; }
   for (int i = tid; i <= LG_BINS; i += THREADS) s_hist[i] = 0;
   for (int i = tid; i < n; i += THREADS) {
     s_gid[i] = adj_idx[off + i];
@@ -902,9 +902,13 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
       if (tid < 32) {
         const int lane = tid;
         int nseg = s_nseg;
-        const float minthr = s_minthr;
-        // nothing at or below the smallest live threshold can ever merge: w > max(thr1,thr2) >= minthr
-        const bool below = (Lw > 0) && !(C_w[0] > minthr);
+        // S0 rule: only the segment of local vertex 0 is emitted, and its next merge needs an entry with
+        // w > max(thr1, thr2) >= thr(S0) = Int(S0) - k/|S0| (unchanged until S0 merges again).  Entries come in
+        // descending order, so once the next weight is <= thr(S0) the emitted segment is final — exact, and far
+        // earlier than waiting for the smallest live threshold of ALL segments (an outlier singleton keeps that at 1-k).
+        const int s0v = s_seg[0];
+        const float thr0 = s_int[s0v] - k / (float)(int)s_size[s0v];
+        const bool below = (Lw > 0) && !(C_w[0] > thr0);
         bool stop = below || nseg <= 1;
         for (int base = 0; base < Lw && !stop; base += 32) {
           const int e = base + lane;
@@ -939,16 +943,8 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
             if (nseg <= 1) { stop = true; break; }
           }
         }
-        // smallest threshold among live segments that still have candidate entries
-        float mt = 3.0e38f;
-        for (int v = lane; v < n; v += 32) {
-          const int sz = (int)s_size[v];
-          if (sz > 0) mt = fminf(mt, s_int[v] - k / (float)sz);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
         if (lane == 0) {
-          s_nseg = nseg; s_minthr = mt;
+          s_nseg = nseg;
           if (nseg <= 1 || below) s_done = 1;
           if (!single_big) {
             float r = 1.5f * (float)(kept + 8) / (float)(L + 8);
@@ -1177,7 +1173,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
     }
     __syncwarp();
     const int m = (int)s_hist[255];
-    float ratio = 1.0f, minthr = 1.0f - k / 1.0f;
+    float ratio = 1.0f;
     int c0 = 0;
     bool done = false;
     while (!done && c0 < LW_BINS && m > 0) {
@@ -1250,7 +1246,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
             }
           }
           const float w0 = __shfl_sync(0xffffffffu, rw, 0);
-          below = !(w0 > minthr);       // w > max(thr1,thr2) >= minthr is impossible from here on
+          below = !(w0 > s_thr[s_seg[0]]);   // S0 rule (see k_local_graph2): the emitted segment cannot merge any more
           stop = below || nseg <= 1;
           if (!stop) merge_batch(rw, rf, lane < kept);
         } else {
@@ -1273,7 +1269,7 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
               __syncwarp();
             }
           }
-          below = !(C_w[0] > minthr);
+          below = !(C_w[0] > s_thr[s_seg[0]]);
           stop = below || nseg <= 1;
           for (int bs = 0; bs < kept && !stop; bs += 32) {
             const int e = bs + lane;
@@ -1281,14 +1277,6 @@ __global__ void __launch_bounds__(LW_WARPS * 32, 8) k_local_graph_warp(const uin
             merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
           }
         }
-        float mt = 3.0e38f;
-        for (int v = lane; v < nv; v += 32) {
-          const int sz = (int)s_size[v];
-          if (sz > 0) mt = fminf(mt, s_thr[v]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-        minthr = mt;
         if (nseg <= 1 || below) done = true;
       }
       ratio = fminf(1.0f, fmaxf(1.25f * (float)(kept + 2) / (float)(tot + 2), 1.0f / 256.0f));
