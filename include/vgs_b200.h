@@ -135,21 +135,6 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size);
  *    crossValidation, closestCheck, clustering) -- */
 vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* s, float cut_thred, int adjacency_min);
 
-/* -- multi-GPU (one process per GPU, every rank holds the same cloud and voxel table): stage 4+5a, the
- *    dominant cost, is partitioned over unit-id ranges; ranks exchange their connect-list slices
- *    (e.g. NCCL broadcast / all-gather of the exported device buffers) and every rank finishes
- *    (mutual filter, closest check, components) on the complete lists.  Results are identical to
- *    vgs_segment on one GPU.  Buffers are DEVICE pointers: cnt = (last-first) int32, idx = the
- *    adjacency slots [e_first, e_last) of vgs_adj_range. -- */
-vgs_status vgs_segment_partial(vgs_handle h, const vgs_sigmas* s, float cut_thred, int64_t first_unit, int64_t last_unit);
-vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, int64_t* e_first, int64_t* e_last);
-/* balanced partition for `parts` ranks: contiguous unit-id ranges with ~equal sum of (neighbourhood size)^2 and the
- * adjacency slots they cover; both arrays have parts + 1 entries (identical on every rank) */
-vgs_status vgs_unit_ranges(vgs_handle h, int parts, int64_t* first_unit, int64_t* first_slot);
-vgs_status vgs_export_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, int32_t* cnt_dev, int32_t* idx_dev);
-vgs_status vgs_import_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, const int32_t* cnt_dev, const int32_t* idx_dev);
-vgs_status vgs_segment_finish(vgs_handle h, const vgs_sigmas* s, float cut_thred, int adjacency_min);
-
 /* -- results: drawColorMapofPointsinClusters + getClusterIdx / getClusterNum (VS.h:947-1014, 111-121;
  *    SV.h:2109-2126).  voxels_min filters VGS clusters (size > voxels_min); ignored for SVGS. -- */
 vgs_status vgs_cluster_count(vgs_handle h, int voxels_min, int64_t* n_all, int64_t* n_exported);

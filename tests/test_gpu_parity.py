@@ -154,8 +154,8 @@ def test_state_errors(built_lib):
 
 
 def test_vgs_without_pair_cache(built_lib, monkeypatch):
-    """VGS_B200_NO_PAIR_CACHE=1: weights evaluated inside every local graph (the SVGS code path) must
-    give the same lists and labels as the offset-indexed pair cache."""
+    """VGS_B200_NO_PAIR_CACHE=1: weights evaluated inside every local graph by the general kernel (the SVGS code
+    path) must give the same lists and labels as the weight rows."""
     monkeypatch.setenv("VGS_B200_NO_PAIR_CACHE", "1")
     xyz = _scene("site")
     g = gpu_stages(xyz)
@@ -168,35 +168,37 @@ def test_vgs_without_pair_cache(built_lib, monkeypatch):
     _compare_vgs(xyz, g2, r)
 
 
-def test_vgs_pair_cache_without_bitmap(built_lib, monkeypatch):
-    """VGS_B200_NO_BITMAP=1: the pair cache finds partners by hash probes of every stencil offset (the path taken for
-    octrees deeper than 11 levels) instead of reading z-runs of the occupancy bitmap; same lists and labels."""
-    monkeypatch.setenv("VGS_B200_NO_BITMAP", "1")
+def test_vgs_row_kernel_fallback_units(built_lib, monkeypatch):
+    """VGS_B200_FORCE_FALLBACK=3: the row kernel hands every third voxel to the general kernel (the path taken by a voxel
+    whose weights overflow the staging buffer inside one weight cell); their connect lists come back as lists and are
+    converted to lattice masks — results must not change."""
+    monkeypatch.setenv("VGS_B200_FORCE_FALLBACK", "3")
     xyz = _scene("site")
     g = gpu_stages(xyz)
-    monkeypatch.delenv("VGS_B200_NO_BITMAP")
+    monkeypatch.delenv("VGS_B200_FORCE_FALLBACK")
+    assert g["counts"]["n_units"] > 0
     _compare_vgs(xyz, g, oracle.run(xyz, math=1))
 
 
 def test_vgs_single_stream_classes(built_lib, monkeypatch):
-    """VGS_B200_CLASS_STREAMS=1: all size-class launches on the handle's stream (default: 6 streams, forked / joined with
-    events); the connect lists do not depend on how the launches overlap."""
+    """VGS_B200_CLASS_STREAMS=1 with the general kernel: all size-class launches on the handle's stream (default: 6
+    streams, forked / joined with events); the connect lists do not depend on how the launches overlap."""
     monkeypatch.setenv("VGS_B200_CLASS_STREAMS", "1")
+    monkeypatch.setenv("VGS_B200_NO_PAIR_CACHE", "1")
     xyz = _scene("site")
     g = gpu_stages(xyz)
     monkeypatch.delenv("VGS_B200_CLASS_STREAMS")
+    monkeypatch.delenv("VGS_B200_NO_PAIR_CACHE")
     _compare_vgs(xyz, g, oracle.run(xyz, math=1))
 
 
-def test_vgs_adjacency_two_pass(built_lib, monkeypatch):
-    """VGS_B200_ADJ_TWO_PASS=1: count / scan / probe-again adjacency (used when the staging rows of the one-pass
-    variant would not fit) gives the same lists as the default one-pass build."""
-    monkeypatch.setenv("VGS_B200_ADJ_TWO_PASS", "1")
-    xyz = _scene("site")
+def test_vgs_dense_blob_long_rows(built_lib):
+    """a solid random blob: neighbourhoods of 100+ voxels, weight rows longer than the 512-entry short-row sort (the
+    long-row launch), staged rounds larger than one warp"""
+    rng = np.random.default_rng(12)
+    xyz = (rng.random((400_000, 3)) * np.array([2.4, 2.4, 2.4]) + 1.0).astype(np.float32)
     g = gpu_stages(xyz)
-    monkeypatch.delenv("VGS_B200_ADJ_TWO_PASS")
-    g2 = gpu_stages(xyz)
-    assert np.array_equal(g["adj_offsets"], g2["adj_offsets"]) and np.array_equal(g["adj_idx"], g2["adj_idx"])
+    assert g["counts"]["max_neighbours"] > 120
     _compare_vgs(xyz, g, oracle.run(xyz, math=1))
 
 
@@ -257,52 +259,86 @@ def test_svgs_drops_max_label_and_unlabelled(built_lib):
     assert np.all(g["point_label"][labels == 0] == -1) and np.all(g["point_label"][labels == ml] == -1)
 
 
-def test_full_size_properties_10m(built_lib):
-    """BASELINE.json configs[2] at full size (10 M points): the oracle would need minutes, so the run is
-    checked through size-independent properties: canonical labels (label = smallest point index of the
-    cluster and that point carries it), every exported cluster has more than voxels_min voxels, cluster
-    counts are consistent, a second run is bit-identical, and unlabelled points belong to dropped clusters."""
+def _rows_sorted(offsets, counts, idx):
+    """(row, id) pairs of CSR lists with `counts` valid entries per row, sorted by (row, id) — set comparison of lists at
+    bench sizes without Python loops"""
+    offsets = np.asarray(offsets, np.int64)
+    counts = np.asarray(counts, np.int64)
+    row = np.repeat(np.arange(len(counts), dtype=np.int64), counts)
+    start = np.repeat(offsets[:-1], counts)
+    within = np.arange(int(counts.sum()), dtype=np.int64) - np.repeat(np.cumsum(counts) - counts, counts)
+    ids = np.asarray(idx)[start + within].astype(np.int64)
+    order = np.lexsort((ids, row))
+    return row[order], ids[order]
+
+
+def _full_size_vs_oracle(xyz, mode=0, labels=None, max_label=0, vccs=False):
+    """one full run through the C ABI at a benchmarked size against the threaded oracle (math=1): canonical labels,
+    adjacency lists (order included), connect lists after the mutual filter, closest-check partners, cluster roots"""
+    from vgs_svgs_segmentation_b200 import capi
+    from util import SVGS_PARAMS
+    pd = dict(SVGS_PARAMS if mode == 1 else VGS_PARAMS)
+    h = capi.Handle(mode=mode)
+    h.set_points(xyz)
+    h.voxelize(pd["voxel_size"])
+    if mode == 1:
+        if vccs:
+            h.make_supervoxels_vccs(0.25, 0.0, 0.25, 0.75, 5)
+            labels, max_label = h.supervoxel_labels()
+        else:
+            h.set_supervoxel_labels(labels, max_label)
+    h.compute_features(pd["points_min"])
+    h.find_adjacency(pd["graph_size"])
+    h.segment(capi.Sigmas(pd["sig_p"], pd["sig_n"], pd["sig_o"], pd["sig_e"], pd["sig_c"], pd["sig_w"]), pd["cut_thred"], pd["adjacency_min"])
+    lab = h.point_labels(pd["voxels_min"])
+    g = dict(adj_offsets=h.blob("ADJ_OFFSETS"), adj_idx=h.blob("ADJ_IDX"), conn1_count=h.blob("CONN1_COUNT"), conn1_idx=h.blob("CONN1_IDX"),
+             attach=h.blob("ATTACH"), root=h.blob("UNIT_ROOT"), counts=h.counts())
+    h.close()
+    import os
+    oracle.set_threads(os.cpu_count() or 1)   # all host threads for the per-unit loop; results do not depend on it
+    try:
+        r = oracle.run(xyz, labels=labels, max_label=max_label, mode=mode, math=1, **{k: v for k, v in pd.items()})
+    finally:
+        oracle.set_threads(1)
+    assert g["counts"]["n_units"] == r.stats["n_units"]
+    np.testing.assert_array_equal(g["adj_offsets"], r.adj_offsets)
+    np.testing.assert_array_equal(g["adj_idx"], r.adj_idx)
+    grow, gid = _rows_sorted(g["adj_offsets"], g["conn1_count"], g["conn1_idx"])
+    orow, oid = _rows_sorted(r.conn1_offsets, np.diff(r.conn1_offsets), r.conn1_idx)
+    np.testing.assert_array_equal(grow, orow)
+    np.testing.assert_array_equal(gid, oid)
+    np.testing.assert_array_equal(g["attach"], r.attach)
+    np.testing.assert_array_equal(lab, r.point_label)
+    print(f"N={len(xyz)} units={r.stats['n_units']} used={r.stats['n_used']} clusters={r.stats['n_clusters_exported']} "
+          f"near_threshold={r.stats['near_threshold']} labels equal: {len(lab)}/{len(lab)}")
+    return lab, r
+
+
+def test_bench_scene_10m_equals_oracle(built_lib):
+    """BASELINE.json configs[2] at FULL size — the scene bench.py times (10 M points, seed 1, 70 m): labels, adjacency,
+    connect lists and closest-check partners equal to the oracle; a second run is bit-identical"""
     from vgs_svgs_segmentation_b200 import capi
     xyz = scenes.construction_site(10_000_000, seed=1, extent=70.0)
+    lab, r = _full_size_vs_oracle(xyz)
     h = capi.Handle()
     h.set_points(xyz)
-    p = capi.make_params(**VGS_PARAMS)
-    lab = h.run(p).copy()
-    c = h.counts()
-    root = h.blob("UNIT_ROOT")
-    pu = h.blob("POINT_UNIT")
-    n_all, n_exp = h.cluster_count(VGS_PARAMS["voxels_min"])
-    assert c["n_points"] == 10_000_000 and c["n_voxels"] == len(root) and n_all == len(np.unique(root))
-    labelled = lab >= 0
-    ids = np.unique(lab[labelled])
-    assert len(ids) == n_exp
-    assert np.array_equal(lab[ids], ids)                       # the smallest point of a cluster carries its own index
-    first = np.full(lab.max() + 1, -1, np.int64)
-    idx = np.flatnonzero(labelled)
-    first[lab[idx][::-1]] = idx[::-1]                          # first occurrence of each label
-    assert np.array_equal(first[ids], ids)                     # ... and no smaller point has that label
-    # label is a function of the voxel's root, and exported roots have > voxels_min voxels
-    r_of_point = root[pu]
-    sizes = np.bincount(root, minlength=len(root))
-    assert np.all(sizes[r_of_point[labelled]] > VGS_PARAMS["voxels_min"])
-    assert np.all(sizes[r_of_point[~labelled]] <= VGS_PARAMS["voxels_min"])
-    lab_of_root = np.full(len(root), -2, np.int64)
-    lab_of_root[r_of_point] = lab
-    assert np.array_equal(lab_of_root[r_of_point], lab)
-    h.set_points(xyz)
-    lab2 = h.run(p)
+    lab2 = h.run(capi.make_params(**VGS_PARAMS))
     h.close()
     assert np.array_equal(lab, lab2)
 
 
-def test_vgs_cta_kernel_path(built_lib, monkeypatch):
-    """VGS_B200_NO_WARP_KERNEL=1: the cached CTA-per-unit kernel (also the fallback of the warp-per-unit
-    kernel) must give the oracle's lists and labels too."""
-    monkeypatch.setenv("VGS_B200_NO_WARP_KERNEL", "1")
-    xyz = _scene("site")
-    g = gpu_stages(xyz)
-    r = oracle.run(xyz, math=1)
-    _compare_vgs(xyz, g, r)
+def test_town_2m_vgs_equals_oracle(built_lib):
+    """configs[0] stand-in (Town_Test.pcd is not distributed): the 2 M-point town scene with Task_File_VGS.txt parameters"""
+    _full_size_vs_oracle(scenes.town(2_000_000))
+
+
+def test_town_2m_svgs_equals_oracle(built_lib):
+    """configs[1] stand-in: SVGS with Task_File_SVGS.txt parameters on the 2 M-point town scene, supervoxels supplied
+    (seed-grid labels, 0.25 m) and made by the CUDA VCCS generator (the oracle is fed the generator's labels)"""
+    xyz = scenes.town(2_000_000)
+    labels = scenes.supervoxel_labels_grid(xyz, 0.25)
+    _full_size_vs_oracle(xyz, mode=1, labels=labels, max_label=int(labels.max()) + 1)
+    _full_size_vs_oracle(xyz, mode=1, vccs=True)
 
 
 def _tiny_clouds():

@@ -56,8 +56,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
 
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
             "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_make_supervoxels_vccs", "vgs_get_supervoxel_labels", "vgs_unit_count",
-            "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_segment_partial", "vgs_adj_range", "vgs_unit_ranges", "vgs_export_connect", "vgs_import_connect",
-            "vgs_segment_finish", "vgs_cluster_count", "vgs_get_point_labels",
+            "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
             "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get"]
 
 _lib = None
@@ -90,12 +89,6 @@ def load():
         L.vgs_compute_features.argtypes = [C.c_void_p, C.c_int]
         L.vgs_find_adjacency.argtypes = [C.c_void_p, C.c_float]
         L.vgs_segment.argtypes = [C.c_void_p, C.POINTER(Sigmas), C.c_float, C.c_int]
-        L.vgs_segment_partial.argtypes = [C.c_void_p, C.POINTER(Sigmas), C.c_float, C.c_int64, C.c_int64]
-        L.vgs_adj_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        L.vgs_unit_ranges.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        L.vgs_export_connect.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
-        L.vgs_import_connect.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
-        L.vgs_segment_finish.argtypes = [C.c_void_p, C.POINTER(Sigmas), C.c_float, C.c_int]
         L.vgs_cluster_count.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.vgs_get_point_labels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.vgs_get_clusters_csr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
@@ -208,30 +201,6 @@ class Handle:
 
     def segment(self, sig: Sigmas, cut_thred, adjacency_min):
         self._ck(self.L.vgs_segment(self.h, C.byref(sig), cut_thred, adjacency_min))
-
-    def segment_partial(self, sig: Sigmas, cut_thred, first, last):
-        self._ck(self.L.vgs_segment_partial(self.h, C.byref(sig), cut_thred, first, last))
-
-    def adj_range(self, first, last):
-        a, b = C.c_int64(), C.c_int64()
-        self._ck(self.L.vgs_adj_range(self.h, first, last, C.byref(a), C.byref(b)))
-        return a.value, b.value
-
-    def unit_ranges(self, parts):
-        """[(first_unit, last_unit)], [(first_slot, last_slot)] of the balanced partition for `parts` ranks"""
-        fu = (C.c_int64 * (parts + 1))()
-        fs = (C.c_int64 * (parts + 1))()
-        self._ck(self.L.vgs_unit_ranges(self.h, parts, fu, fs))
-        return ([(int(fu[r]), int(fu[r + 1])) for r in range(parts)], [(int(fs[r]), int(fs[r + 1])) for r in range(parts)])
-
-    def export_connect(self, first, last, cnt_ptr: int, idx_ptr: int):
-        self._ck(self.L.vgs_export_connect(self.h, first, last, C.c_void_p(cnt_ptr), C.c_void_p(idx_ptr)))
-
-    def import_connect(self, first, last, cnt_ptr: int, idx_ptr: int):
-        self._ck(self.L.vgs_import_connect(self.h, first, last, C.c_void_p(cnt_ptr), C.c_void_p(idx_ptr)))
-
-    def segment_finish(self, sig: Sigmas, cut_thred, adjacency_min):
-        self._ck(self.L.vgs_segment_finish(self.h, C.byref(sig), cut_thred, adjacency_min))
 
     def cluster_count(self, voxels_min):
         a, b = C.c_int64(), C.c_int64()

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "vgs_kernels.cuh"
+#include "vgs_rows.cuh"
 #include "vgs_vccs.cuh"
 
 using namespace vgs;
@@ -72,7 +73,6 @@ struct vgs_context {
   int64_t nu = 0;         // units: voxels (VGS) / supervoxels (SVGS)
   int64_t n_valid = 0;    // points that belong to a unit (sorted positions [0, n_valid))
   bool have_graph = false;       // connect lists of stage 4+5a complete (own range computed or imported)
-  int64_t graph_covered = 0;     // units whose connect lists are in place (own range + imported ranges)
   bool units_external = false;   // SVGS units made by vgs_make_supervoxels_grid (not from labels)
   bool have_units = false, have_features = false, have_adj = false, have_segments = false, have_geometry = false;
   float bb_f[6] = {0, 0, 0, 0, 0, 0};   // float-narrowed bounding box members (VS.h:1123)
@@ -86,26 +86,31 @@ struct vgs_context {
   // device buffers
   DBuf keysA, keysB, valsA, valsB, hist, tiles, flags, scan, small;
   DBuf ustart, ukey, pos_unit, rec, key3, center, plainm, tk, tv, stencil;
-  DBuf adj_cnt, adj_off, adj_idx, adj_stage, class_count, class_list;
+  DBuf adj_cnt, adj_off, adj_idx, adj_code, class_count, class_list;
   DBuf conn0_cnt, conn0_idx, conn1_cnt, conn1_idx, attach, parent, root, csize, cminpt, labels_out, tmp;
   uint64_t* d_keys = nullptr;   // sorted keys (points to keysA or keysB)
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
-  std::vector<int4> stencil_host;   // lattice offsets of the radius search (VGS)
-  // derived stencil tables, rebuilt only when (voxel_size, graph_size) change: columns of the radius stencil, the
-  // pair-cache stencil (differences of two offsets, lexicographically positive half) and its columns
-  std::vector<int4> adj_cols_host, st2_host, pc_cols_host;
-  int st_rho = 0, st_r2 = 0, st_half = 0;
+  // lattice searches (VGS): host tables rebuilt only when (voxel_size, graph_size, float-noise bound) change
+  std::vector<int4> stencil_host;   // radius stencil, sorted by integer distance class
+  std::vector<int4> adj_cols_host, pc_cols_host;   // columns (dx, dy, mask of dz) of the radius / pair stencil
+  int st_rho = 0, st_r2 = 0, lbits = 3, mwords = 0;
   float st_vs = -1.f, st_gs = -1.f;
-  DBuf bitmap, stencil2, pair_table, need_rows, fallback, lg_scratch, uflags, singles;
-  int use_warp_kernel = 1;          // VGS cached path: warp-per-unit local graph kernel
-  int lw_chunk = LW_CH;             // target useful entries per chunk (tuning knob VGS_B200_LW_CHUNK)
+  double st_noise = -1.0;
+  bool rows_ok = false;             // pair-weight rows usable (stencil reach <= 5 cells)
+  int64_t max_row_len = 0, n_rows = 0, n_long = 0;
+  uint32_t kminmax[6] = {0, 0, 0, 0, 0, 0};   // smallest / largest occupied voxel key per axis
+  BitGrid grid{};
+  LatticeGeom lgeo{};
+  DBuf d_adj_cols, d_pc_cols, tb_slot, tb_code5, tb_first, tb_last;
+  DBuf bm_all, bm_used, row_len, row_off, row_npos, rows, cursor, long_rows, cstats, conn_mask;
+  DBuf fallback, uflags, singles;
+  bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
-  int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph
-  int use_bitmap = 1;               // pair-cache partner search on an occupancy bitmap (0: hash probes; VGS_B200_NO_BITMAP)
+  int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph (general kernel; VGS_B200_NO_PAIR_CACHE)
   int cc_jumps = 6;                 // pointer-jumping rounds over the initial component forest
-  int adj_two_pass = 0;             // 1 = count / scan / probe again instead of staging rows (VGS_B200_ADJ_TWO_PASS)
+  int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
     DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, owner, owner2, dist, claim;
@@ -168,12 +173,13 @@ static inline cudaError_t stream_wait(cudaStream_t st) {
 namespace {
 
 // exclusive scan of n u32 (in -> out, may alias); total (u64) read back to the host if total != null
-vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* total_host) {
+vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* total_host,
+                    unsigned long long* d_total = nullptr) {
   int64_t nt = cdiv(n, SC_TILE);
   if (nt < 1) nt = 1;
   CK(h->tiles.reserve((size_t)(nt + 1) * 4 + 16));
   CK(h->small.reserve(4096));
-  unsigned long long* d_total = h->small.as<unsigned long long>() + 8;
+  if (!d_total) d_total = h->small.as<unsigned long long>() + 8;
   LAUNCH(k_scan_reduce, (unsigned)nt, SC_THREADS, 0, in, n, h->tiles.as<uint32_t>());
   LAUNCH(k_scan_tiles, 1, 1024, 0, h->tiles.as<uint32_t>(), nt, d_total);
   LAUNCH(k_scan_down, (unsigned)nt, SC_THREADS, 0, in, out, n, h->tiles.as<uint32_t>());
@@ -317,11 +323,12 @@ void resolve_timers(vgs_handle h) {
   h->tm_pending = 0;
 }
 
-std::vector<int4> make_stencil(float voxel_size_f, float graph_size_f) {
-  // integer lattice offsets whose ideal centre distance could pass the float test dist2 < (float)(r*r)
+std::vector<int4> make_stencil(float voxel_size_f, float graph_size_f, double noise) {
+  // integer lattice offsets whose ideal centre distance could pass the float test dist2 < (float)(r*r);
+  // noise = bound on the float error of dist2 for this cloud (grows with the distance from the origin)
   double res = (double)voxel_size_f, r = (double)graph_size_f;
-  int rho = (int)std::ceil(r / res) + 1;
-  double lim = r * r * (1.0 + 1e-4) + 1e-9;
+  int rho = (int)std::ceil(std::sqrt(r * r + noise) / res) + 1;
+  double lim = r * r * (1.0 + 1e-4) + 1e-9 + noise;
   std::vector<int4> st;
   for (int dx = -rho; dx <= rho; dx++)
     for (int dy = -rho; dy <= rho; dy++)
@@ -372,11 +379,8 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (const char* e_cs = getenv("VGS_B200_CLASS_STREAMS")) { int v = atoi(e_cs); if (v >= 1 && v <= 1 + vgs_context::N_AUX) h->class_streams = v; }
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
-  if (const char* e_bm = getenv("VGS_B200_NO_BITMAP")) h->use_bitmap = (e_bm[0] == '1') ? 0 : 1;
+  if (const char* e_ff = getenv("VGS_B200_FORCE_FALLBACK")) { int v = atoi(e_ff); if (v >= 1) h->force_fallback = v; }
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
-  if (const char* e_tp = getenv("VGS_B200_ADJ_TWO_PASS")) h->adj_two_pass = (e_tp[0] == '1') ? 1 : 0;
-  if (const char* e_nw = getenv("VGS_B200_NO_WARP_KERNEL")) h->use_warp_kernel = (e_nw[0] == '1') ? 0 : 1;
-  if (const char* e_ch = getenv("VGS_B200_LW_CHUNK")) { int v = atoi(e_ch); if (v >= 1 && v <= LW_CS) h->lw_chunk = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
   {
     auto optin = [&](const void* fn, size_t want_total) -> cudaError_t {
@@ -386,15 +390,12 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
       return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(want_total - fa.sharedSizeBytes));
     };
     const size_t kMax = 227 * 1024;
-    cudaError_t r = optin((const void*)k_local_graph2<64, true>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, true>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, true>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<64, false>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128, false>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256, false>, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_local_graph_warp, kMax);
-    if (r == cudaSuccess) r = optin((const void*)k_adjacency, 200 * 1024);
-    if (r == cudaSuccess) r = optin((const void*)k_adjacency_bm, 200 * 1024);
+    cudaError_t r = optin((const void*)k_local_graph2<64>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<128>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph2<256>, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_local_graph_rows, kMax);
+    if (r == cudaSuccess) r = optin((const void*)k_adj_fill, 200 * 1024);
+    if (r == cudaSuccess) r = optin((const void*)k_rows_sort, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
       cudaGetLastError();
@@ -412,10 +413,12 @@ void vgs_destroy(vgs_handle h) {
   cudaStreamSynchronize(h->stream);
   DBuf* all[] = {&h->xyz_own, &h->labels_own, &h->keysA, &h->keysB, &h->valsA, &h->valsB, &h->hist, &h->tiles, &h->flags, &h->scan,
                  &h->small, &h->ustart, &h->ukey, &h->pos_unit, &h->rec, &h->key3, &h->center, &h->plainm, &h->tk, &h->tv,
-                 &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->class_count, &h->class_list, &h->conn0_cnt,
+                 &h->stencil, &h->adj_cnt, &h->adj_off, &h->adj_idx, &h->adj_code, &h->class_count, &h->class_list, &h->conn0_cnt,
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
-                 &h->labels_out, &h->tmp, &h->stencil2, &h->pair_table, &h->need_rows, &h->fallback, &h->lg_scratch, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB, &h->cstart, &h->ckey, &h->cpos, &h->gridmin,
-                 &h->adj_stage, &h->bitmap};
+                 &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
+                 &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
+                 &h->tb_last, &h->bm_all, &h->bm_used, &h->row_len, &h->row_off, &h->row_npos, &h->rows, &h->cursor, &h->long_rows,
+                 &h->cstats, &h->conn_mask};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
   DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm,
@@ -538,10 +541,20 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     int64_t nunits = 0;
     s = build_units(h, ks, n, &nunits);
     if (s) return s;
+    // voxel keys + occupied key range (the extent of the occupancy grids of the lattice searches)
+    uint32_t* d_kmm = h->small.as<uint32_t>() + 208;
+    {
+      const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+      CK(cudaMemcpyAsync(d_kmm, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+      CK(h->key3.reserve((size_t)nunits * 12 + 16));
+      LAUNCH(k_voxel_keys, (unsigned)cdiv(nunits, 256), 256, 0, h->ukey.as<uint64_t>(), nunits, h->depth,
+             h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->key3.as<uint32_t>(), d_kmm);
+    }
     // peel the sentinel segment if present
     uint64_t lastkey = 0; uint32_t laststart = 0;
     CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->kminmax, d_kmm, sizeof(h->kminmax), cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
     int64_t n_fin = n;
     if (lastkey >> (3 * h->depth)) { n_fin = laststart; nunits--; }
@@ -814,10 +827,12 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   CK(h->uflags.reserve((size_t)nu + 16));
   LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
          h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->uflags.as<uint8_t>(), d_used);
-  unsigned long long used = 0;
-  CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(stream_wait(h->stream));
-  h->n_used = (int64_t)used;
+  if (h->mode == VGS_MODE_SVGS) {   // VGS: the count arrives with the adjacency totals (one host round trip less)
+    unsigned long long used = 0;
+    CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(stream_wait(h->stream));
+    h->n_used = (int64_t)used;
+  }
   h->have_features = true;
   t.stop();
   return VGS_OK;
@@ -827,10 +842,9 @@ static vgs_status ensure_geometry(vgs_handle h) {
   if (h->mode != VGS_MODE_VGS || !h->voxelized) return h->fail(VGS_ERR_STATE, "voxel geometry needs vgs_voxelize in VGS mode");
   if (h->have_geometry) return VGS_OK;
   const int64_t nu = h->nu;
-  CK(h->key3.reserve((size_t)nu * 12 + 16)); CK(h->center.reserve((size_t)nu * 12 + 16));
+  CK(h->center.reserve((size_t)nu * 12 + 16));
   float res_f = (float)(double)h->voxel_size;   // setVoxelSize narrows the resolution to float (VS.h:127)
-  LAUNCH(k_voxel_geometry, (unsigned)cdiv(nu, 256), 256, 0, h->ukey.as<uint64_t>(), nu, h->depth,
-         h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, res_f, h->bb_f[0], h->bb_f[1], h->bb_f[2], h->key3.as<uint32_t>(),
+  LAUNCH(k_voxel_centers, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, res_f, h->bb_f[0], h->bb_f[1], h->bb_f[2],
          h->center.as<float>());
   h->have_geometry = true;
   return VGS_OK;
@@ -851,6 +865,91 @@ vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz) {
   { vgs_status s = ensure_geometry(h); if (s) return s; }
   CK(cudaMemcpyAsync(xyz, h->center.p, (size_t)h->nu * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(stream_wait(h->stream));
+  return VGS_OK;
+}
+
+// Host tables of the lattice searches, rebuilt (and uploaded) only when (voxel_size, graph_size, float-noise bound) change:
+// radius stencil sorted by integer distance class, its columns, slot tables, and the pair stencil (differences of two
+// stencil offsets, lexicographically positive half) as columns.
+static vgs_status build_lattice_tables(vgs_handle h, float graph_size, double noise) {
+  if (h->st_vs == h->voxel_size && h->st_gs == graph_size && h->st_noise == noise) return VGS_OK;
+  std::vector<int4> st = make_stencil(h->voxel_size, graph_size, noise);
+  for (int4& o : st) o.w = o.x * o.x + o.y * o.y + o.z * o.z;
+  std::sort(st.begin(), st.end(), [](const int4& a, const int4& b) {
+    if (a.w != b.w) return a.w < b.w;
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  int rho = 0;
+  for (const int4& o : st) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
+  if (rho > 15) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
+  const int nst = (int)st.size();
+  if (nst >= 65535 || adj_fill_smem(nst) > 200 * 1024) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
+  auto columns = [](const std::vector<int4>& offs, int reach) {
+    std::vector<int4> cols;
+    for (const int4& o : offs) {
+      bool found = false;
+      for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + reach); found = true; break; }
+      if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + reach), 0));
+    }
+    return cols;
+  };
+  h->stencil_host = st;
+  h->st_rho = rho;
+  h->adj_cols_host = columns(st, rho);
+  // slot tables
+  const int S = 2 * rho + 1;
+  std::vector<uint16_t> slot_of_code((size_t)S * S * S, 0xffff), code5(nst), cf(nst), cl(nst);
+  // distance classes are only trusted when they are far apart compared with the float noise of dist2
+  const double res = (double)h->voxel_size;
+  const bool classes_ok = noise * 4.0 < res * res;
+  for (int s = 0; s < nst; s++) {
+    slot_of_code[(size_t)((st[s].x + rho) * S + (st[s].y + rho)) * S + (st[s].z + rho)] = (uint16_t)s;
+    code5[s] = (uint16_t)pack5(st[s].x + rho, st[s].y + rho, st[s].z + rho);
+  }
+  for (int s = 0; s < nst;) {
+    int e = s;
+    while (e + 1 < nst && (classes_ok ? st[e + 1].w == st[s].w : true)) e++;
+    for (int t = s; t <= e; t++) { cf[t] = (uint16_t)s; cl[t] = (uint16_t)e; }
+    s = e + 1;
+  }
+  // pair stencil
+  const int r2 = 2 * rho, S2 = 2 * r2 + 1;
+  h->st_r2 = r2;
+  h->rows_ok = rho <= 5 && S * S * S <= 65535;
+  h->pc_cols_host.clear();
+  if (h->rows_ok) {
+    std::vector<char> seen((size_t)S2 * S2 * S2, 0);
+    std::vector<int4> st2;
+    for (const int4& p1 : st)
+      for (const int4& p2 : st) {
+        int dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+        if (!(dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0))))) continue;
+        int code = ((dx + r2) * S2 + (dy + r2)) * S2 + (dz + r2);
+        if (seen[code]) continue;
+        seen[code] = 1;
+        st2.push_back(make_int4(dx, dy, dz, 0));
+      }
+    h->pc_cols_host = columns(st2, r2);
+    h->max_row_len = 2 * (int64_t)st2.size();
+  }
+  h->lbits = rho <= 3 ? 3 : 4;
+  h->mwords = (S * S * S + 31) / 32;
+  // upload (synchronous with respect to the host vectors: the copies are made from pageable memory)
+  CK(h->d_adj_cols.reserve(h->adj_cols_host.size() * sizeof(int4) + 16));
+  CK(cudaMemcpyAsync(h->d_adj_cols.p, h->adj_cols_host.data(), h->adj_cols_host.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CK(h->d_pc_cols.reserve(h->pc_cols_host.size() * sizeof(int4) + 16));
+  if (!h->pc_cols_host.empty())
+    CK(cudaMemcpyAsync(h->d_pc_cols.p, h->pc_cols_host.data(), h->pc_cols_host.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CK(h->tb_slot.reserve(slot_of_code.size() * 2 + 16)); CK(h->tb_code5.reserve((size_t)nst * 2 + 16));
+  CK(h->tb_first.reserve((size_t)nst * 2 + 16)); CK(h->tb_last.reserve((size_t)nst * 2 + 16));
+  CK(cudaMemcpyAsync(h->tb_slot.p, slot_of_code.data(), slot_of_code.size() * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->tb_code5.p, code5.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->tb_first.p, cf.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->tb_last.p, cl.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(stream_wait(h->stream));     // the host vectors go out of scope
+  h->st_vs = h->voxel_size; h->st_gs = graph_size; h->st_noise = noise;
   return VGS_OK;
 }
 
@@ -919,10 +1018,23 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     t.stop();
     return VGS_OK;
   }
-  { vgs_status sg_ = ensure_geometry(h); if (sg_) return sg_; }
+  // ---- VGS: findAllVoxelAdjacency (VS.h:223-265) on the voxel lattice ----
   h->graph_size = graph_size;
   h->have_adj = h->have_segments = false;
   const int64_t nu = h->nu;
+  const float res_f = (float)(double)h->voxel_size;
+  // float noise of a squared centre distance: centres carry <= 1/2 ulp of the largest coordinate each
+  double maxc = 0;
+  for (int a = 0; a < 3; a++) {
+    maxc = std::max(maxc, std::fabs(((double)h->kminmax[a] + 0.5) * res_f + h->bb_f[a]));
+    maxc = std::max(maxc, std::fabs(((double)h->kminmax[3 + a] + 0.5) * res_f + h->bb_f[a]));
+  }
+  int ex = 0;
+  std::frexp(maxc, &ex);
+  const double ulp = std::ldexp(1.0, ex - 24);
+  const double noise = maxc > 0 ? 12.0 * (double)graph_size * ulp : 0.0;
+  { vgs_status s_ = build_lattice_tables(h, graph_size, noise); if (s_) return s_; }
+  const int nst = (int)h->stencil_host.size(), rho = h->st_rho, r2c = h->st_r2;
   // hash table: plain morton -> voxel id
   uint64_t capacity = 64;
   while (capacity < (uint64_t)nu * 2) capacity <<= 1;
@@ -932,369 +1044,229 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(cudaMemsetAsync(h->tk.p, 0xff, capacity * 8, h->stream));
   LAUNCH(k_plain_morton, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, h->plainm.as<uint64_t>());
   LAUNCH(k_hash_insert, (unsigned)cdiv(nu, 256), 256, 0, h->plainm.as<uint64_t>(), nu, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask);
-  if (h->st_vs != h->voxel_size || h->st_gs != graph_size) {
-    h->stencil_host = make_stencil(h->voxel_size, graph_size);
-    int rho = 0;
-    for (const int4& o : h->stencil_host) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
-    auto columns = [](const std::vector<int4>& offs, int reach) {
-      std::vector<int4> cols;
-      for (const int4& o : offs) {
-        bool found = false;
-        for (int4& c : cols) if (c.x == o.x && c.y == o.y) { c.z |= 1 << (o.z + reach); found = true; break; }
-        if (!found) cols.push_back(make_int4(o.x, o.y, 1 << (o.z + reach), 0));
-      }
-      return cols;
-    };
-    h->st_rho = rho;
-    h->adj_cols_host = rho <= 15 ? columns(h->stencil_host, rho) : std::vector<int4>();
-    const int r2 = 2 * rho, S = 2 * r2 + 1;
-    h->st_r2 = r2;
-    h->st_half = (S * S * S - 1) / 2;
-    std::vector<char> seen((size_t)S * S * S, 0);
-    h->st2_host.clear();
-    for (const int4& p1 : h->stencil_host)
-      for (const int4& p2 : h->stencil_host) {
-        int dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
-        if (!(dx > 0 || (dx == 0 && (dy > 0 || (dy == 0 && dz > 0))))) continue;
-        int code = ((dx + r2) * S + (dy + r2)) * S + (dz + r2);
-        if (seen[code]) continue;
-        seen[code] = 1;
-        h->st2_host.push_back(make_int4(dx, dy, dz, code - h->st_half - 1));
-      }
-    h->pc_cols_host = r2 <= 15 ? columns(h->st2_host, r2) : std::vector<int4>();
-    h->st_vs = h->voxel_size; h->st_gs = graph_size;
-  }
-  const std::vector<int4>& st = h->stencil_host;
-  const int nst = (int)st.size();
-  const int wpb = 4;
-  size_t smem = (size_t)wpb * nst * 8;
-  if (smem > 200 * 1024) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
-  CK(h->stencil.reserve((size_t)nst * sizeof(int4)));
-  CK(cudaMemcpyAsync(h->stencil.p, st.data(), (size_t)nst * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-  double r = (double)graph_size;
-  float r2 = (float)(r * r);
+  // occupancy grids over the occupied key range (+ margin: no bounds checks in the searches)
+  const int margin = std::max(rho, r2c) + 1;
+  BitGrid& g = h->grid;
+  g.x0 = (int)h->kminmax[0] - margin; g.y0 = (int)h->kminmax[1] - margin; g.z0 = (int)h->kminmax[2] - margin;
+  const uint64_t nx = (uint64_t)(h->kminmax[3] - h->kminmax[0] + 1) + 2 * margin;
+  g.ny = (uint32_t)(h->kminmax[4] - h->kminmax[1] + 1) + 2 * margin;
+  g.nz = (uint32_t)(h->kminmax[5] - h->kminmax[2] + 1) + 2 * margin;
+  const uint64_t nbits = nx * g.ny * g.nz;
+  if (nbits > ((uint64_t)1 << 35)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: occupied key range too large for the occupancy grid (> 4 GB): tile the scene");
+  const size_t bm_bytes = (size_t)(nbits / 8) + 64;
+  CK(h->bm_all.reserve(bm_bytes)); CK(h->bm_used.reserve(bm_bytes));
+  CK(cudaMemsetAsync(h->bm_all.p, 0, bm_bytes, h->stream));
+  CK(cudaMemsetAsync(h->bm_used.p, 0, bm_bytes, h->stream));
+  LAUNCH(k_bitgrid_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, g, h->bm_all.as<uint32_t>(),
+         h->bm_used.as<uint32_t>());
+  LatticeGeom& lg = h->lgeo;
+  lg.res_f = res_f; lg.mnx = h->bb_f[0]; lg.mny = h->bb_f[1]; lg.mnz = h->bb_f[2];
+  { double r = (double)graph_size; lg.r2 = (float)(r * r); }
+  lg.rho = rho; lg.r2c = r2c;
+  // counts: neighbours of every voxel, weight-row length of every used voxel
+  const bool want_rows = h->rows_ok && h->use_pair_cache;
   CK(h->adj_cnt.reserve((size_t)(nu + 1) * 4)); CK(h->adj_off.reserve((size_t)(nu + 1) * 4));
-  // one probing pass when the fixed-stride staging rows fit (nu * nst ids); otherwise count, scan, probe again
-  const bool one_pass = !h->adj_two_pass && (size_t)nu * (size_t)nst * 4 <= ((size_t)8 << 30);
-  if (one_pass) CK(h->adj_stage.reserve((size_t)nu * (size_t)nst * 4 + 16));
-  const int rho_s = h->st_rho;
-  if (one_pass && h->use_bitmap && h->depth <= 11 && rho_s <= 15 && nst < 65536 && (size_t)wpb * nst * 10 <= 200 * 1024) {
-    // lattice search on the all-voxel occupancy bitmap: stencil columns (dx, dy, mask of dz)
-    const std::vector<int4>& cols = h->adj_cols_host;
-    const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
-    CK(h->bitmap.reserve(bm_bytes));
-    CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
-    LAUNCH(k_bitmap_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), (const uint8_t*)nullptr, nu, h->depth, h->bitmap.as<uint32_t>());
-    CK(h->stencil2.reserve(cols.size() * sizeof(int4)));
-    CK(cudaMemcpyAsync(h->stencil2.p, cols.data(), cols.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_adjacency_bm, (unsigned)cdiv(nu, wpb), wpb * 32, (size_t)wpb * nst * 10, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
-           h->stencil2.as<int4>(), (int)cols.size(), rho_s, h->bitmap.as<uint32_t>(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(),
-           h->hmask, r2, h->adj_cnt.as<uint32_t>(), h->adj_stage.as<int32_t>(), nst);
-  } else
-  LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
-         h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, one_pass ? 2 : 0,
-         h->adj_cnt.as<uint32_t>(), (const uint32_t*)nullptr, one_pass ? h->adj_stage.as<int32_t>() : (int32_t*)nullptr, nst);
-  unsigned long long total = 0;
-  vgs_status s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, &total);
+  CK(h->row_len.reserve((size_t)(nu + 1) * 4)); CK(h->row_off.reserve((size_t)(nu + 1) * 4)); CK(h->row_npos.reserve((size_t)nu * 2 + 16));
+  CK(h->long_rows.reserve((size_t)nu * 4 + 16)); CK(h->cstats.reserve(256));
+  CK(cudaMemsetAsync(h->cstats.p, 0, 256, h->stream));
+  LAUNCH(k_adj_count, (unsigned)cdiv(nu, 8), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
+         h->bm_used.as<uint32_t>(), h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), h->d_pc_cols.as<int4>(),
+         want_rows ? (int)h->pc_cols_host.size() : 0, h->adj_cnt.as<uint32_t>(), h->row_len.as<uint32_t>(), h->row_npos.as<uint16_t>(),
+         ROWS_SHORT_CAP, h->long_rows.as<uint32_t>(), h->cstats.as<CountStats>());
+  unsigned long long* d_tot_adj = h->small.as<unsigned long long>() + 8;
+  unsigned long long* d_tot_rows = h->small.as<unsigned long long>() + 9;
+  vgs_status s = scan_u32(h, h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), nu, nullptr, d_tot_adj);
   if (s) return s;
-  if (total >= (1ull << 32)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: more than 2^32 adjacency entries on one device");
-  uint32_t tot32 = (uint32_t)total;
-  CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, &tot32, 4, cudaMemcpyHostToDevice, h->stream));
-  h->n_adj = (int64_t)total;
-  CK(h->adj_idx.reserve((size_t)total * 4 + 16));
-  if (one_pass)
-    LAUNCH(k_adjacency_compact, (unsigned)cdiv(nu * 32, 256), 256, 0, h->adj_stage.as<int32_t>(), nst, h->adj_off.as<uint32_t>(), nu,
-           h->adj_idx.as<int32_t>());
-  else
-    LAUNCH(k_adjacency, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->key3.as<uint32_t>(), h->center.as<float>(), nu, h->depth,
-           h->stencil.as<int4>(), nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
-           h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), nst);
+  s = scan_u32(h, h->row_len.as<uint32_t>(), h->row_off.as<uint32_t>(), nu, nullptr, d_tot_rows);
+  if (s) return s;
+  CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, d_tot_adj, 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->row_off.as<uint32_t>() + nu, d_tot_rows, 4, cudaMemcpyDeviceToDevice, h->stream));
+  unsigned long long totals[2] = {0, 0};
+  CountStats cs{};
+  CK(cudaMemcpyAsync(totals, d_tot_adj, 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&cs, h->cstats.p, sizeof(cs), cudaMemcpyDeviceToHost, h->stream));
+  CK(stream_wait(h->stream));
+  if (totals[0] >= (1ull << 32)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: more than 2^32 adjacency entries on one device");
+  if (totals[1] >= (1ull << 32)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: more than 2^32 pair-weight entries on one device");
+  h->n_adj = (int64_t)totals[0];
+  h->n_rows = (int64_t)totals[1];
+  h->n_long = (int64_t)cs.n_long;
+  h->n_pairs = (int64_t)cs.sum_nn; h->max_n = (int64_t)cs.max_n; h->n_used = (int64_t)cs.n_used;
+  if (cs.max_n > 255) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: a voxel has more than 255 neighbours within graph_size");
+  CK(h->adj_idx.reserve((size_t)h->n_adj * 4 + 16)); CK(h->adj_code.reserve((size_t)h->n_adj * 2 + 16));
+  unsigned* d_err = h->small.as<unsigned>() + 200;
+  CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
+  AdjTables tb{h->tb_slot.as<uint16_t>(), h->tb_code5.as<uint16_t>(), h->tb_first.as<uint16_t>(), h->tb_last.as<uint16_t>()};
+  LAUNCH(k_adj_fill, (unsigned)cdiv(nu, ADJ_WARPS), ADJ_WARPS * 32, adj_fill_smem(nst), h->key3.as<uint32_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
+         h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), tb, nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask,
+         h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), d_err);
   h->have_adj = true;
   t.stop();
   return VGS_OK;
 }
 
-static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first, int64_t last);
+static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred);
 static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min);
 
 vgs_status vgs_segment(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   if (!h || !sg) return VGS_ERR_INVALID;
   if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_segment: call vgs_find_adjacency first");
-  vgs_status s = segment_graph(h, sg, cut_thred, 0, h->nu);
+  vgs_status s = segment_graph(h, sg, cut_thred);
   if (s) return s;
   return segment_finish(h, sg, cut_thred, adjacency_min);
 }
 
-vgs_status vgs_segment_partial(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first_unit, int64_t last_unit) {
-  if (!h || !sg) return VGS_ERR_INVALID;
-  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_segment_partial: call vgs_find_adjacency first");
-  if (first_unit < 0 || last_unit > h->nu || first_unit > last_unit) return h->fail(VGS_ERR_INVALID, "vgs_segment_partial: bad unit range");
-  return segment_graph(h, sg, cut_thred, first_unit, last_unit);
-}
-
-vgs_status vgs_segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
-  if (!h || !sg) return VGS_ERR_INVALID;
-  if (!h->have_graph) return h->fail(VGS_ERR_STATE, "vgs_segment_finish: connect lists incomplete — call vgs_segment_partial, then import EVERY other range");
-  return segment_finish(h, sg, cut_thred, adjacency_min);
-}
-
-vgs_status vgs_adj_range(vgs_handle h, int64_t first_unit, int64_t last_unit, int64_t* e_first, int64_t* e_last) {
-  if (!h || !e_first || !e_last) return VGS_ERR_INVALID;
-  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_adj_range: call vgs_find_adjacency first");
-  if (first_unit < 0 || last_unit > h->nu || first_unit > last_unit) return h->fail(VGS_ERR_INVALID, "vgs_adj_range: bad unit range");
-  CK(cudaSetDevice(h->device));
-  uint32_t a = 0, b = 0;
-  CK(cudaMemcpyAsync(&a, h->adj_off.as<uint32_t>() + first_unit, 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(&b, h->adj_off.as<uint32_t>() + last_unit, 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(stream_wait(h->stream));
-  *e_first = a; *e_last = b;
+// general kernel (one CTA per unit, weights evaluated from the records) over a list of units
+static vgs_status launch_general(vgs_handle h, cudaStream_t st, const uint32_t* list, uint32_t count, int n_class, int T, uint32_t max_n,
+                                 const GraphParams& gp, const float* d_wempty) {
+  const int ncap = (int)((max_n + 3u) & ~3u), mcap = n_class * (n_class - 1);
+  size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + 4 * REC_PAD) + (2 * LG_BINS + 2) * 4 + 64;
+  const int bucketed = (smem + (size_t)mcap * 2 <= 220 * 1024) ? 1 : 0;   // bin-ordered pool index if it fits
+  if (bucketed) smem += (size_t)mcap * 2;
+#define LG(TT)                                                                                                      \
+  do {                                                                                                              \
+    auto kfn = k_local_graph2<TT>;                                                                                  \
+    LAUNCH_ON(st, kfn, count, TT, smem, list, count, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),           \
+              h->rec.as<float>(), gp, ncap, mcap, d_wempty, bucketed, h->conn0_cnt.as<uint32_t>(),                  \
+              h->conn0_idx.as<int32_t>());                                                                          \
+  } while (0)
+  if (T == 64) LG(64); else if (T == 128) LG(128); else LG(256);
+#undef LG
   return VGS_OK;
 }
 
-// Contiguous unit-id ranges with ~equal sum of n^2 (n = neighbourhood size, the pair-work proxy) for `parts` ranks,
-// and the adjacency slots they cover: first_unit / first_slot have parts + 1 entries.  Deterministic, identical on
-// every rank (all ranks hold the same adjacency).
-vgs_status vgs_unit_ranges(vgs_handle h, int parts, int64_t* first_unit, int64_t* first_slot) {
-  if (!h || !first_unit || !first_slot || parts < 1) return VGS_ERR_INVALID;
-  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_unit_ranges: call vgs_find_adjacency first");
-  CK(cudaSetDevice(h->device));
-  const int64_t nu = h->nu;
-  h->host_u32.resize((size_t)nu + 1);
-  CK(cudaMemcpyAsync(h->host_u32.data(), h->adj_off.p, (size_t)(nu + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(stream_wait(h->stream));
-  const uint32_t* off = h->host_u32.data();
-  double total = 0;
-  for (int64_t u = 0; u < nu; u++) { const double n = (double)(off[u + 1] - off[u]); total += n * n; }
-  first_unit[0] = 0;
-  int r = 1;
-  double acc = 0;
-  for (int64_t u = 0; u < nu && r < parts; u++) {
-    // cut before the first unit whose prefix sum reaches r/parts of the total (numpy.searchsorted(w, t, 'left'))
-    while (r < parts && acc >= total * (double)r / (double)parts) first_unit[r++] = u;
-    const double n = (double)(off[u + 1] - off[u]);
-    acc += n * n;
-  }
-  while (r < parts) first_unit[r++] = nu;
-  first_unit[parts] = nu;
-  for (int i = 0; i <= parts; i++) first_slot[i] = (int64_t)off[first_unit[i]];
-  return VGS_OK;
-}
-
-static vgs_status connect_copy(vgs_handle h, int64_t first, int64_t last, int32_t* cnt_dev, int32_t* idx_dev, bool to_caller) {
-  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "connect lists: call vgs_find_adjacency first");
-  if (first < 0 || last > h->nu || first > last || !cnt_dev || !idx_dev) return h->fail(VGS_ERR_INVALID, "connect lists: bad range or buffer");
-  CK(cudaSetDevice(h->device));
-  int64_t e0, e1;
-  vgs_status s = vgs_adj_range(h, first, last, &e0, &e1);
-  if (s) return s;
-  const size_t E = (size_t)h->n_adj;
-  CK(h->conn0_cnt.reserve((size_t)h->nu * 4)); CK(h->conn0_idx.reserve(E * 4 + 16));
-  void* c = h->conn0_cnt.as<uint32_t>() + first; void* i = h->conn0_idx.as<int32_t>() + e0;
-  if (to_caller) {
-    CK(cudaMemcpyAsync(cnt_dev, c, (size_t)(last - first) * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(idx_dev, i, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
-  } else {
-    CK(cudaMemcpyAsync(c, cnt_dev, (size_t)(last - first) * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(i, idx_dev, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToDevice, h->stream));
-    h->graph_covered += last - first;
-    h->have_graph = h->graph_covered >= h->nu;   // every range present (a lost exchange must not pass silently)
-  }
-  CK(stream_wait(h->stream));
-  return VGS_OK;
-}
-vgs_status vgs_export_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, int32_t* cnt_dev, int32_t* idx_dev) {
-  if (!h) return VGS_ERR_INVALID;
-  return connect_copy(h, first_unit, last_unit, cnt_dev, idx_dev, true);
-}
-vgs_status vgs_import_connect(vgs_handle h, int64_t first_unit, int64_t last_unit, const int32_t* cnt_dev, const int32_t* idx_dev) {
-  if (!h) return VGS_ERR_INVALID;
-  return connect_copy(h, first_unit, last_unit, const_cast<int32_t*>(cnt_dev), const_cast<int32_t*>(idx_dev), false);
-}
-
-static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int64_t first, int64_t last) {
+static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_thred) {
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
   h->have_segments = false;
-  h->have_graph = false;
   h->have_cluster_stats = false;
+  h->conn0_is_mask = false;
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
   gp.cut = cut_thred;
   const size_t E = (size_t)h->n_adj;
-  CK(h->conn0_cnt.reserve((size_t)nu * 4)); CK(h->conn0_idx.reserve(E * 4 + 16));
+  CK(h->conn0_cnt.reserve((size_t)nu * 4));
   CK(h->conn1_cnt.reserve((size_t)nu * 4)); CK(h->conn1_idx.reserve(E * 4 + 16));
   CK(h->attach.reserve((size_t)nu * 4)); CK(h->parent.reserve((size_t)nu * 4)); CK(h->root.reserve((size_t)nu * 4));
-  // ---- stage 4+5a: local graphs ----
-  {
-    StageTimer t(h, &h->tm.graph_ms, 5);
-    CK(h->class_count.reserve(256));
-    CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
-    CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
-    LAUNCH(k_class_init, (unsigned)cdiv(nu, 256), 256, 0, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), nu);
-    unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
-    float* d_wempty = h->small.as<float>() + 160;
-    uint32_t* d_maxn = h->class_count.as<uint32_t>() + 16;
-    CK(cudaMemsetAsync(h->class_count.p, 0, 256, h->stream));
-    CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
-    CK(cudaMemsetAsync(h->conn0_cnt.as<uint32_t>() + first, 0, (size_t)(last - first) * 4, h->stream));   // own range only: other ranges are imported / computed by other calls
-    LAUNCH(k_wempty, 1, 1, 0, gp.pp, d_wempty);
-    const bool partial = !(first == 0 && last == nu);
-    uint8_t* d_need = nullptr;
-    if (partial) {   // pair-cache rows this rank's local graphs will read
-      CK(h->need_rows.reserve((size_t)nu + 16));
-      d_need = h->need_rows.as<uint8_t>();
-      CK(cudaMemsetAsync(d_need, 0, (size_t)nu, h->stream));
-    }
-    LAUNCH(k_bin_classes, (unsigned)cdiv((last - first) * 32 + 1, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
-           h->uflags.as<uint8_t>(), nu, first, last, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
-           d_maxn, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), d_stats, d_need);
-    // class lists ordered by unit id (deterministic, and consecutive CTAs work on neighbouring voxels, which
-    // keeps the pair-table rows they share in L2): one stable 8-bit radix pass on (class, unit id)
-    uint64_t* cls_keys; uint32_t* cls_sorted;
+  StageTimer t(h, &h->tm.graph_ms, 5);
+  float* d_wempty = h->small.as<float>() + 160;
+  LAUNCH(k_wempty, 1, 1, 0, gp.pp, d_wempty);
+  unsigned long long* d_dbg = nullptr;
+  if (getenv("VGS_B200_DEBUG_COUNTERS")) {
+    d_dbg = h->small.as<unsigned long long>() + 64;
+    CK(cudaMemsetAsync(d_dbg, 0, 64, h->stream));
+  }
+  const bool rows_path = h->mode == VGS_MODE_VGS && h->rows_ok && h->use_pair_cache;
+  if (rows_path) {
+    // ---- stage 4: weight rows (every unordered pair of used voxels once) ----
+    const LatticeGeom& lg = h->lgeo;
+    unsigned* d_err = h->small.as<unsigned>() + 200;
+    uint32_t* d_fb_count = h->small.as<uint32_t>() + 201;
+    CK(cudaMemsetAsync(d_err, 0, 8, h->stream));
     {
-      vgs_status s_ = radix_sort(h, nu, 8, &cls_keys, &cls_sorted, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(),
-                                 h->cvalsA.as<uint32_t>(), h->cvalsB.as<uint32_t>());
-      if (s_) return s_;
+      StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
+      CK(h->rows.reserve((size_t)h->n_rows * 8 + 64)); CK(h->cursor.reserve((size_t)nu * 4 + 16));
+      LAUNCH(k_rows_cursor, (unsigned)cdiv(nu, 256), 256, 0, h->row_off.as<uint32_t>(), h->row_npos.as<uint16_t>(), nu, h->cursor.as<uint32_t>());
+      LAUNCH(k_rows_fill, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg, h->grid, h->bm_used.as<uint32_t>(),
+             h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
+             h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->cursor.as<uint32_t>(), h->rows.as<uint2>(), d_err);
+      LAUNCH(k_rows_sort, (unsigned)cdiv(nu, RS2_WARPS), RS2_WARPS * 32, (size_t)RS2_WARPS * 2 * ROWS_SHORT_CAP * 8, h->row_off.as<uint32_t>(), nu,
+             (const uint32_t*)nullptr, 0u, ROWS_SHORT_CAP, h->rows.as<uint2>());
+      if (h->n_long > 0) {
+        const int cap_long = (int)((h->max_row_len + 63) & ~(int64_t)63);
+        LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 8, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
+               (uint32_t)h->n_long, cap_long, h->rows.as<uint2>());
+      }
+      tpc.stop();
     }
-    uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
-    unsigned long long stats[3];
-    CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(cmaxn, d_maxn, sizeof(cmaxn), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
+    // ---- stage 5a: one warp per voxel ----
+    const int mw = h->mwords;
+    CK(h->conn_mask.reserve((size_t)nu * mw * 4 + 16));
+    CK(h->fallback.reserve((size_t)nu * 4 + 16));
+    LAUNCH(k_local_graph_rows, (unsigned)cdiv(nu, LR_WARPS), LR_WARPS * 32, lr_slice_bytes(h->lbits, mw) * LR_WARPS, (int64_t)0, nu,
+           h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw,
+           h->row_off.as<uint32_t>(), h->rows.as<uint2>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
+           h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, d_dbg);
+    uint32_t fe[2] = {0, 0};   // [0] = error bits of the fill kernels, [1] = units handed back
+    CK(cudaMemcpyAsync(fe, d_err, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
-    h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
-    if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a local graph has more than 181 enumerated (or 255 total) units (graph_size / unit spacing too large)");
-    // pair-weight cache (VGS lattice): each unordered pair of used voxels evaluated once
-    bool cached = false;
-    int half = 0, r2 = 0;
-    if (h->mode == VGS_MODE_VGS && h->use_pair_cache && !h->stencil_host.empty()) {
-      r2 = h->st_r2;
-      half = h->st_half;
-      size_t bytes = (size_t)nu * (size_t)half * sizeof(float2);
-      bool fits = bytes <= h->pair_table.cap;
-      if (!fits) {   // only when the table has to grow: cudaMemGetInfo is a slow driver call
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        fits = bytes < (free_b + h->pair_table.cap) / 2;
-      }
-      if (fits) {
-        const std::vector<int4>& st2 = h->st2_host;
-        CK(h->pair_table.reserve(bytes));
-        StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
-        if (h->use_bitmap && h->depth <= 11 && 2 * r2 + 1 <= 13 && half < 65536) {   // PC_QCAP holds 13 hits per column and lane
-          // partner search on an occupancy bitmap of the used voxels: stencil columns (dx, dy, mask of dz)
-          const std::vector<int4>& cols = h->pc_cols_host;
-          const size_t bm_bytes = ((size_t)1 << (3 * h->depth)) / 8 + 64;
-          CK(h->bitmap.reserve(bm_bytes));
-          CK(cudaMemsetAsync(h->bitmap.p, 0, bm_bytes, h->stream));
-          LAUNCH(k_bitmap_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, h->depth, h->bitmap.as<uint32_t>());
-          CK(h->stencil2.reserve(cols.size() * sizeof(int4)));
-          CK(cudaMemcpyAsync(h->stencil2.p, cols.data(), cols.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-          LAUNCH(k_pair_cache_bm, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
-                 h->stencil2.as<int4>(), (int)cols.size(), r2, h->bitmap.as<uint32_t>(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(),
-                 h->hmask, gp.pp, h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
-        } else {
-          CK(h->stencil2.reserve(st2.size() * sizeof(int4)));
-          CK(cudaMemcpyAsync(h->stencil2.p, st2.data(), st2.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-          LAUNCH(k_pair_cache, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, h->depth,
-                 h->stencil2.as<int4>(), (int)st2.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
-                 h->pair_table.as<float2>(), half, d_need, h->uflags.as<uint8_t>());
-        }
-        tpc.stop();
-        cached = true;
-      }
-    }
-    // warp-per-unit kernel for the cached VGS path; units it cannot handle come back in a fallback list
-    uint32_t* d_fb_count = h->class_count.as<uint32_t>() + 48;
-    const bool use_warp = cached && h->use_warp_kernel;
-    unsigned long long* d_dbg = nullptr;
-    if (getenv("VGS_B200_DEBUG_COUNTERS")) {
-      d_dbg = h->small.as<unsigned long long>() + 64;
-      CK(cudaMemsetAsync(d_dbg, 0, 64, h->stream));
-    }
-    size_t scratch_off = 0;
-    if (use_warp) {
-      CK(h->fallback.reserve((size_t)nu * 4 + 16));
-      size_t need = 0;
-      for (int c = 0; c < N_CLASSES; c++)
-        if (cc[c] && CLASS_N_HOST[c] <= 128) need += (size_t)cc[c] * (size_t)CLASS_N_HOST[c] * (size_t)(CLASS_N_HOST[c] - 1);
-      CK(h->lg_scratch.reserve(need * 3 + 64));
-    }
-    uint32_t max_n_all = 0;
-    for (int c = 0; c < N_CLASSES; c++) max_n_all = std::max(max_n_all, cc[c] ? cmaxn[c] : 0u);
-    size_t class_off[N_CLASSES + 1];
-    class_off[0] = 0;
-    for (int c = 0; c < N_CLASSES; c++) class_off[c + 1] = class_off[c] + cc[c];
-    // classes of big units first (few units, long per-unit time), spread over the class streams
-    const int nstreams = h->class_streams;
-    if (nstreams > 1) {
-      CK(cudaEventRecord(h->ev_fork, h->stream));
-      for (int i = 0; i < nstreams - 1; i++) CK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
-    }
-    int launch_no = 0;
-    for (int c = N_CLASSES - 1; c >= 0; c--) {
-      if (!cc[c]) continue;
-      const int ncap = (int)((cmaxn[c] + 3u) & ~3u), mcap = CLASS_N_HOST[c] * (CLASS_N_HOST[c] - 1), T = CLASS_T_HOST[c];
-      const int si = launch_no++ % nstreams;
-      cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
-      if (use_warp && CLASS_N_HOST[c] <= 128) {
-        const size_t slice = lw_slice_bytes(ncap, mcap);
-        const uint32_t* wlist = cls_sorted + class_off[c];
-        unsigned short* scratch = h->lg_scratch.as<unsigned short>() + scratch_off;
-        scratch_off += (size_t)cc[c] * (size_t)(mcap + mcap / 2);
-        LAUNCH_ON(st, k_local_graph_warp, (unsigned)cdiv(cc[c], LW_WARPS), LW_WARPS * 32, slice * LW_WARPS, wlist, cc[c],
-               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->uflags.as<uint8_t>(), h->key3.as<uint32_t>(), cut_thred, ncap,
-               mcap, h->pair_table.as<float2>(), half, r2, d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(),
-               h->fallback.as<uint32_t>(), d_fb_count, scratch, h->lw_chunk, d_dbg);
-        continue;
-      }
-      size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + (cached ? 16 : 4 * REC_PAD)) + (2 * LG_BINS + 2) * 4 + 64;
-      const int bucketed = (smem + (size_t)mcap * 2 <= 220 * 1024) ? 1 : 0;   // bin-ordered pool index if it fits
-      if (bucketed) smem += (size_t)mcap * 2;
-      const uint32_t* list = cls_sorted + class_off[c];
-#define LG(TT, CC)                                                                                                  \
-  do {                                                                                                              \
-    auto kfn = k_local_graph2<TT, CC>;                                                                              \
-    LAUNCH_ON(st, kfn, cc[c], TT, smem, list, cc[c], h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),           \
-           h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2,        \
-           d_wempty, bucketed, h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());                                                \
-  } while (0)
-      if (cached) { if (T == 64) LG(64, true); else if (T == 128) LG(128, true); else LG(256, true); }
-      else { if (T == 64) LG(64, false); else if (T == 128) LG(128, false); else LG(256, false); }
-#undef LG
-    }
-    if (nstreams > 1)
-      for (int i = 0; i < nstreams - 1; i++) {
-        CK(cudaEventRecord(h->ev_join[i], h->aux[i]));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
-      }
+    if (fe[0]) return h->fail(VGS_ERR_CUDA, "vgs_segment: internal inconsistency between the occupancy grid and the voxel table (error bits " + std::to_string(fe[0]) + ")");
+    h->n_fallback = fe[1];
     if (d_dbg) {
       unsigned long long dd[8];
       CK(cudaMemcpyAsync(dd, d_dbg, 64, cudaMemcpyDeviceToHost, h->stream));
       CK(stream_wait(h->stream));
-      fprintf(stderr, "[vgs debug] units %llu chunks %llu (%.2f/unit) scanned %llu (%.1f/unit) kept %llu (%.1f/unit) m/unit %.1f final_nseg/unit %.2f nv/unit %.1f\n",
-              dd[3], dd[0], (double)dd[0] / (double)std::max(1ull, dd[3]), dd[1], (double)dd[1] / (double)std::max(1ull, dd[3]), dd[2],
-              (double)dd[2] / (double)std::max(1ull, dd[3]), (double)dd[4] / (double)std::max(1ull, dd[3]),
-              (double)dd[5] / (double)std::max(1ull, dd[3]), (double)dd[6] / (double)std::max(1ull, dd[3]));
+      fprintf(stderr, "[vgs debug] units %llu rounds %llu (%.2f/unit) staged %llu (%.1f/unit) final_nseg/unit %.2f nv/unit %.1f fallback %u\n", dd[3], dd[0],
+              (double)dd[0] / (double)std::max(1ull, dd[3]), dd[2], (double)dd[2] / (double)std::max(1ull, dd[3]),
+              (double)dd[5] / (double)std::max(1ull, dd[3]), (double)dd[6] / (double)std::max(1ull, dd[3]), fe[1]);
     }
-    if (use_warp) {   // units the warp kernel handed back: general CTA kernel sized for the largest neighbourhood
-      uint32_t nfb = 0;
-      CK(cudaMemcpyAsync(&nfb, d_fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
-      CK(stream_wait(h->stream));
-      h->n_fallback = nfb;
-      if (nfb) {
-        const int ncap = (int)((max_n_all + 3u) & ~3u), mcap = CLASS_N_HOST[N_CLASSES - 1] * (CLASS_N_HOST[N_CLASSES - 1] - 1);
-        size_t smem = (size_t)mcap * 6 + (size_t)LG_CS * 6 + (size_t)ncap * (14 + 16) + (2 * LG_BINS + 2) * 4 + 64;
-        auto kfn = k_local_graph2<256, true>;
-        LAUNCH(kfn, nfb, 256, smem, h->fallback.as<uint32_t>(), nfb, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
-               h->rec.as<float>(), h->key3.as<uint32_t>(), gp, ncap, mcap, h->pair_table.as<float2>(), half, r2, d_wempty, 0,
-               h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>());
-      }
+    if (fe[1]) {   // units the row kernel handed back: general kernel sized for the largest neighbourhood, then list -> mask
+      CK(h->conn0_idx.reserve(E * 4 + 16));
+      vgs_status s_ = launch_general(h, h->stream, h->fallback.as<uint32_t>(), fe[1], CLASS_N_HOST[N_CLASSES - 1], 256, (uint32_t)h->max_n, gp, d_wempty);
+      if (s_) return s_;
+      LAUNCH(k_conn_list_to_mask, (unsigned)cdiv((int64_t)fe[1] * 32, 128), 128, 0, h->fallback.as<uint32_t>(), fe[1], h->adj_off.as<uint32_t>(),
+             h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(), lg.rho, mw,
+             h->conn_mask.as<uint32_t>());
     }
+    h->conn0_is_mask = true;
     t.stop();
+    h->have_graph = true;
+    return VGS_OK;
   }
-  h->graph_covered = last - first;               // a new own range invalidates earlier imports
-  h->have_graph = h->graph_covered >= nu;
+  // ---- general path (SVGS; VGS when the weight rows are disabled or the stencil is too wide): units binned by the
+  //      size of their local graph, one launch per class over up to 6 streams ----
+  CK(h->conn0_idx.reserve(E * 4 + 16));
+  CK(h->class_count.reserve(256));
+  CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
+  CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
+  LAUNCH(k_class_init, (unsigned)cdiv(nu, 256), 256, 0, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), nu);
+  unsigned long long* d_stats = h->small.as<unsigned long long>() + 24;
+  uint32_t* d_maxn = h->class_count.as<uint32_t>() + 16;
+  CK(cudaMemsetAsync(h->class_count.p, 0, 256, h->stream));
+  CK(cudaMemsetAsync(d_stats, 0, 32, h->stream));
+  CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));
+  LAUNCH(k_bin_classes, (unsigned)cdiv(nu * 32 + 1, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+         h->uflags.as<uint8_t>(), nu, (int64_t)0, nu, cut_thred, h->mode == VGS_MODE_SVGS ? 1 : 0, d_wempty, h->class_count.as<uint32_t>(),
+         d_maxn, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), d_stats);
+  // class lists ordered by unit id: one stable 8-bit radix pass on (class, unit id)
+  uint64_t* cls_keys; uint32_t* cls_sorted;
+  {
+    vgs_status s_ = radix_sort(h, nu, 8, &cls_keys, &cls_sorted, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(),
+                               h->cvalsA.as<uint32_t>(), h->cvalsB.as<uint32_t>());
+    if (s_) return s_;
+  }
+  uint32_t cc[N_CLASSES], cmaxn[N_CLASSES];
+  unsigned long long stats[3];
+  CK(cudaMemcpyAsync(cc, h->class_count.p, sizeof(cc), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cmaxn, d_maxn, sizeof(cmaxn), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
+  CK(stream_wait(h->stream));
+  h->n_pairs = (int64_t)stats[0]; h->max_n = (int64_t)stats[1];
+  if (stats[2]) return h->fail(VGS_ERR_LIMIT, "vgs_segment: a local graph has more than 181 enumerated (or 255 total) units (graph_size / unit spacing too large)");
+  size_t class_off[N_CLASSES + 1];
+  class_off[0] = 0;
+  for (int c = 0; c < N_CLASSES; c++) class_off[c + 1] = class_off[c] + cc[c];
+  // classes of big units first (few units, long per-unit time), spread over the class streams
+  const int nstreams = h->class_streams;
+  if (nstreams > 1) {
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int i = 0; i < nstreams - 1; i++) CK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
+  }
+  int launch_no = 0;
+  for (int c = N_CLASSES - 1; c >= 0; c--) {
+    if (!cc[c]) continue;
+    const int si = launch_no++ % nstreams;
+    cudaStream_t st = si == 0 ? h->stream : h->aux[si - 1];
+    vgs_status s_ = launch_general(h, st, cls_sorted + class_off[c], cc[c], CLASS_N_HOST[c], CLASS_T_HOST[c], cmaxn[c], gp, d_wempty);
+    if (s_) return s_;
+  }
+  if (nstreams > 1)
+    for (int i = 0; i < nstreams - 1; i++) {
+      CK(cudaEventRecord(h->ev_join[i], h->aux[i]));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
+    }
+  t.stop();
+  h->have_graph = true;
   return VGS_OK;
 }
 
@@ -1311,8 +1283,13 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
   // ---- stage 5b: mutual filter ----
   {
     StageTimer t(h, &h->tm.mutual_ms, 6);
-    LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
-           h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
+    if (h->conn0_is_mask)
+      LAUNCH(k_mutual_mask, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(),
+             h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(), nu, h->lgeo.rho, h->mwords, h->conn1_cnt.as<uint32_t>(),
+             h->conn1_idx.as<int32_t>());
+    else
+      LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
+             h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
     t.stop();
   }
   // ---- stage 5c: closest check ----
@@ -1554,7 +1531,16 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
     }
     case VGS_BLOB_ADJ_IDX: if (!h->have_adj) break; return copy_out(h->adj_idx.p, (size_t)h->n_adj * 4);
     case VGS_BLOB_CONN0_COUNT: if (!h->have_segments) break; return copy_out(h->conn0_cnt.p, (size_t)nu * 4);
-    case VGS_BLOB_CONN0_IDX: if (!h->have_segments) break; return copy_out(h->conn0_idx.p, (size_t)h->n_adj * 4);
+    case VGS_BLOB_CONN0_IDX: {
+      if (!h->have_segments) break;
+      if (!dst) { *bytes = (size_t)h->n_adj * 4; return VGS_OK; }
+      if (h->conn0_is_mask) {   // the row kernel keeps the lists as lattice masks: expand them in adjacency order
+        CK(h->conn0_idx.reserve((size_t)h->n_adj * 4 + 16));
+        LAUNCH(k_conn_mask_to_list, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(),
+               h->adj_code.as<uint16_t>(), nu, h->lgeo.rho, h->mwords, h->conn_mask.as<uint32_t>(), h->conn0_idx.as<int32_t>());
+      }
+      return copy_out(h->conn0_idx.p, (size_t)h->n_adj * 4);
+    }
     case VGS_BLOB_CONN1_COUNT: if (!h->have_segments) break; return copy_out(h->conn1_cnt.p, (size_t)nu * 4);
     case VGS_BLOB_CONN1_IDX: if (!h->have_segments) break; return copy_out(h->conn1_idx.p, (size_t)h->n_adj * 4);
     case VGS_BLOB_ATTACH: if (!h->have_segments) break; return copy_out(h->attach.p, (size_t)nu * 4);

@@ -1,0 +1,737 @@
+// vgs_rows.cuh — VGS lattice kernels built around an occupancy grid of the occupied key range ("BitGrid") and
+// per-voxel rows of pair weights ordered by weight.
+//
+//   stage 3  k_adj_count / k_adj_fill : radius adjacency (findAllVoxelAdjacency VS.h:223-265) written straight to the CSR,
+//                                       lists ordered by (dist2, id) with a rank sort inside each lattice distance class
+//   stage 4  k_rows_fill / k_rows_sort: every unordered pair of used voxels that can meet in a local graph is evaluated ONCE
+//                                       (buildAdjacencyGraph VS.h:1796-1910 re-evaluates it in every graph) and both directed
+//                                       weights are filed in the row of their source voxel; rows are ordered by weight cell
+//   stage 5a k_local_graph_rows       : cutGraphSegmentation (VS.h:1913-2029) of one voxel per warp, consuming only the heavy
+//                                       prefix of the rows of its neighbours (S0 rule: the cut of the voxel itself is final
+//                                       once the next weight is <= Int(S0) - k/|S0|)
+//   stage 5b k_mutual_mask            : crossValidation (VS.h:2111-2179) on lattice-offset bit masks
+#pragma once
+#include "vgs_kernels.cuh"
+
+namespace vgs {
+
+// ---- occupancy grid over the occupied key range + a margin, so stencil probes need no bounds checks ----
+struct BitGrid {
+  int x0, y0, z0;          // key of cell (0,0,0) = smallest occupied key - margin
+  uint32_t ny, nz;         // extents incl. margins; bit = ((x-x0)*ny + (y-y0))*nz + (z-z0)
+};
+__device__ __forceinline__ uint64_t bg_bit(const BitGrid& g, int x, int y, int z) {
+  return ((uint64_t)(uint32_t)(x - g.x0) * g.ny + (uint32_t)(y - g.y0)) * g.nz + (uint32_t)(z - g.z0);
+}
+// bits [b0, b0 + len) of the grid, len <= 32 (bit j = cell z0 + j of the run)
+__device__ __forceinline__ uint32_t bg_run(const uint32_t* __restrict__ bm, uint64_t b0, int len) {
+  const uint64_t two = (uint64_t)__ldg(bm + (b0 >> 5)) | ((uint64_t)__ldg(bm + (b0 >> 5) + 1) << 32);
+  return (uint32_t)(two >> (b0 & 31)) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
+}
+__global__ void __launch_bounds__(256) k_bitgrid_set(const uint32_t* __restrict__ key3, const uint8_t* __restrict__ uflags, int64_t nv,
+                                                   BitGrid g, uint32_t* __restrict__ bm_all, uint32_t* __restrict__ bm_used) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const uint64_t b = bg_bit(g, (int)key3[3 * v], (int)key3[3 * v + 1], (int)key3[3 * v + 2]);
+  atomicOr(&bm_all[b >> 5], 1u << (b & 31));
+  if (uflags[v] & F_USED) atomicOr(&bm_used[b >> 5], 1u << (b & 31));
+}
+
+// voxel key + smallest / largest occupied key per axis (the extent of the occupancy grids)
+__global__ void __launch_bounds__(256) k_voxel_keys(const uint64_t* __restrict__ ukey, int64_t nu, int depth, int descending,
+                                                  uint32_t* __restrict__ key3, uint32_t* __restrict__ kminmax /* [6] */) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t kx = 0xffffffffu, ky = 0xffffffffu, kz = 0xffffffffu, Kx = 0, Ky = 0, Kz = 0;
+  if (u < nu && !(ukey[u] >> (3 * depth))) {     // the segment of the non-finite points (sentinel key) has no voxel key
+    uint64_t m = ukey[u];
+    const uint64_t mask = (1ull << (3 * depth)) - 1ull;
+    if (descending) m = ~m & mask;
+    morton_decode(m, kx, ky, kz);
+    key3[3 * u] = kx; key3[3 * u + 1] = ky; key3[3 * u + 2] = kz;
+    Kx = kx; Ky = ky; Kz = kz;
+  }
+  kx = __reduce_min_sync(0xffffffffu, kx); ky = __reduce_min_sync(0xffffffffu, ky); kz = __reduce_min_sync(0xffffffffu, kz);
+  Kx = __reduce_max_sync(0xffffffffu, Kx); Ky = __reduce_max_sync(0xffffffffu, Ky); Kz = __reduce_max_sync(0xffffffffu, Kz);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&kminmax[0], kx); atomicMin(&kminmax[1], ky); atomicMin(&kminmax[2], kz);
+    atomicMax(&kminmax[3], Kx); atomicMax(&kminmax[4], Ky); atomicMax(&kminmax[5], Kz);
+  }
+}
+__global__ void __launch_bounds__(256) k_voxel_centers(const uint32_t* __restrict__ key3, int64_t nu, float res_f, float mnx, float mny,
+                                                     float mnz, float* __restrict__ center) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu) return;
+  center[3 * u] = (float)(((double)key3[3 * u] + 0.5f) * res_f + mnx);
+  center[3 * u + 1] = (float)(((double)key3[3 * u + 1] + 0.5f) * res_f + mny);
+  center[3 * u + 2] = (float)(((double)key3[3 * u + 2] + 0.5f) * res_f + mnz);
+}
+
+// geometry of the lattice searches, filled by the host
+struct LatticeGeom {
+  float res_f, mnx, mny, mnz;   // float-narrowed members the centres are computed from (VS.h:2102-2109)
+  float r2;                     // (float)(graph_size^2): FLANN's strict test dist2 < r2
+  int rho;                      // reach of the radius stencil (cells)
+  int r2c;                      // reach of the pair stencil = 2 * rho
+};
+// centre coordinate of key k exactly as k_voxel_centers stores it
+__device__ __forceinline__ float centre_of(uint32_t k, float res_f, float mn) { return (float)(((double)k + 0.5f) * res_f + mn); }
+// FLANN L2_Simple: sequential float accumulation of squared differences
+__device__ __forceinline__ float flann_d2(float qx, float qy, float qz, float cx, float cy, float cz) {
+  const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
+  float d2 = 0.f; d2 += dx * dx; d2 += dy * dy; d2 += dz * dz;
+  return d2;
+}
+
+// 5-bit packed lattice offsets relative to a centre voxel: (o + rho) per axis, x | y << 5 | z << 10
+__host__ __device__ __forceinline__ uint32_t pack5(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 5) | ((uint32_t)z << 10); }
+// 6-bit fields (bit 5 of each field is a guard bit for the field-parallel range test of the consumer)
+__host__ __device__ __forceinline__ uint32_t pack6(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 6) | ((uint32_t)z << 12); }
+
+// ---- stage 3a: neighbour count of every voxel (all-voxel grid, radius stencil, float test on the centres computed
+//      from the keys) and, for used voxels, the length of its weight row (used-voxel grid, pair stencil: partners in
+//      the lexicographically positive half are evaluated by this voxel, those in the negative half by the partner).
+//      One warp per voxel, lanes over stencil columns (dx, dy, mask of dz). ----
+struct CountStats { unsigned long long sum_nn, max_n, n_long, n_used; };
+__global__ void __launch_bounds__(256) k_adj_count(const uint32_t* __restrict__ key3, const uint8_t* __restrict__ uflags, int64_t nv,
+                                                 LatticeGeom lg, BitGrid g, const uint32_t* __restrict__ bm_all,
+                                                 const uint32_t* __restrict__ bm_used, const int4* __restrict__ adj_cols, int n_adj_cols,
+                                                 const int4* __restrict__ pc_cols, int n_pc_cols, uint32_t* __restrict__ adj_cnt,
+                                                 uint32_t* __restrict__ row_len, uint16_t* __restrict__ row_npos, int long_len,
+                                                 uint32_t* __restrict__ long_rows, CountStats* __restrict__ stats) {
+  __shared__ unsigned long long s_sum[8];
+  __shared__ unsigned s_max[8], s_used[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t v = (int64_t)blockIdx.x * 8 + w;
+  unsigned long long my_sum = 0; unsigned my_max = 0, my_used = 0;
+  if (v < nv) {
+    const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
+    const float qx = centre_of(kx, lg.res_f, lg.mnx), qy = centre_of(ky, lg.res_f, lg.mny), qz = centre_of(kz, lg.res_f, lg.mnz);
+    int cnt = 0;
+    for (int ci = lane; ci < n_adj_cols; ci += 32) {
+      const int4 o = adj_cols[ci];
+      const int x = kx + o.x, y = ky + o.y;
+      uint32_t hits = bg_run(bm_all, bg_bit(g, x, y, kz - lg.rho), 2 * lg.rho + 1) & (uint32_t)o.z;
+      const float cx = centre_of(x, lg.res_f, lg.mnx), cy = centre_of(y, lg.res_f, lg.mny);
+      while (hits) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float cz = centre_of(kz - lg.rho + j, lg.res_f, lg.mnz);
+        cnt += flann_d2(qx, qy, qz, cx, cy, cz) < lg.r2 ? 1 : 0;
+      }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    int npos = 0, nneg = 0;
+    const bool used = (uflags[v] & F_USED) != 0;
+    if (used) {
+      const int span = 2 * lg.r2c + 1;
+      for (int ci = lane; ci < n_pc_cols; ci += 32) {
+        const int4 o = pc_cols[ci];
+        npos += __popc(bg_run(bm_used, bg_bit(g, kx + o.x, ky + o.y, kz - lg.r2c), span) & (uint32_t)o.z);
+        // mirrored column: partners whose positive half contains this voxel
+        const uint32_t mm = __brev((uint32_t)o.z) >> (32 - span);
+        nneg += __popc(bg_run(bm_used, bg_bit(g, kx - o.x, ky - o.y, kz - lg.r2c), span) & mm);
+      }
+      npos = __reduce_add_sync(0xffffffffu, npos);
+      nneg = __reduce_add_sync(0xffffffffu, nneg);
+    }
+    if (lane == 0) {
+      adj_cnt[v] = (uint32_t)cnt;
+      const uint32_t len = (uint32_t)(npos + nneg);
+      row_len[v] = len;
+      row_npos[v] = (uint16_t)npos;
+      if ((int)len > long_len) long_rows[atomicAdd(&stats->n_long, 1ull)] = (uint32_t)v;
+      my_sum = used ? (unsigned long long)cnt * (unsigned long long)(cnt - 1) : 0ull;
+      my_max = (unsigned)cnt; my_used = used ? 1u : 0u;
+    }
+  }
+  if (lane == 0) { s_sum[w] = my_sum; s_max[w] = my_max; s_used[w] = my_used; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0; unsigned m = 0, us = 0;
+    for (int i = 0; i < 8; i++) { s += s_sum[i]; m = max(m, s_max[i]); us += s_used[i]; }
+    if (s) atomicAdd(&stats->sum_nn, s);
+    if (us) atomicAdd(&stats->n_used, (unsigned long long)us);
+    atomicMax(&stats->max_n, (unsigned long long)m);
+  }
+}
+
+// ---- stage 3b: ordered neighbour lists straight into the CSR.  Candidates are keyed by their stencil slot (slots are
+//      sorted by integer distance class on the host); inside a class the order is FLANN's (float dist2, id), found by a
+//      rank count over the class only — the classes are >= res^2 apart, far above the float noise of dist2 (the host
+//      passes ONE class = a full rank sort when the cloud is so far from the origin that this is not certain).
+//      adj_code = 5-bit packed offset of the neighbour (pack5), used by the graph and mutual-filter kernels. ----
+struct AdjTables {
+  const uint16_t* slot_of_code;   // ((dx+rho)*S + (dy+rho))*S + (dz+rho) -> stencil slot (0xffff = not in the stencil)
+  const uint16_t* slot_code5;     // slot -> pack5(dx+rho, dy+rho, dz+rho)
+  const uint16_t* cls_first;      // slot -> first slot of its distance class
+  const uint16_t* cls_last;       // slot -> last slot of its distance class
+};
+constexpr int ADJ_WARPS = 4;
+__host__ __device__ inline size_t adj_fill_smem(int nst) {
+  const int nst8 = (nst + 7) & ~7;
+  return (size_t)ADJ_WARPS * ((size_t)nst8 * 10 + (size_t)(nst8 / 32 + 2) * 8);
+}
+__global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __restrict__ key3, int64_t nv, LatticeGeom lg, BitGrid g,
+                                                           const uint32_t* __restrict__ bm_all, const int4* __restrict__ adj_cols,
+                                                           int n_adj_cols, AdjTables tb, int nst, const unsigned long long* __restrict__ tk,
+                                                           const uint32_t* __restrict__ tv, uint64_t hmask,
+                                                           const uint32_t* __restrict__ adj_off, int32_t* __restrict__ adj_idx,
+                                                           uint16_t* __restrict__ adj_code, unsigned* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nst8 = (nst + 7) & ~7, nblk = nst8 / 32 + 2;
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smraw) + (size_t)w * nst8;   // per slot: (d2 bits << 32) | id, ~0 = absent
+  unsigned short* q = reinterpret_cast<unsigned short*>(smraw + (size_t)ADJ_WARPS * nst8 * 8) + (size_t)w * nst8;   // hit queue
+  unsigned* sP = reinterpret_cast<unsigned*>(smraw + (size_t)ADJ_WARPS * nst8 * 10) + (size_t)w * nblk * 2;        // presence words
+  unsigned* sC = sP + nblk;                                                                                       // present slots before the word
+  const int64_t v = (int64_t)blockIdx.x * ADJ_WARPS + w;
+  if (v >= nv) return;
+  const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
+  const float qx = centre_of(kx, lg.res_f, lg.mnx), qy = centre_of(ky, lg.res_f, lg.mny), qz = centre_of(kz, lg.res_f, lg.mnz);
+  const int rho = lg.rho, S = 2 * rho + 1;
+  for (int s = lane; s < nst; s += 32) skey[s] = ~0ull;
+  int nq = 0;
+  for (int base = 0; base < n_adj_cols; base += 32) {
+    const int ci = base + lane;
+    uint32_t hits = 0;
+    int cbase = 0;
+    if (ci < n_adj_cols) {
+      const int4 o = adj_cols[ci];
+      hits = bg_run(bm_all, bg_bit(g, kx + o.x, ky + o.y, kz - rho), S) & (uint32_t)o.z;
+      cbase = ((o.x + rho) * S + (o.y + rho)) * S;
+    }
+    const int cnt = __popc(hits);
+    const int incl = (int)warp_incl_scan((unsigned)cnt, lane);
+    int pos = nq + incl - cnt;
+    while (hits) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      q[pos++] = (unsigned short)(cbase + j);
+    }
+    nq += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  for (int e = lane; e < nq; e += 32) {
+    const int c = q[e];
+    const int dz = c % S - rho, dy = (c / S) % S - rho, dx = c / (S * S) - rho;
+    const float d2 = flann_d2(qx, qy, qz, centre_of(kx + dx, lg.res_f, lg.mnx), centre_of(ky + dy, lg.res_f, lg.mny),
+                              centre_of(kz + dz, lg.res_f, lg.mnz));
+    if (!(d2 < lg.r2)) continue;
+    const int id = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+    if (id < 0) { atomicOr(err, 1u); continue; }     // grid and hash table disagree: cannot happen
+    skey[tb.slot_of_code[c]] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+  }
+  __syncwarp();
+  {   // presence words + running counts
+    unsigned run = 0;
+    for (int s0 = 0; s0 < nst; s0 += 32) {
+      const int s = s0 + lane;
+      const uint32_t bal = __ballot_sync(0xffffffffu, s < nst && skey[s] != ~0ull);
+      if (lane == 0) { sP[s0 >> 5] = bal; sC[s0 >> 5] = run; }
+      run += __popc(bal);
+    }
+  }
+  __syncwarp();
+  const uint32_t off = adj_off[v];
+  const uint32_t total = adj_off[v + 1] - off;
+  for (int s = lane; s < nst; s += 32) {
+    const unsigned long long me = skey[s];
+    if (me == ~0ull) continue;
+    const int f = tb.cls_first[s], l = tb.cls_last[s];
+    int rank = 0;
+    for (int t = f; t <= l; t++) rank += skey[t] < me ? 1 : 0;     // absent slots hold ~0: never smaller
+    const uint32_t p = sC[f >> 5] + __popc(sP[f >> 5] & ((1u << (f & 31)) - 1u)) + (uint32_t)rank;
+    if (p < total) {
+      adj_idx[off + p] = (int32_t)(unsigned)(me & 0xffffffffull);
+      adj_code[off + p] = tb.slot_code5[s];
+    } else atomicOr(err, 2u);                       // count and fill disagree: cannot happen
+  }
+}
+
+// ---- stage 4: weight rows.  Entry = (float weight, cell << 18 | pack6(d + r2c)): the directed weight w(a -> b) lives in
+//      the row of a, keyed by the lattice offset d = key_b - key_a.  cell = floor((1 - w) * 1024) orders a row coarsely
+//      (k_rows_sort); the consumer sorts exactly inside the cells it takes. ----
+constexpr int ROW_CELLS = 1024;
+constexpr int ROWS_SHORT_CAP = 512;   // rows up to this length are sorted four per CTA; longer ones one per CTA
+__host__ __device__ __forceinline__ uint32_t row_cell(float w) {
+  // monotone non-increasing in w; NaN and w <= 0 fall into the last cell
+  if (!(w > 0.f)) return ROW_CELLS - 1;
+  const int q = (int)((1.0f - w) * (float)ROW_CELLS);
+  return q < 0 ? 0u : (q > ROW_CELLS - 1 ? (uint32_t)(ROW_CELLS - 1) : (uint32_t)q);
+}
+// every weight of a cell >= c is <= this bound (1 - w is exact for w >= 0.5, else off by <= 2^-25; the slack covers it)
+__device__ __forceinline__ float row_cell_upper(int c) { return (1.0f - (float)c * (1.0f / (float)ROW_CELLS)) + 1.2e-7f; }
+
+// cursor[v] = first free slot of the incoming (negative-half) part of row v
+__global__ void __launch_bounds__(256) k_rows_cursor(const uint32_t* __restrict__ row_off, const uint16_t* __restrict__ row_npos, int64_t nv,
+                                                   uint32_t* __restrict__ cursor) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv) cursor[v] = row_off[v] + row_npos[v];
+}
+
+constexpr int RF_QCAP = 32 + 32 * 32;   // a lane queues at most one z-run (<= 32 hits) per column step
+__global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
+                                                 BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
+                                                 const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv, uint64_t hmask,
+                                                 PairParams pp, const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ row_off,
+                                                 uint32_t* __restrict__ cursor, uint2* __restrict__ rows, unsigned* __restrict__ err) {
+  __shared__ unsigned short pend[4][RF_QCAP];
+  __shared__ float s_ra[4][REC_FLOATS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t v = (int64_t)blockIdx.x * 4 + w;
+  if (v >= nv) return;
+  if (!(uflags[v] & F_USED)) return;
+  if (lane < REC_FLOATS) s_ra[w][lane] = rec[v * REC_FLOATS + lane];
+  __syncwarp();
+  const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
+  const int r2 = lg.r2c, S = 2 * r2 + 1;
+  const uint32_t my_row = row_off[v];
+  int npend = 0, done = 0;
+  auto process = [&](int first, int cnt) {
+    if (lane < cnt) {
+      const int c = pend[w][first + lane];              // ((dx+r2)*S + (dy+r2))*S + (dz+r2)
+      const int dz = c % S - r2, dy = (c / S) % S - r2, dx = c / (S * S) - r2;
+      const int b = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+      if (b < 0) { atomicOr(err, 4u); }
+      else {
+        float rb[REC_FLOATS];
+        const float4* src = reinterpret_cast<const float4*>(rec + (int64_t)b * REC_FLOATS);
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) { float4 t = __ldg(src + qd); rb[4 * qd] = t.x; rb[4 * qd + 1] = t.y; rb[4 * qd + 2] = t.z; rb[4 * qd + 3] = t.w; }
+        float w_ab, w_ba;
+        pair_weights(s_ra[w], rb, pp, w_ab, w_ba);
+        rows[my_row + done + lane] = make_uint2(__float_as_uint(w_ab), (row_cell(w_ab) << 18) | pack6(dx + r2, dy + r2, dz + r2));
+        const uint32_t slot = atomicAdd(&cursor[b], 1u);
+        rows[slot] = make_uint2(__float_as_uint(w_ba), (row_cell(w_ba) << 18) | pack6(r2 - dx, r2 - dy, r2 - dz));
+      }
+    }
+    done += cnt;
+  };
+  for (int base = 0; base < n_pc_cols; base += 32) {
+    const int ci = base + lane;
+    uint32_t hits = 0;
+    int cbase = 0;
+    if (ci < n_pc_cols) {
+      const int4 o = pc_cols[ci];
+      hits = bg_run(bm_used, bg_bit(g, kx + o.x, ky + o.y, kz - r2), S) & (uint32_t)o.z;
+      cbase = ((o.x + r2) * S + (o.y + r2)) * S;
+    }
+    const int cnt = __popc(hits);
+    const int incl = (int)warp_incl_scan((unsigned)cnt, lane);
+    int pos = npend + incl - cnt;
+    while (hits) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      pend[w][pos++] = (unsigned short)(cbase + j);
+    }
+    npend += __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    while (npend >= 32) { process(npend - 32, 32); npend -= 32; }
+    __syncwarp();
+  }
+  process(0, npend);
+}
+
+// ---- rows ordered by weight cell: LSD radix sort (2 passes x 5 bits) of one row per warp in shared memory ----
+constexpr int RS2_WARPS = 4;
+__global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __restrict__ row_off, int64_t nv, const uint32_t* __restrict__ list,
+                                                            uint32_t nlist, int cap, uint2* __restrict__ rows) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint2* A = reinterpret_cast<uint2*>(smraw) + (size_t)w * 2 * cap;
+  uint2* B = A + cap;
+  __shared__ unsigned s_cnt[RS2_WARPS][32];
+  int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  if (list) { if (v >= (int64_t)nlist) return; v = list[v]; }
+  else if (v >= nv) return;
+  const uint32_t off = row_off[v];
+  const int len = (int)(row_off[v + 1] - off);
+  if (len <= 1 || len > cap) return;          // longer rows are sorted by the launch over the long-row list
+  for (int i = lane; i < len; i += 32) A[i] = rows[off + i];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const int shift = 18 + 5 * pass;
+    s_cnt[w][lane] = 0;
+    __syncwarp();
+    for (int i0 = 0; i0 < len; i0 += 32) {
+      const int i = i0 + lane;
+      const unsigned d = i < len ? ((A[i].y >> shift) & 31u) : 0xffffu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
+      __syncwarp();
+    }
+    const unsigned c = s_cnt[w][lane];
+    const unsigned inc = warp_incl_scan(c, lane);
+    __syncwarp();
+    s_cnt[w][lane] = inc - c;
+    __syncwarp();
+    for (int i0 = 0; i0 < len; i0 += 32) {
+      const int i = i0 + lane;
+      uint2 e = make_uint2(0, 0);
+      unsigned d = 0xffffu;
+      if (i < len) { e = A[i]; d = (e.y >> shift) & 31u; }
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      unsigned pos = 0;
+      if (i < len) pos = s_cnt[w][d] + __popc(peers & lt);
+      __syncwarp();
+      if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
+      if (i < len) B[pos] = e;
+      __syncwarp();
+    }
+    uint2* t = A; A = B; B = t;
+  }
+  for (int i = lane; i < len; i += 32) rows[off + i] = A[i];
+}
+
+// ---- stage 5a: cutGraphSegmentation (VS.h:1913-2029) of one voxel per warp from the weight rows.
+//      The reference sorts all n^2 weights of the neighbourhood; the merge loop only ever acts on an entry whose two
+//      vertices lie in different segments, and the emitted segment (that of local vertex 0) is final once the next
+//      weight is <= thr(S0) = Int(S0) - k/|S0| (S0 rule, exact).  Here the warp walks the rows of its used neighbours
+//      in rounds of descending weight cells [c0, c1): an entry of row j is w(j -> partner at lattice offset d); it
+//      belongs to this local graph iff the partner lies inside the neighbourhood (offset table lookup), and it is staged
+//      iff the two vertices are in different segments.  Staged entries are sorted exactly (w desc, flat index asc) and
+//      merged like the reference does; the round size adapts to the number of staged entries.
+//      Output: lattice-offset bit mask of the connect list (+ its size); units this kernel cannot handle (staging
+//      overflow inside one cell) go to the fallback list of the general kernel. ----
+constexpr int LR_WARPS = 4;
+constexpr int LR_NCAP = 184;     // used neighbours of one voxel (MAX_NEIGH = 181)
+constexpr int LR_CS = 256;       // staging capacity (entries)
+constexpr int LR_TARGET = 28;    // staged entries aimed at per round (<= 32: sorted in registers)
+__host__ __device__ inline size_t lr_slice_bytes(int lbits, int mwords) {
+  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_mask (4 B) | C_f, s_nc (2 B) | s_seg, s_size, s_loc (1 B)
+  size_t b = (size_t)LR_CS * 4 + (size_t)LR_NCAP * 4 * 5 + (size_t)mwords * 4 + (size_t)LR_CS * 2 + (size_t)LR_NCAP * 2 +
+             (size_t)LR_NCAP * 2 + ((size_t)1 << (3 * lbits));
+  return (b + 15) & ~(size_t)15;
+}
+__global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
+                                                                     const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
+                                                                     const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords,
+                                                                     const uint32_t* __restrict__ row_off, const uint2* __restrict__ rows,
+                                                                     const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
+                                                                     uint32_t* __restrict__ conn_mask, uint32_t* __restrict__ fallback,
+                                                                     uint32_t* __restrict__ fallback_count, int force_fb_mod,
+                                                                     unsigned long long* __restrict__ dbg) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t u = first + (int64_t)blockIdx.x * LR_WARPS + wq;
+  if (u >= last) return;
+  unsigned char* base = smraw + (size_t)wq * lr_slice_bytes(lbits, mwords);
+  float* C_w = reinterpret_cast<float*>(base);                          // LR_CS
+  float* s_thr = C_w + LR_CS;                                           // NCAP: Int(C) - k/|C| of segment C
+  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_thr + LR_NCAP);      // NCAP: pack6(o + rho) of the vertex
+  uint32_t* s_cur = s_off6 + LR_NCAP;                                   // NCAP: next unread entry of the vertex's row
+  uint32_t* s_end = s_cur + LR_NCAP;                                    // NCAP
+  uint32_t* s_sav = s_end + LR_NCAP;                                    // NCAP: cursors at the start of the round
+  uint32_t* s_mask = s_sav + LR_NCAP;                                   // mwords: output mask
+  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_mask + mwords);   // LR_CS
+  unsigned short* s_nc = C_f + LR_CS;                                   // NCAP: cell of the next unread entry (ROW_CELLS = exhausted)
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_nc + LR_NCAP);    // NCAP
+  unsigned char* s_size = s_seg + LR_NCAP;                              // NCAP
+  unsigned char* s_loc = s_size + LR_NCAP;                              // 1 << 3*lbits: lattice offset -> local vertex, 0xff = none
+  __shared__ int s_cnt[LR_WARPS];
+  const uint32_t lt = (1u << lane) - 1u;
+  const int nloc = 1 << (3 * lbits);
+  const uint32_t lmask = (1u << lbits) - 1u;
+  const int S1 = 2 * rho + 1;
+
+  for (int i = lane; i < mwords; i += 32) s_mask[i] = 0;
+  if (!(uflags[u] & F_USED)) {          // unused voxels have empty connect lists (VS.h:403-409)
+    for (int i = lane; i < mwords; i += 32) conn_mask[(size_t)u * mwords + i] = 0;
+    if (lane == 0) conn_cnt[u] = 0;
+    return;
+  }
+  for (int i = lane; i < nloc / 4; i += 32) reinterpret_cast<uint32_t*>(s_loc)[i] = 0xffffffffu;
+  __syncwarp();
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off);
+  int nv = 0;
+  // vertex table of the USED neighbours in adjacency order (local vertex 0 = the voxel itself); unused voxels cannot
+  // merge (their weight is w_empty <= cut bound, else the unit goes to the general kernel), and the tie-break order
+  // (col * n + row over all neighbours, VS.h:1922) is preserved by the monotone renumbering
+  for (int b0 = 0; b0 < n; b0 += 32) {
+    const int i = b0 + lane;
+    bool us = false;
+    int64_t gq = 0;
+    uint32_t c5 = 0;
+    if (i < n) {
+      gq = adj_idx[off + i];
+      c5 = adj_code[off + i];
+      us = (__ldg(uflags + gq) & F_USED) != 0;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, us);
+    if (us) {
+      const int j = nv + __popc(bal & lt);
+      if (j < LR_NCAP) {
+        const uint32_t ox = c5 & 31u, oy = (c5 >> 5) & 31u, oz = (c5 >> 10) & 31u;
+        s_off6[j] = pack6((int)ox, (int)oy, (int)oz);
+        s_loc[ox | (oy << lbits) | (oz << (2 * lbits))] = (unsigned char)j;
+        const uint32_t r0 = __ldg(row_off + gq), r1 = __ldg(row_off + gq + 1);
+        s_cur[j] = r0; s_end[j] = r1;
+        s_nc[j] = r0 < r1 ? (unsigned short)(__ldg(&rows[r0].y) >> 18) : (unsigned short)ROW_CELLS;
+        s_seg[j] = (unsigned char)j; s_size[j] = 1; s_thr[j] = 1.0f - k / 1.0f;
+      }
+    }
+    nv += __popc(bal);
+  }
+  __syncwarp();
+  const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
+  bool to_fallback = (wempty[0] > lb) || nv > LR_NCAP;     // empty pairs could merge / too many vertices: general kernel
+  if (force_fb_mod > 0 && (u % force_fb_mod) == 0) to_fallback = true;   // test knob VGS_B200_FORCE_FALLBACK
+  int nseg = nv;
+  bool stop = false;
+  auto merge_batch = [&](float w, int f, bool valid) {
+    const int v1 = f >> 8, v2 = f & 255;
+    uint32_t todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+      bool pred = false, a_wins = true;
+      int sa = 0, sb = 0;
+      if ((todo >> lane) & 1u) {
+        sa = s_seg[v1]; sb = s_seg[v2];
+        if (sa != sb) {
+          const float m1 = s_thr[sa], m2 = s_thr[sb];
+          a_wins = (m1 >= m2);
+          pred = w > (a_wins ? m1 : m2);
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+      if (!bal) break;
+      const int Lm = __ffs(bal) - 1;
+      const int keepl = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
+      const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
+      const float wl = __shfl_sync(0xffffffffu, w, Lm);
+      for (int v = lane; v < nv; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
+      if (lane == 0) {
+        const int nsz = (int)s_size[keepl] + (int)s_size[drop];
+        s_thr[keepl] = wl - k / (float)nsz; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
+      }
+      nseg--;
+      __syncwarp();
+      todo &= ~((2u << Lm) - 1u);
+      if (nseg <= 1) { stop = true; break; }
+    }
+  };
+  if (!to_fallback && nv > 1) {
+    // field-parallel range test of pack6(o_j + rho) + pack6(d + 2 rho) = pack6(p + 3 rho): p inside the neighbourhood
+    // cube iff every field lies in [2 rho, 4 rho]
+    const uint32_t G = 0x20820u, ONES = 0x1041u;
+    const uint32_t add_hi = (uint32_t)(31 - 4 * rho) * ONES, sub_lo = (uint32_t)(2 * rho) * ONES;
+    int c0 = ROW_CELLS;
+    for (int j = lane; j < nv; j += 32) c0 = min(c0, (int)s_nc[j]);
+    c0 = __reduce_min_sync(0xffffffffu, c0);
+    int span = 4;
+    while (!stop && c0 < ROW_CELLS) {
+      // S0 rule on the cell bound: every unread entry has a weight <= row_cell_upper(c0)
+      if (!(row_cell_upper(c0) > s_thr[s_seg[0]])) break;
+      const int c1 = min(ROW_CELLS, c0 + span);
+      if (lane == 0) s_cnt[wq] = 0;
+      __syncwarp();
+      int cmin = ROW_CELLS;
+      for (int j = lane; j < nv; j += 32) {
+        int nc = (int)s_nc[j];
+        uint32_t c = s_cur[j];
+        s_sav[j] = c;
+        if (nc >= c1) { cmin = min(cmin, nc); continue; }
+        const uint32_t e = s_end[j];
+        const uint32_t oj = s_off6[j];
+        const int sj = s_seg[j];
+        while (true) {
+          const uint2 en = __ldg(&rows[c]);
+          if ((int)(en.y >> 18) >= c1) { nc = (int)(en.y >> 18); break; }
+          c++;
+          const uint32_t sum = oj + (en.y & 0x3ffffu);
+          const bool inside = (((sum + add_hi) & G) == 0u) && ((((sum | G) - sub_lo) & G) == G);
+          if (inside) {
+            const uint32_t p = sum - sub_lo;
+            const int i = s_loc[(p & lmask) | (((p >> 6) & lmask) << lbits) | (((p >> 12) & lmask) << (2 * lbits))];
+            if (i != 0xff && s_seg[i] != sj) {
+              const int slot = atomicAdd(&s_cnt[wq], 1);
+              // entry (row j, col i) = weight(idx[j] -> idx[i]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
+              if (slot < LR_CS) { C_w[slot] = __uint_as_float(en.x); C_f[slot] = (unsigned short)((i << 8) | j); }
+            }
+          }
+          if (c >= e) { nc = ROW_CELLS; break; }
+        }
+        s_cur[j] = c;
+        s_nc[j] = (unsigned short)nc;
+        cmin = min(cmin, nc);
+      }
+      __syncwarp();
+      const int kept = s_cnt[wq];
+      if (kept > LR_CS) {
+        if (span == 1) { to_fallback = true; break; }       // one cell alone overflows the staging buffer
+        // roll the cursors back and retry with a narrower round
+        for (int j = lane; j < nv; j += 32) {
+          const uint32_t sv = s_sav[j];
+          if (s_cur[j] != sv) { s_cur[j] = sv; s_nc[j] = (unsigned short)(__ldg(&rows[sv].y) >> 18); }
+        }
+        __syncwarp();
+        span = max(1, span / 4);
+        continue;
+      }
+      if (dbg && lane == 0) { atomicAdd(&dbg[0], 1ull); atomicAdd(&dbg[2], (unsigned long long)kept); }
+      if (kept > 0) {
+        if (kept <= 32) {
+          float rw = lane < kept ? C_w[lane] : -1.0f;
+          int rf = lane < kept ? (int)C_f[lane] : 0xffff;
+#pragma unroll
+          for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+              const float wo = __shfl_xor_sync(0xffffffffu, rw, jj);
+              const int fo = __shfl_xor_sync(0xffffffffu, rf, jj);
+              const bool other_first = (wo > rw) || (wo == rw && fo < rf);
+              const bool up = (lane & kk) == 0, lower = (lane & jj) == 0;
+              if ((up == lower) ? other_first : !other_first) { rw = wo; rf = fo; }
+            }
+          }
+          merge_batch(rw, rf, lane < kept);
+        } else {
+          int P = 64;
+          while (P < kept) P <<= 1;
+          for (int i = kept + lane; i < P; i += 32) { C_w[i] = -1.0f; C_f[i] = 0xffff; }
+          __syncwarp();
+          for (int kk = 2; kk <= P; kk <<= 1) {
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+              for (int i = lane; i < P; i += 32) {
+                const int x = i ^ jj;
+                if (x > i) {
+                  const float wi = C_w[i], wx = C_w[x];
+                  const unsigned short fi = C_f[i], fx = C_f[x];
+                  const bool x_before_i = (wx > wi) || (wx == wi && fx < fi);
+                  const bool up = (i & kk) == 0;
+                  if (x_before_i == up) { C_w[i] = wx; C_w[x] = wi; C_f[i] = fx; C_f[x] = fi; }
+                }
+              }
+              __syncwarp();
+            }
+          }
+          for (int bs = 0; bs < kept && !stop; bs += 32) {
+            const int e = bs + lane;
+            const bool valid = e < kept;
+            merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
+          }
+        }
+      }
+      // next round: first cell that still holds an unread entry; size adapted to the yield of this one
+      c0 = __reduce_min_sync(0xffffffffu, cmin);
+      span = min(256, max(1, (span * (LR_TARGET + 4)) / (kept + 4)));
+    }
+    if (dbg && lane == 0) { atomicAdd(&dbg[3], 1ull); atomicAdd(&dbg[5], (unsigned long long)nseg); atomicAdd(&dbg[6], (unsigned long long)nv); }
+  }
+  if (to_fallback) {
+    if (lane == 0) fallback[atomicAdd(fallback_count, 1u)] = (uint32_t)u;
+    return;
+  }
+  // --- emit the segment that contains local vertex 0 (the voxel itself) as a lattice-offset mask ---
+  __syncwarp();
+  const int s0 = s_seg[0];
+  int cnt = 0;
+  for (int b = 0; b < nv; b += 32) {
+    const int v = b + lane;
+    const bool in = v < nv && s_seg[v] == s0;
+    if (in) {
+      const uint32_t o6 = s_off6[v];
+      const int lin = ((int)(o6 & 63u) * S1 + (int)((o6 >> 6) & 63u)) * S1 + (int)((o6 >> 12) & 63u);
+      atomicOr(&s_mask[lin >> 5], 1u << (lin & 31));
+    }
+    cnt += __popc(__ballot_sync(0xffffffffu, in));
+  }
+  __syncwarp();
+  for (int i = lane; i < mwords; i += 32) conn_mask[(size_t)u * mwords + i] = s_mask[i];
+  if (lane == 0) conn_cnt[u] = (uint32_t)cnt;
+}
+
+// general-kernel results (connect LIST at the adjacency offsets) -> lattice mask, for the units of the fallback list
+__global__ void __launch_bounds__(128) k_conn_list_to_mask(const uint32_t* __restrict__ list, uint32_t nlist, const uint32_t* __restrict__ adj_off,
+                                                         const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
+                                                         const uint32_t* __restrict__ conn_cnt, const int32_t* __restrict__ conn_idx, int rho,
+                                                         int mwords, uint32_t* __restrict__ conn_mask) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (li >= nlist) return;
+  const uint32_t u = list[li];
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off), c = (int)conn_cnt[u];
+  const int S1 = 2 * rho + 1;
+  for (int i = lane; i < mwords; i += 32) conn_mask[(size_t)u * mwords + i] = 0;
+  __syncwarp();
+  // both lists are in adjacency order: walk them together
+  for (int e = lane; e < n; e += 32) {
+    const int g = adj_idx[off + e];
+    bool in = false;
+    for (int t = 0; t < c; t++) if (conn_idx[off + t] == g) { in = true; break; }
+    if (in) {
+      const uint32_t c5 = adj_code[off + e];
+      const int lin = ((int)(c5 & 31u) * S1 + (int)((c5 >> 5) & 31u)) * S1 + (int)((c5 >> 10) & 31u);
+      atomicOr(&conn_mask[(size_t)u * mwords + (lin >> 5)], 1u << (lin & 31));
+    }
+  }
+}
+
+// lattice mask -> connect list at the adjacency offsets, adjacency order (debug blobs / SVGS-style consumers)
+__global__ void __launch_bounds__(128) k_conn_mask_to_list(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
+                                                         const uint16_t* __restrict__ adj_code, int64_t nu, int rho, int mwords,
+                                                         const uint32_t* __restrict__ conn_mask, int32_t* __restrict__ conn_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= nu) return;
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off);
+  const int S1 = 2 * rho + 1;
+  int kept = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    bool in = false;
+    int g = -1;
+    if (e < n) {
+      g = adj_idx[off + e];
+      const uint32_t c5 = adj_code[off + e];
+      const int lin = ((int)(c5 & 31u) * S1 + (int)((c5 >> 5) & 31u)) * S1 + (int)((c5 >> 10) & 31u);
+      in = (conn_mask[(size_t)u * mwords + (lin >> 5)] >> (lin & 31)) & 1u;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    if (in) conn_idx[off + kept + __popc(bal & ((1u << lane) - 1u))] = g;
+    kept += __popc(bal);
+  }
+}
+
+// ---- stage 5b: crossValidation (VS.h:2111-2179) on the masks: j stays in L[i] iff i is in L[j], i.e. iff the bit of the
+//      mirrored offset is set in the mask of j.  Lists of size <= 1 are left as they are.  One warp per voxel. ----
+__global__ void __launch_bounds__(128) k_mutual_mask(const uint32_t* __restrict__ adj_off, const int32_t* __restrict__ adj_idx,
+                                                   const uint16_t* __restrict__ adj_code, const uint32_t* __restrict__ cnt0,
+                                                   const uint32_t* __restrict__ mask0, int64_t nu, int rho, int mwords,
+                                                   uint32_t* __restrict__ cnt1, int32_t* __restrict__ idx1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= nu) return;
+  const int c = (int)cnt0[u];
+  if (c == 0) { if (lane == 0) cnt1[u] = 0; return; }
+  const uint32_t off = adj_off[u];
+  const int n = (int)(adj_off[u + 1] - off);
+  const int S1 = 2 * rho + 1, top = S1 * S1 * S1 - 1;
+  int kept = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    bool keep = false;
+    int j = -1;
+    if (e < n) {
+      j = adj_idx[off + e];
+      const uint32_t c5 = adj_code[off + e];
+      const int lin = ((int)(c5 & 31u) * S1 + (int)((c5 >> 5) & 31u)) * S1 + (int)((c5 >> 10) & 31u);
+      if ((mask0[(size_t)u * mwords + (lin >> 5)] >> (lin & 31)) & 1u) {
+        if (c <= 1) keep = true;
+        else {
+          const int ml = top - lin;                    // offset of u seen from j
+          keep = (__ldg(&mask0[(size_t)j * mwords + (ml >> 5)]) >> (ml & 31)) & 1u;
+        }
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) idx1[off + kept + __popc(bal & ((1u << lane) - 1u))] = j;
+    kept += __popc(bal);
+  }
+  if (lane == 0) cnt1[u] = (uint32_t)kept;
+}
+
+}  // namespace vgs
