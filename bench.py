@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py — points/sec segmented end-to-end (BASELINE.json metric) on N B200s of one node.
 
-A "step" = one full VGS segmentation (voxelise -> features -> adjacency -> local graphs ->
-mutual filter -> closest check -> components -> per-point labels) of one synthetic
-construction-site scene (BASELINE.json configs[2]: 10 M points, Task_File_VGS.txt parameters).
+A "step" = one full segmentation of one synthetic scene through the C ABI of libvgs_b200.so:
+  VGS : voxelise -> features -> adjacency -> weight rows -> local graphs -> mutual filter -> closest check -> components
+        -> per-point labels (Task_File_VGS.txt parameters)
+  SVGS: voxelise -> VCCS supervoxels (CUDA generator) -> the same pipeline on supervoxels (Task_File_SVGS.txt parameters)
 
-  value : whole-job points/s with the point cloud already resident in HBM (device pointer in,
-          device labels out), CUDA-event timed per step, L2 flushed between steps.
-  e2e   : the same through the host-buffer C-ABI call (pinned host xyz in, host labels out,
-          H2D + D2H inside the timed region).
-  roofline : the dominant stage (local graph kernels), algorithmic bytes / event time / measured HBM peak.
-  cpu_baseline : the CPU oracle (single thread, like the reference) on a bounded sample.
+  --config site10m (default) : BASELINE.json configs[2], 10 M-point construction site, VGS           [the headline line]
+           town2m            : configs[0] stand-in (Town_Test.pcd is not distributed), 2 M points, VGS
+           town2m_svgs       : configs[1] stand-in, 2 M points, SVGS
+           urban100m         : configs[3], 100 M-point urban scene, VGS (one GPU: fits in 180 GB)
 
-`--impl reference` times the CPU restatement of the reference (oracle, glibc libm) instead.
-Multi-GPU (torchrun): every rank segments its own tile of the site grid (weak scaling), no
-data-path collective inside the timed region except the barrier; max over ranks.
+  value    : whole-job points/s, point cloud already resident in HBM (device pointer in, device labels out), CUDA events
+             around every step on the launching stream, a 512 MB buffer written between steps (L2 flush).
+  e2e      : the same through the host-buffer call (pinned host xyz in, host labels out; H2D + D2H inside the timed region).
+  roofline : the kernel group with the largest share of the step; `kernels` lists every group (CUDA-event time measured
+             live inside the library, algorithmic bytes from vgs_kernel_timings, fraction of the measured HBM peak).
+  cpu_baseline : the CPU oracle, single thread (as the reference runs), on a bounded sample of the same workload.
+
+`--impl reference` times the CPU restatement of the reference (the oracle; the reference itself cannot be compiled here)
+on the SAME scene with all host threads, and checks its labels against one run of the CUDA path when a GPU is present.
+
+N > 1 (torchrun, one rank per GPU): `--mode slabs` (default for VGS) segments ONE scene split into spatial slabs with halo
+voxels, cross-slab component merge over NCCL (strong scaling); `--mode replicas` runs one independent tile per rank.
 """
 from __future__ import annotations
 
@@ -31,7 +39,22 @@ sys.path.insert(0, ROOT)
 
 VGS_PARAMS = dict(voxel_size=0.15, graph_size=0.5, sig_p=0.2, sig_n=0.2, sig_o=0.2, sig_e=0.2, sig_c=0.2, sig_w=2.0,
                   cut_thred=0.3, points_min=10, adjacency_min=3, voxels_min=3)
+SVGS_PARAMS = dict(voxel_size=0.05, graph_size=0.5, sig_p=0.2, sig_n=0.2, sig_o=0.2, sig_e=0.2, sig_c=0.75, sig_w=1.0,
+                   cut_thred=0.5, points_min=10, adjacency_min=3, voxels_min=3)
+VCCS = dict(seed_resolution=0.25, color_importance=0.0, spatial_importance=0.25, normal_importance=0.75, refine_iterations=5)
 HBM_FALLBACK_GBS = 6650.0
+
+CONFIGS = {
+    "site10m": dict(scene="construction_site", points=10_000_000, mode=0,
+                    what="VGS, synthetic construction-site scene (BASELINE.json configs[2]), Task_File_VGS.txt parameters"),
+    "town2m": dict(scene="town", points=2_000_000, mode=0,
+                   what="VGS, synthetic town scene standing in for Town_Test.pcd (configs[0]), Task_File_VGS.txt parameters"),
+    "town2m_svgs": dict(scene="town", points=2_000_000, mode=1,
+                        what="SVGS, synthetic town scene standing in for Town_Test.pcd (configs[1]), Task_File_SVGS.txt parameters, "
+                             "supervoxels by the CUDA VCCS generator inside the step"),
+    "urban100m": dict(scene="urban", points=100_000_000, mode=0,
+                      what="VGS, synthetic Semantic3D-scale urban scene (configs[3]), Task_File_VGS.txt parameters"),
+}
 
 
 def measured_peak():
@@ -108,57 +131,111 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_scene(n_points, rank):
+def make_scene(cfg, n_points=None, tile=0):
+    """the config's scene at n_points (default: its full size); extents scale with sqrt(points) so the density stays that of
+    the full scene; tile > 0 shifts a replica (its own seed) by 80 m in x"""
     from vgs_svgs_segmentation_b200 import scenes
-    # each rank = one 70 m tile of a site grid (tile origin shifted by 80 m in x), own seed
-    extent = 70.0 * (n_points / 10_000_000) ** 0.5
-    return scenes.construction_site(n_points, seed=1 + rank, extent=extent, offset=(80.0 * rank, 0.0, 0.0))
+    c = CONFIGS[cfg]
+    n = int(n_points or c["points"])
+    if c["scene"] == "construction_site":
+        return scenes.construction_site(n, seed=1 + tile, extent=70.0 * (n / 10_000_000) ** 0.5, offset=(80.0 * tile, 0.0, 0.0))
+    if c["scene"] == "town":
+        return scenes.town(n, seed=20170610 + tile, extent=60.0 * (n / 2_000_000) ** 0.5, offset=(80.0 * tile, 0.0, 0.0))
+    return scenes.urban(n, seed=2 + tile, extent=320.0 * (n / 100_000_000) ** 0.5, offset=(400.0 * tile, 0.0, 0.0))
 
 
-def cpu_baseline(sample_points, math=0, threads=1):
-    """threads = 1: as the reference runs (it has no threading); threads > 1: the per-unit local-graph loop of the oracle
-    (the dominant cost) over OpenMP threads, same results"""
+def params_of(cfg):
+    return dict(SVGS_PARAMS if CONFIGS[cfg]["mode"] == 1 else VGS_PARAMS)
+
+
+def oracle_run(cfg, pts, threads, math):
+    """the CPU restatement on `pts`; SVGS: supervoxel labels by the oracle's own VCCS restatement (synchronous schedule)"""
     from oracle import oracle
-    pts = make_scene(sample_points, 0)
+    pd = params_of(cfg)
     cores = oracle.set_threads(threads)
     t0 = time.perf_counter()
-    r = oracle.run(pts, math=math)
-    dt = time.perf_counter() - t0
-    oracle.set_threads(1)
-    how = "single thread, as the reference runs" if cores == 1 else f"{cores} OpenMP threads on the per-unit local-graph loop"
+    try:
+        if CONFIGS[cfg]["mode"] == 1:
+            v = oracle.vccs(pts, voxel_res=pd["voxel_size"], seed_res=VCCS["seed_resolution"], color_importance=VCCS["color_importance"],
+                            spatial_importance=VCCS["spatial_importance"], normal_importance=VCCS["normal_importance"],
+                            refine_iterations=VCCS["refine_iterations"], schedule=1)
+            r = oracle.run(pts, labels=v.point_label, max_label=v.max_label, mode=1, math=math, **pd)
+        else:
+            r = oracle.run(pts, math=math, **pd)
+    finally:
+        oracle.set_threads(1)
+    return r, time.perf_counter() - t0, cores
+
+
+def cpu_baseline(cfg, sample_points):
+    """single thread, as the reference runs (it has no threading), on a bounded sample of the workload"""
+    pts = make_scene(cfg, sample_points)
+    r, dt, cores = oracle_run(cfg, pts, 1, 0)
     return {"value": sample_points / dt, "unit": "points/s", "cores": cores, "kind": "port",
-            "sample": f"construction_site {sample_points} points (same density as the workload), CPU oracle, {how}, "
-                      f"{dt:.2f} s, {r.stats['pair_evals']} pair evaluations"}, pts, r
+            "sample": f"{CONFIGS[cfg]['scene']} scene cut down to {sample_points} points at the density of the workload, CPU oracle "
+                      f"(glibc libm), single thread as the reference runs, {dt:.2f} s, {r.stats['pair_evals']} pair evaluations"}
+
+
+def gpu_step(h, capi, cfg, pd, labels_ptr_or_array, on_device):
+    """one full segmentation on handle h (points already set) through the C-ABI calls"""
+    if CONFIGS[cfg]["mode"] == 0:
+        h.run(capi.make_params(**pd), labels_ptr_or_array, on_device=on_device)
+        return
+    h.voxelize(pd["voxel_size"])
+    h.make_supervoxels_vccs(**VCCS)
+    h.compute_features(pd["points_min"])
+    h.find_adjacency(pd["graph_size"])
+    h.segment(capi.Sigmas(pd["sig_p"], pd["sig_n"], pd["sig_o"], pd["sig_e"], pd["sig_c"], pd["sig_w"]), pd["cut_thred"], pd["adjacency_min"])
+    ptr = labels_ptr_or_array if isinstance(labels_ptr_or_array, int) else labels_ptr_or_array.ctypes.data
+    h._ck(h.L.vgs_get_point_labels(h.h, pd["voxels_min"], capi.C.c_void_p(ptr), 1 if on_device else 0))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = args.steps, args.warmup
+    import numpy as np
+    import __graft_entry__ as g
+    g.build(oracle=True, quiet=True)
+    cfg = args.config
+    threads = os.cpu_count() or 1          # "all the host threads it can use"; the reference itself is single-threaded
+    pts = make_scene(cfg, args.ref_points or None)
+    n = pts.shape[0]
     per = []
-    info = None
-    threads = os.cpu_count() or 1       # "all the host threads it can use"; the reference itself is single-threaded
-    for i in range(warm + steps):
-        info, _, _ = cpu_baseline(args.ref_points, math=0, threads=threads)
+    r = None
+    warm = min(args.warmup, 1)             # every step is tens of seconds of CPU work: one warm-up pass is plenty
+    for i in range(warm + args.steps):
+        r, dt, cores = oracle_run(cfg, pts, threads, 1)
         if i >= warm:
-            per.append(args.ref_points / info["value"])
+            per.append(dt)
     ms = 1e3 * sum(per) / len(per)
-    val = args.ref_points / (ms / 1e3)
-    info["value"] = val
+    val = n / (ms / 1e3)
+    parity = None
+    try:      # the CPU labels against one run of the CUDA path on the same scene (when a GPU is here)
+        import torch
+        if torch.cuda.is_available() and CONFIGS[cfg]["mode"] == 0:
+            from vgs_svgs_segmentation_b200 import capi
+            h = capi.Handle(mode=0, device=0)
+            h.set_points(pts)
+            lab = h.run(capi.make_params(**params_of(cfg)))
+            h.close()
+            parity = {"labels_equal": bool(np.array_equal(lab, r.point_label)), "points": int(n),
+                      "near_threshold_decisions": int(r.stats["near_threshold"])}
+    except Exception as e:   # noqa: BLE001
+        parity = {"error": str(e)[:200]}
+    info = {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": f"the full {CONFIGS[cfg]['scene']} scene of the config ({n} points) per step, CPU oracle with correctly rounded libm "
+                      f"(the definition the CUDA path is compared with), per-unit local-graph loop on {cores} OpenMP threads"}
     print(json.dumps({
         "impl": "reference", "metric": "points/sec segmented end-to-end", "value": val, "unit": "points/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"VGS, synthetic construction-site scene {args.points} points per GPU (BASELINE.json configs[2]), "
-                               "Task_File_VGS.txt parameters (voxel 0.15, graph 0.5, sigma 0.2 x5, sig_w 2, cut 0.3, "
-                               "points_min 10, adjacency_min 3, voxels_min 3)",
-                   "sample": f"each step = the CPU oracle on a bounded {args.ref_points}-point sample of that scene (same density)"},
-        "cpu_baseline": info,
+        "config": {"workload": f"{CONFIGS[cfg]['what']}, {n} points", "name": cfg, "same_scene_as_default_arm": args.ref_points in (0, None)},
+        "cpu_baseline": info, "parity": parity,
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference cannot be compiled (needs PCL 1.8.1, and voxel_segmentation.h:2279 is undefined); "
-                "this is the CPU oracle restatement; the reference is single-threaded, here its per-unit loop runs on all host "
-                "threads (cpu_baseline.cores); the single-thread figure is the cpu_baseline of the default arm"}))
+        "note": "the reference cannot be compiled (needs PCL 1.8.1, and voxel_segmentation.h:2279 is undefined); this is the CPU oracle "
+                "restatement; the reference is single-threaded, here its dominant per-unit loop runs on all host threads (cpu_baseline.cores); "
+                "the single-thread figure is the cpu_baseline of the default arm"}))
 
 
 def main():
@@ -167,19 +244,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--points", type=int, default=10_000_000)
-    ap.add_argument("--ref-points", type=int, default=2_000_000)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--points", type=int, default=0, help="override the number of points of the config's scene (density kept)")
+    ap.add_argument("--ref-points", type=int, default=0, help="--impl reference: 0 = the full scene of the config")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--mode", default="tiles", choices=["tiles", "partitioned"],
-                    help="N>1: 'tiles' = one independent site tile per rank (weak scaling, no exchange); "
-                         "'partitioned' = ONE scene, local-graph stage split over ranks + NCCL exchange (strong scaling)")
+    ap.add_argument("--mode", default=None, choices=["slabs", "replicas"],
+                    help="N>1: 'slabs' = ONE scene split into spatial slabs with halo voxels + cross-slab merge over NCCL (strong scaling); "
+                         "'replicas' = one independent tile per rank (weak scaling, no exchange)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
-
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config is None:
+        args.config = "site10m"
     if args.impl == "reference":
         run_reference(args)
         return
+    args.warmup = max(args.warmup, 3)
 
     import numpy as np
     import torch
@@ -189,54 +269,57 @@ def main():
     from vgs_svgs_segmentation_b200 import capi
 
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU path)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    partitioned = args.mode == "partitioned" and world > 1
-    pts = make_scene(args.points, 0 if partitioned else rank)
-    n = pts.shape[0]
-    host_xyz = torch.from_numpy(pts).pin_memory()
-    host_lab = torch.empty(n, dtype=torch.int32).pin_memory()
-    dev_xyz = host_xyz.cuda(non_blocking=False)
-    dev_lab = torch.empty(n, dtype=torch.int32, device="cuda")
-    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")  # 512 MB > 126 MB L2
-    stream = torch.cuda.current_stream()
-    h = capi.Handle(mode=capi.VGS_MODE_VGS, device=local, stream=stream.cuda_stream)
-    params = capi.make_params(**VGS_PARAMS)
+    cfg = args.config
+    cmode = CONFIGS[cfg]["mode"]
+    pd = params_of(cfg)
+    mode = args.mode or "replicas"
+    slabs = mode == "slabs" and world > 1 and cmode == 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from vgs_svgs_segmentation_b200.multigpu import segment_partitioned
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")  # 512 MB > 126 MB L2
+    if slabs:
+        from vgs_svgs_segmentation_b200 import slabs as slabmod
+        out = slabmod.bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, make_scene, measured_peak, CONFIGS)
+        if rank == 0:
+            if not args.no_cpu:
+                out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample)
+            print(json.dumps(out))
+        dist.destroy_process_group()
+        return
+
+    pts = make_scene(cfg, args.points or None, tile=rank)
+    n = pts.shape[0]
+    host_xyz = torch.from_numpy(pts).pin_memory()
+    host_lab = torch.empty(n, dtype=torch.int32).pin_memory()
+    dev_xyz = host_xyz.cuda(non_blocking=False)
+    dev_lab = torch.empty(n, dtype=torch.int32, device="cuda")
+    h = capi.Handle(mode=cmode, device=local, stream=stream.cuda_stream)
 
     def step_resident():
         h.set_points_device(dev_xyz.data_ptr(), n, 12)
-        if partitioned:
-            segment_partitioned(h, params, rank, world, dev_lab.data_ptr(), on_device=True)
-        else:
-            h.run(params, dev_lab.data_ptr(), on_device=True)
+        gpu_step(h, capi, cfg, pd, dev_lab.data_ptr(), True)
 
     def step_e2e():
         h.set_points_host_ptr(host_xyz.data_ptr(), n, 12)
-        if partitioned:
-            segment_partitioned(h, params, rank, world, host_lab.numpy(), on_device=False)
-        else:
-            h.run(params, host_lab.numpy(), on_device=False)
+        gpu_step(h, capi, cfg, pd, host_lab.numpy(), False)
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
     for _ in range(args.warmup):
         step_resident()
     launches0 = h.timings()["kernel_launches"]
-    stage_acc = {}
-    times = []
+    stage_acc, kern_acc, times = {}, {}, []
     barrier()
     with ClockSampler(local) as clk:
         t_wall0 = time.perf_counter()
@@ -250,9 +333,12 @@ def main():
             times.append(e0.elapsed_time(e1))
             for k, v in h.timings().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
+            for kt in h.kernel_timings():
+                a = kern_acc.setdefault(kt["name"], dict(ms=0.0, launches=kt["launches"], alg_bytes=kt["alg_bytes"]))
+                a["ms"] += kt["ms"]
         barrier()
         t_wall = time.perf_counter() - t_wall0
-    launches = h.timings()["kernel_launches"] - launches0
+    launches = (h.timings()["kernel_launches"] - launches0) // args.steps
     counts = h.counts()
     ms = sum(times) / len(times)
 
@@ -269,78 +355,54 @@ def main():
         te.append((time.perf_counter() - t0) * 1e3)
     barrier()
     ms_e2e = sum(te) / len(te)
-    # the e2e labels must equal the resident-path labels
-    same = bool(torch.equal(host_lab.cuda(), dev_lab))
+    same = bool(torch.equal(host_lab.cuda(), dev_lab))     # the e2e labels must equal the resident-path labels
 
-    # max over ranks
-    if world > 1:
+    if world > 1:     # max over ranks
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
         tot = torch.tensor([n], device="cuda", dtype=torch.int64)
         dist.all_reduce(tot)
-        total_points = n if partitioned else int(tot[0])
+        total_points = int(tot[0])
     else:
         total_points = n
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        V, E, N = counts["n_units"], counts["n_adjacency"], counts["n_points"]
         per_stage = {k: stage_acc[k] / args.steps for k in stage_acc if k.endswith("_ms")}
-        # algorithmic bytes per stage (SURVEY.md §8d / DESIGN.md §kernels)
-        alg = {"origin_ms": 12 * N, "voxelize_ms": 20 * N + 16 * V, "features_ms": 16 * N + 64 * V,
-               "adjacency_ms": 32 * V + 4 * E, "graph_ms": 8 * E + 64 * V, "mutual_ms": 12 * E,
-               "components_ms": 8 * E + 8 * V, "labels_ms": 8 * N + 4 * V}
-        stages = {}
-        for k, b in alg.items():
-            t_ms = per_stage.get(k, 0.0)
-            if t_ms > 0:
-                stages[k[:-3]] = {"ms": round(t_ms, 4), "alg_bytes": int(b), "GBps": round(b / t_ms / 1e6, 2),
-                                  "frac_of_hbm": round(b / t_ms / 1e6 / peak, 4)}
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tf) and n == 10_000_000 and not partitioned:
-            try:
-                t_ = json.load(open(tf))
-                traffic = float(t_["dram_bytes_read"]) + float(t_["dram_bytes_write"])
-            except Exception:
-                traffic = None
-        dom = max(per_stage, key=lambda k: per_stage[k] if k in alg else -1)
-        dom_b = alg[dom]
-        achieved = dom_b / per_stage[dom] / 1e6
+        kernels = []
+        for name, a in kern_acc.items():
+            t_ms = a["ms"] / args.steps
+            gbs = a["alg_bytes"] / t_ms / 1e6 if t_ms > 0 else 0.0
+            kernels.append({"kernel": name, "ms": round(t_ms, 4), "launches": a["launches"], "alg_bytes": a["alg_bytes"],
+                            "GBps": round(gbs, 1), "frac_of_hbm": round(gbs / peak, 4), "share_of_step": round(t_ms / ms, 4)})
+        dom = max(kernels, key=lambda kk: kk["ms"])
         out = {
             "metric": "points/sec segmented end-to-end", "value": total_points / (ms / 1e3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"VGS, ONE synthetic construction-site scene of {n} points, local-graph stage partitioned over "
-                                    f"{world} GPUs + NCCL exchange of connect lists, " if partitioned else
-                                    f"VGS, synthetic construction-site scene {n} points per GPU (BASELINE.json configs[2]), ") +
-                                   "Task_File_VGS.txt parameters (voxel 0.15, graph 0.5, sigma 0.2 x5, sig_w 2, cut 0.3, "
-                                   "points_min 10, adjacency_min 3, voxels_min 3)",
-                       "multi_gpu_mode": args.mode if world > 1 else "single", "points_per_gpu": n, "l2": "512 MB buffer written between timed steps (L2 flush); per-step working set > 1 GB",
-                       "tiles": world, "voxels": V, "used_voxels": counts["n_used"], "adjacency_entries": E,
-                       "pair_weights": counts["n_pairs"], "clusters": counts["n_clusters_exported"]},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{CONFIGS[cfg]['what']}, {n} points per GPU", "name": cfg,
+                       "multi_gpu_mode": "replicas (one independent tile per rank, no exchange)" if world > 1 else "single",
+                       "points_per_gpu": n, "l2": "512 MB buffer written between timed steps (L2 flush); per-step working set > 1 GB",
+                       "voxels": counts["n_voxels"], "units": counts["n_units"], "used_units": counts["n_used"],
+                       "adjacency_entries": counts["n_adjacency"], "pair_weights_of_the_reference": counts["n_pairs"],
+                       "clusters": counts["n_clusters_exported"], "octree_depth": counts["octree_depth"]},
             "e2e": {"value": total_points / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 12 * n,
                     "d2h_bytes_per_step": 4 * n, "ms_per_step": ms_e2e, "labels_equal_resident_path": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_pair_cache_bm + k_bin_classes + k_local_graph_warp (stage 4+5a, all size classes)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_kind": peak_kind, "algorithmic_bytes": int(dom_b),
-                         "algorithmic_bytes_no_reuse": int(72 * E + 64 * V),
-                         "sm_issue_active_pct_ncu": 60.8,
-                         "note": "achieved = algorithmic bytes (8*E + 64*V, SURVEY.md 8d / DESIGN.md section 4) / CUDA-event time of the "
-                                 "stage; SURVEY.md 8d classifies this stage as compute/latency bound (sum of n^2 pair work), not HBM bound: "
-                                 "ncu shows 61 % issue-slot utilisation and 8 % DRAM throughput for k_local_graph_warp "
-                                 "(profiles/r01_ncu_local_graph_warp_final.md); algorithmic_bytes_no_reuse = 64*E record gathers + 8*E if no "
-                                 "record were reused; traffic = ncu dram read+write bytes of the stage's kernels per pass on this workload "
-                                 "(profiles/r01_traffic.json): the pair table rows (8.8 KB, sparse) and the bin-ordered entry scratch"},
-            "stages": stages,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["GBps"] / peak, "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes": dom["alg_bytes"],
+                         "ms": dom["ms"],
+                         "note": "the kernel group with the largest share of the step; achieved = algorithmic bytes of the group (DESIGN.md "
+                                 "section 4, reported by vgs_kernel_timings) / its CUDA-event time measured in this run; every group is in "
+                                 "`kernels`; ncu DRAM traffic per kernel is in profiles/ (not repeated here: it is not measured by this run)"},
+            "kernels": kernels,
+            "stages_ms": {k[:-3]: round(v, 4) for k, v in per_stage.items() if v > 0},
             "clocks": clk.summary(),
             "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu:
-            info, _, _ = cpu_baseline(args.cpu_sample, math=0)
-            out["cpu_baseline"] = info
+            out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample)
         print(json.dumps(out))
     h.close()
     if world > 1:

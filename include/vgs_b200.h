@@ -160,6 +160,16 @@ vgs_status vgs_run(vgs_handle h, const vgs_params* p, int32_t* label_per_point, 
 vgs_status vgs_get_counts(vgs_handle h, vgs_counts* out);
 vgs_status vgs_stage_timings(vgs_handle h, vgs_timings* out);
 vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* bytes); /* dst NULL: size only */
+/* per-kernel-group CUDA-event times of the last run with the algorithmic HBM bytes each group is accounted with
+ * (DESIGN.md section 4); *n = capacity in, number of groups that ran out.  name points to static storage. */
+typedef struct vgs_kernel_timing {
+  const char* name;
+  float ms;
+  int32_t launches;
+  int64_t alg_bytes;
+  int64_t reserved;
+} vgs_kernel_timing;
+vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n);
 
 #ifdef __cplusplus
 }

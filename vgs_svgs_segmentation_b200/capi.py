@@ -43,6 +43,10 @@ class Timings(C.Structure):
                [("kernel_launches", C.c_int64), ("pair_cache_ms", C.c_float), ("reserved", C.c_float * 3)]
 
 
+class KernelTiming(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_int32), ("alg_bytes", C.c_int64), ("reserved", C.c_int64)]
+
+
 class Counts(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_points", "n_finite", "n_voxels", "n_units", "n_used", "n_adjacency", "n_pairs",
                                          "n_singles", "n_attached", "n_clusters_all", "n_clusters_exported", "octree_depth",
@@ -57,7 +61,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
             "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_make_supervoxels_vccs", "vgs_get_supervoxel_labels", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
-            "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get"]
+            "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get", "vgs_kernel_timings"]
 
 _lib = None
 
@@ -96,6 +100,7 @@ def load():
         L.vgs_get_counts.argtypes = [C.c_void_p, C.POINTER(Counts)]
         L.vgs_stage_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.vgs_debug_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.vgs_kernel_timings.argtypes = [C.c_void_p, C.POINTER(KernelTiming), C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -238,6 +243,14 @@ class Handle:
         t = Timings()
         self._ck(self.L.vgs_stage_timings(self.h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timings._fields_ if k != "reserved"}
+
+    def kernel_timings(self) -> list:
+        """[{name, ms, launches, alg_bytes}] per kernel group of the last run"""
+        arr = (KernelTiming * 32)()
+        n = C.c_int(32)
+        self._ck(self.L.vgs_kernel_timings(self.h, arr, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), ms=float(arr[i].ms), launches=int(arr[i].launches), alg_bytes=int(arr[i].alg_bytes))
+                for i in range(n.value)]
 
     def blob(self, name: str) -> np.ndarray:
         kind, dt = BLOBS[name]

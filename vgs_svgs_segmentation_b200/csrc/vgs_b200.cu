@@ -98,7 +98,7 @@ struct vgs_context {
   float st_vs = -1.f, st_gs = -1.f;
   double st_noise = -1.0;
   bool rows_ok = false;             // pair-weight rows usable (stencil reach <= 5 cells)
-  int64_t max_row_len = 0, n_rows = 0, n_long = 0;
+  int64_t max_row_len = 0, n_rows = 0, n_long = 0, grid_bytes = 0;
   uint32_t kminmax[6] = {0, 0, 0, 0, 0, 0};   // smallest / largest occupied voxel key per axis
   BitGrid grid{};
   LatticeGeom lgeo{};
@@ -129,6 +129,12 @@ struct vgs_context {
   int class_streams = 6;            // VGS_B200_CLASS_STREAMS (1 = everything on the handle's stream; measured flat from 4 to 8)
   float* tm_slot[16] = {};
   unsigned tm_pending = 0;
+  // per-kernel-group timers (vgs_kernel_timings): one event pair per group and run
+  static constexpr int NK = 17;
+  cudaEvent_t kev[2 * NK] = {};
+  float k_ms[NK] = {};
+  int k_launches[NK] = {};
+  unsigned k_pending = 0;
 
   vgs_status fail(vgs_status s, const std::string& m) { err = m; return s; }
   vgs_status fail_cuda(cudaError_t e, const char* what, int line) {
@@ -312,9 +318,28 @@ struct StageTimer {
   }
 };
 
+// kernel-group timer: brackets the launches of one group (names in vgs_kernel_timings)
+enum KId { K_ORIGIN = 0, K_QUANTISE, K_SORT, K_HEADS, K_FEATURES, K_HASH, K_GRID, K_ADJ_COUNT, K_ADJ_FILL, K_ROWS_FILL, K_ROWS_SORT,
+           K_GRAPH_ROWS, K_GRAPH_GENERAL, K_MUTUAL, K_CLOSEST, K_COMPONENTS, K_LABELS };
+struct KTimer {
+  vgs_handle h; int id; int64_t l0;
+  KTimer(vgs_handle h_, int id_) : h(h_), id(id_), l0(h_->launches) { cudaEventRecord(h->kev[2 * id], h->stream); }
+  void stop() {
+    cudaEventRecord(h->kev[2 * id + 1], h->stream);
+    h->k_pending |= 1u << id;
+    h->k_launches[id] = (int)(h->launches - l0);
+  }
+};
+
 void resolve_timers(vgs_handle h) {
-  if (!h->tm_pending) return;
+  if (!h->tm_pending && !h->k_pending) return;
   cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < vgs_context::NK; i++)
+    if ((h->k_pending >> i) & 1u) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, h->kev[2 * i], h->kev[2 * i + 1]) == cudaSuccess) h->k_ms[i] = ms;
+    }
+  h->k_pending = 0;
   for (int i = 0; i < 15; i++)
     if ((h->tm_pending >> i) & 1u) {
       float ms = 0;
@@ -372,6 +397,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     h->own_stream = true;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  for (auto& ev : h->kev) cudaEventCreate(&ev);
   for (int i = 0; i < vgs_context::N_AUX; i++) {
     cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
@@ -426,6 +452,7 @@ void vgs_destroy(vgs_handle h) {
                  &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.cnt, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->kev) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < vgs_context::N_AUX; i++) { if (h->aux[i]) cudaStreamDestroy(h->aux[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -443,6 +470,8 @@ vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_
   h->voxelized = h->have_units = h->have_features = h->have_adj = h->have_segments = false;
   h->d_labels = nullptr;
   h->tm_pending = 0;
+  h->k_pending = 0;
+  for (int i = 0; i < vgs_context::NK; i++) { h->k_ms[i] = 0.f; h->k_launches[i] = 0; }
   h->tm = vgs_timings{};
   if (on_device) { h->d_xyz = xyz; }
   else {
@@ -493,6 +522,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   std::vector<size_t> events_before;  // #growth events before each epoch started
   {
     StageTimer t(h, &h->tm.origin_ms, 1);
+    KTimer kt(h, K_ORIGIN);
     int64_t cursor = 0;
     while (true) {
       int64_t idx;
@@ -519,6 +549,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
         for (int a = 0; a < 3; a++)
           if ((st.events[k].lowered >> a) & 1u) ep.shift[e][a] += 1u << st.events[k].depth_old;
     }
+    kt.stop();
     t.stop();
   }
   for (int a = 0; a < 3; a++) { h->box.mn[a] = st.mn[a]; h->box.mx[a] = st.mx[a]; }
@@ -531,11 +562,16 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     StageTimer t(h, &h->tm.voxelize_ms, 2);
     CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
     CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
+    KTimer kq(h, K_QUANTISE);
     LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, ep, st.res, h->depth,
            h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr);
+    kq.stop();
     uint64_t* ks; uint32_t* vs;
+    KTimer ksrt(h, K_SORT);
     vgs_status s = radix_sort(h, n, 3 * h->depth + 1, &ks, &vs);
     if (s) return s;
+    ksrt.stop();
+    KTimer kh(h, K_HEADS);
     // number of finite points = first sorted position whose key has the sentinel bit: count via head scan
     // (sentinel keys form at most one extra segment at the end)
     int64_t nunits = 0;
@@ -554,6 +590,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     uint64_t lastkey = 0; uint32_t laststart = 0;
     CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+    kh.stop();
     CK(cudaMemcpyAsync(h->kminmax, d_kmm, sizeof(h->kminmax), cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
     int64_t n_fin = n;
@@ -825,8 +862,10 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   unsigned long long* d_used = h->small.as<unsigned long long>() + 16;
   CK(cudaMemsetAsync(d_used, 0, 8, h->stream));
   CK(h->uflags.reserve((size_t)nu + 16));
+  KTimer kf(h, K_FEATURES);
   LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
          h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->uflags.as<uint8_t>(), d_used);
+  kf.stop();
   if (h->mode == VGS_MODE_SVGS) {   // VGS: the count arrives with the adjacency totals (one host round trip less)
     unsigned long long used = 0;
     CK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1041,9 +1080,11 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   h->hmask = capacity - 1;
   CK(h->plainm.reserve((size_t)nu * 8));
   CK(h->tk.reserve(capacity * 8)); CK(h->tv.reserve(capacity * 4));
+  KTimer khash(h, K_HASH);
   CK(cudaMemsetAsync(h->tk.p, 0xff, capacity * 8, h->stream));
   LAUNCH(k_plain_morton, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, h->plainm.as<uint64_t>());
   LAUNCH(k_hash_insert, (unsigned)cdiv(nu, 256), 256, 0, h->plainm.as<uint64_t>(), nu, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask);
+  khash.stop();
   // occupancy grids over the occupied key range (+ margin: no bounds checks in the searches)
   const int margin = std::max(rho, r2c) + 1;
   BitGrid& g = h->grid;
@@ -1055,10 +1096,13 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   if (nbits > ((uint64_t)1 << 35)) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: occupied key range too large for the occupancy grid (> 4 GB): tile the scene");
   const size_t bm_bytes = (size_t)(nbits / 8) + 64;
   CK(h->bm_all.reserve(bm_bytes)); CK(h->bm_used.reserve(bm_bytes));
+  KTimer kgrid(h, K_GRID);
   CK(cudaMemsetAsync(h->bm_all.p, 0, bm_bytes, h->stream));
   CK(cudaMemsetAsync(h->bm_used.p, 0, bm_bytes, h->stream));
   LAUNCH(k_bitgrid_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, g, h->bm_all.as<uint32_t>(),
          h->bm_used.as<uint32_t>());
+  kgrid.stop();
+  h->grid_bytes = (int64_t)bm_bytes;
   LatticeGeom& lg = h->lgeo;
   lg.res_f = res_f; lg.mnx = h->bb_f[0]; lg.mny = h->bb_f[1]; lg.mnz = h->bb_f[2];
   { double r = (double)graph_size; lg.r2 = (float)(r * r); }
@@ -1069,6 +1113,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(h->row_len.reserve((size_t)(nu + 1) * 4)); CK(h->row_off.reserve((size_t)(nu + 1) * 4)); CK(h->row_npos.reserve((size_t)nu * 2 + 16));
   CK(h->long_rows.reserve((size_t)nu * 4 + 16)); CK(h->cstats.reserve(256));
   CK(cudaMemsetAsync(h->cstats.p, 0, 256, h->stream));
+  KTimer kcnt(h, K_ADJ_COUNT);
   LAUNCH(k_adj_count, (unsigned)cdiv(nu, 8), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
          h->bm_used.as<uint32_t>(), h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), h->d_pc_cols.as<int4>(),
          want_rows ? (int)h->pc_cols_host.size() : 0, h->adj_cnt.as<uint32_t>(), h->row_len.as<uint32_t>(), h->row_npos.as<uint16_t>(),
@@ -1081,6 +1126,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   if (s) return s;
   CK(cudaMemcpyAsync(h->adj_off.as<uint32_t>() + nu, d_tot_adj, 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->row_off.as<uint32_t>() + nu, d_tot_rows, 4, cudaMemcpyDeviceToDevice, h->stream));
+  kcnt.stop();
   unsigned long long totals[2] = {0, 0};
   CountStats cs{};
   CK(cudaMemcpyAsync(totals, d_tot_adj, 16, cudaMemcpyDeviceToHost, h->stream));
@@ -1097,9 +1143,11 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   unsigned* d_err = h->small.as<unsigned>() + 200;
   CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
   AdjTables tb{h->tb_slot.as<uint16_t>(), h->tb_code5.as<uint16_t>(), h->tb_first.as<uint16_t>(), h->tb_last.as<uint16_t>()};
+  KTimer kfill(h, K_ADJ_FILL);
   LAUNCH(k_adj_fill, (unsigned)cdiv(nu, ADJ_WARPS), ADJ_WARPS * 32, adj_fill_smem(nst), h->key3.as<uint32_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
          h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), tb, nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask,
          h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), d_err);
+  kfill.stop();
   h->have_adj = true;
   t.stop();
   return VGS_OK;
@@ -1166,10 +1214,13 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     {
       StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
       CK(h->rows.reserve((size_t)h->n_rows * 8 + 64)); CK(h->cursor.reserve((size_t)nu * 4 + 16));
+      KTimer krf(h, K_ROWS_FILL);
       LAUNCH(k_rows_cursor, (unsigned)cdiv(nu, 256), 256, 0, h->row_off.as<uint32_t>(), h->row_npos.as<uint16_t>(), nu, h->cursor.as<uint32_t>());
       LAUNCH(k_rows_fill, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg, h->grid, h->bm_used.as<uint32_t>(),
              h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
              h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->cursor.as<uint32_t>(), h->rows.as<uint2>(), d_err);
+      krf.stop();
+      KTimer krs(h, K_ROWS_SORT);
       LAUNCH(k_rows_sort, (unsigned)cdiv(nu, RS2_WARPS), RS2_WARPS * 32, (size_t)RS2_WARPS * 2 * ROWS_SHORT_CAP * 8, h->row_off.as<uint32_t>(), nu,
              (const uint32_t*)nullptr, 0u, ROWS_SHORT_CAP, h->rows.as<uint2>());
       if (h->n_long > 0) {
@@ -1177,16 +1228,19 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
         LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 8, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
                (uint32_t)h->n_long, cap_long, h->rows.as<uint2>());
       }
+      krs.stop();
       tpc.stop();
     }
     // ---- stage 5a: one warp per voxel ----
     const int mw = h->mwords;
     CK(h->conn_mask.reserve((size_t)nu * mw * 4 + 16));
     CK(h->fallback.reserve((size_t)nu * 4 + 16));
+    KTimer kgr(h, K_GRAPH_ROWS);
     LAUNCH(k_local_graph_rows, (unsigned)cdiv(nu, LR_WARPS), LR_WARPS * 32, lr_slice_bytes(h->lbits, mw) * LR_WARPS, (int64_t)0, nu,
            h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw,
            h->row_off.as<uint32_t>(), h->rows.as<uint2>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
            h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, d_dbg);
+    kgr.stop();
     uint32_t fe[2] = {0, 0};   // [0] = error bits of the fill kernels, [1] = units handed back
     CK(cudaMemcpyAsync(fe, d_err, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
@@ -1202,11 +1256,13 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     }
     if (fe[1]) {   // units the row kernel handed back: general kernel sized for the largest neighbourhood, then list -> mask
       CK(h->conn0_idx.reserve(E * 4 + 16));
+      KTimer kgg(h, K_GRAPH_GENERAL);
       vgs_status s_ = launch_general(h, h->stream, h->fallback.as<uint32_t>(), fe[1], CLASS_N_HOST[N_CLASSES - 1], 256, (uint32_t)h->max_n, gp, d_wempty);
       if (s_) return s_;
       LAUNCH(k_conn_list_to_mask, (unsigned)cdiv((int64_t)fe[1] * 32, 128), 128, 0, h->fallback.as<uint32_t>(), fe[1], h->adj_off.as<uint32_t>(),
              h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->conn0_cnt.as<uint32_t>(), h->conn0_idx.as<int32_t>(), lg.rho, mw,
              h->conn_mask.as<uint32_t>());
+      kgg.stop();
     }
     h->conn0_is_mask = true;
     t.stop();
@@ -1217,6 +1273,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
   //      size of their local graph, one launch per class over up to 6 streams ----
   CK(h->conn0_idx.reserve(E * 4 + 16));
   CK(h->class_count.reserve(256));
+  KTimer kgg(h, K_GRAPH_GENERAL);
   CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
   CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
   LAUNCH(k_class_init, (unsigned)cdiv(nu, 256), 256, 0, h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>(), nu);
@@ -1265,6 +1322,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       CK(cudaEventRecord(h->ev_join[i], h->aux[i]));
       CK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
     }
+  kgg.stop();
   t.stop();
   h->have_graph = true;
   return VGS_OK;
@@ -1283,6 +1341,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
   // ---- stage 5b: mutual filter ----
   {
     StageTimer t(h, &h->tm.mutual_ms, 6);
+    KTimer km(h, K_MUTUAL);
     if (h->conn0_is_mask)
       LAUNCH(k_mutual_mask, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(),
              h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(), nu, h->lgeo.rho, h->mwords, h->conn1_cnt.as<uint32_t>(),
@@ -1290,11 +1349,13 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     else
       LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
              h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
+    km.stop();
     t.stop();
   }
   // ---- stage 5c: closest check ----
   {
     StageTimer t(h, &h->tm.closest_ms, 7);
+    KTimer kc(h, K_CLOSEST);
     CK(cudaMemsetAsync(h->attach.p, 0xff, (size_t)nu * 4, h->stream));
     uint32_t* d_changed = h->small.as<uint32_t>() + 128;
     uint32_t* d_scnt = h->small.as<uint32_t>() + 132;
@@ -1321,17 +1382,20 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     unsigned long long singles = scnt[1];
     h->n_singles = (int64_t)singles;
     h->closest_rounds = rounds;
+    kc.stop();
     t.stop();
   }
   // ---- stage 5d: components ----
   {
     StageTimer t(h, &h->tm.components_ms, 8);
+    KTimer kcc(h, K_COMPONENTS);
     LAUNCH(k_cc_init, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>(),
            h->attach.as<int32_t>(), nu, h->parent.as<int>());
     for (int r = 0; r < h->cc_jumps; r++) LAUNCH(k_cc_jump, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu);
     LAUNCH(k_cc_hook, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(),
            h->conn1_idx.as<int32_t>(), h->attach.as<int32_t>(), nu, h->parent.as<int>());
     LAUNCH(k_cc_flatten, (unsigned)cdiv(nu, 256), 256, 0, h->parent.as<int>(), nu, h->root.as<int>());
+    kcc.stop();
     t.stop();
   }
   h->have_segments = true;
@@ -1373,6 +1437,7 @@ vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, i
   if (!h || !labels) return VGS_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   StageTimer t(h, &h->tm.labels_ms, 9);
+  KTimer kl(h, K_LABELS);
   vgs_status s = ensure_cluster_stats(h, voxels_min);
   if (s) return s;
   const int min_excl = h->mode == VGS_MODE_SVGS ? -1 : voxels_min;
@@ -1380,6 +1445,7 @@ vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, i
   if (!on_device) { CK(h->labels_out.reserve((size_t)h->n * 4)); d_out = h->labels_out.as<int32_t>(); }
   LAUNCH(k_point_labels, (unsigned)cdiv(h->n, 256), 256, 0, h->d_perm, h->pos_unit.as<uint32_t>(), h->root.as<int>(),
          h->csize.as<uint32_t>(), h->cminpt.as<uint32_t>(), h->n, h->n_valid, min_excl, d_out, (int32_t*)nullptr);
+  kl.stop();
   t.stop();
   if (!on_device) {
     StageTimer t2(h, &h->tm.d2h_ms, 10);
@@ -1465,6 +1531,33 @@ vgs_status vgs_stage_timings(vgs_handle h, vgs_timings* out) {
   resolve_timers(h);
   *out = h->tm;
   out->kernel_launches = h->launches;
+  return VGS_OK;
+}
+
+vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
+  if (!h || !n) return VGS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  resolve_timers(h);
+  static const char* names[vgs_context::NK] = {
+      "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_head_flags + scan + k_head_write + k_voxel_keys",
+      "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
+      "adjacency fill: k_adj_fill", "weight rows: k_rows_cursor + k_rows_fill", "weight rows: k_rows_sort", "local graphs: k_local_graph_rows",
+      "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",
+      "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels"};
+  const int64_t N = h->n, V = h->nu, E = h->n_adj, R = h->n_rows, MW = h->mwords;
+  const int64_t KB = 8;     // bytes per sort key
+  const int passes = (3 * h->depth + 1 + 7) / 8;
+  // algorithmic bytes = compulsory HBM traffic with inputs / outputs materialised once
+  const int64_t bytes[vgs_context::NK] = {
+      12 * N, 12 * N + (KB + 4) * N, (int64_t)passes * 2 * (KB + 4) * N, KB * N + 4 * N + 28 * V, 16 * N + 64 * V, 32 * V, 13 * V + 2 * h->grid_bytes,
+      20 * V, 16 * V + 6 * E, 64 * V + 8 * R, 16 * R, 6 * E + 8 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
+  int c = 0;
+  for (int i = 0; i < vgs_context::NK && out && c < *n; i++) {
+    if (h->k_launches[i] == 0 && h->k_ms[i] == 0.f) continue;
+    out[c].name = names[i]; out[c].ms = h->k_ms[i]; out[c].alg_bytes = bytes[i]; out[c].launches = h->k_launches[i]; out[c].reserved = 0;
+    c++;
+  }
+  *n = c;
   return VGS_OK;
 }
 
