@@ -103,7 +103,7 @@ struct vgs_context {
   BitGrid grid{};
   LatticeGeom lgeo{};
   DBuf d_adj_cols, d_pc_cols, tb_slot, tb_code5, tb_first, tb_last;
-  DBuf bm_all, bm_used, row_len, row_off, row_npos, rows, cursor, long_rows, cstats, conn_mask;
+  DBuf bm_all, bm_used, row_len, row_off, rows, long_rows, cstats, conn_mask;
   DBuf fallback, uflags, singles;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
@@ -443,7 +443,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
-                 &h->tb_last, &h->bm_all, &h->bm_used, &h->row_len, &h->row_off, &h->row_npos, &h->rows, &h->cursor, &h->long_rows,
+                 &h->tb_last, &h->bm_all, &h->bm_used, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
                  &h->cstats, &h->conn_mask};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
@@ -971,7 +971,7 @@ static vgs_status build_lattice_tables(vgs_handle h, float graph_size, double no
         st2.push_back(make_int4(dx, dy, dz, 0));
       }
     h->pc_cols_host = columns(st2, r2);
-    h->max_row_len = 2 * (int64_t)st2.size();
+    h->max_row_len = (int64_t)st2.size();
   }
   h->lbits = rho <= 3 ? 3 : 4;
   h->mwords = (S * S * S + 31) / 32;
@@ -1110,13 +1110,13 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   // counts: neighbours of every voxel, weight-row length of every used voxel
   const bool want_rows = h->rows_ok && h->use_pair_cache;
   CK(h->adj_cnt.reserve((size_t)(nu + 1) * 4)); CK(h->adj_off.reserve((size_t)(nu + 1) * 4));
-  CK(h->row_len.reserve((size_t)(nu + 1) * 4)); CK(h->row_off.reserve((size_t)(nu + 1) * 4)); CK(h->row_npos.reserve((size_t)nu * 2 + 16));
+  CK(h->row_len.reserve((size_t)(nu + 1) * 4)); CK(h->row_off.reserve((size_t)(nu + 1) * 4));
   CK(h->long_rows.reserve((size_t)nu * 4 + 16)); CK(h->cstats.reserve(256));
   CK(cudaMemsetAsync(h->cstats.p, 0, 256, h->stream));
   KTimer kcnt(h, K_ADJ_COUNT);
   LAUNCH(k_adj_count, (unsigned)cdiv(nu, 8), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
          h->bm_used.as<uint32_t>(), h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), h->d_pc_cols.as<int4>(),
-         want_rows ? (int)h->pc_cols_host.size() : 0, h->adj_cnt.as<uint32_t>(), h->row_len.as<uint32_t>(), h->row_npos.as<uint16_t>(),
+         want_rows ? (int)h->pc_cols_host.size() : 0, h->adj_cnt.as<uint32_t>(), h->row_len.as<uint32_t>(),
          ROWS_SHORT_CAP, h->long_rows.as<uint32_t>(), h->cstats.as<CountStats>());
   unsigned long long* d_tot_adj = h->small.as<unsigned long long>() + 8;
   unsigned long long* d_tot_rows = h->small.as<unsigned long long>() + 9;
@@ -1213,20 +1213,19 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(cudaMemsetAsync(d_err, 0, 8, h->stream));
     {
       StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
-      CK(h->rows.reserve((size_t)h->n_rows * 8 + 64)); CK(h->cursor.reserve((size_t)nu * 4 + 16));
+      CK(h->rows.reserve((size_t)h->n_rows * 16 + 64));
       KTimer krf(h, K_ROWS_FILL);
-      LAUNCH(k_rows_cursor, (unsigned)cdiv(nu, 256), 256, 0, h->row_off.as<uint32_t>(), h->row_npos.as<uint16_t>(), nu, h->cursor.as<uint32_t>());
       LAUNCH(k_rows_fill, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg, h->grid, h->bm_used.as<uint32_t>(),
              h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
-             h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->cursor.as<uint32_t>(), h->rows.as<uint2>(), d_err);
+             h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_err);
       krf.stop();
       KTimer krs(h, K_ROWS_SORT);
-      LAUNCH(k_rows_sort, (unsigned)cdiv(nu, RS2_WARPS), RS2_WARPS * 32, (size_t)RS2_WARPS * 2 * ROWS_SHORT_CAP * 8, h->row_off.as<uint32_t>(), nu,
-             (const uint32_t*)nullptr, 0u, ROWS_SHORT_CAP, h->rows.as<uint2>());
+      LAUNCH(k_rows_sort, (unsigned)cdiv(nu, RS2_WARPS), RS2_WARPS * 32, (size_t)RS2_WARPS * 2 * ROWS_SHORT_CAP * 16, h->row_off.as<uint32_t>(), nu,
+             (const uint32_t*)nullptr, 0u, ROWS_SHORT_CAP, h->rows.as<uint4>());
       if (h->n_long > 0) {
         const int cap_long = (int)((h->max_row_len + 63) & ~(int64_t)63);
-        LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 8, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
-               (uint32_t)h->n_long, cap_long, h->rows.as<uint2>());
+        LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 16, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
+               (uint32_t)h->n_long, cap_long, h->rows.as<uint4>());
       }
       krs.stop();
       tpc.stop();
@@ -1236,9 +1235,9 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(h->conn_mask.reserve((size_t)nu * mw * 4 + 16));
     CK(h->fallback.reserve((size_t)nu * 4 + 16));
     KTimer kgr(h, K_GRAPH_ROWS);
-    LAUNCH(k_local_graph_rows, (unsigned)cdiv(nu, LR_WARPS), LR_WARPS * 32, lr_slice_bytes(h->lbits, mw) * LR_WARPS, (int64_t)0, nu,
+    LAUNCH(k_local_graph_rows, (unsigned)nu, 32, lr_smem_bytes(h->lbits, mw), (int64_t)0, nu,
            h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw,
-           h->row_off.as<uint32_t>(), h->rows.as<uint2>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
+           h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
            h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, d_dbg);
     kgr.stop();
     uint32_t fe[2] = {0, 0};   // [0] = error bits of the fill kernels, [1] = units handed back
@@ -1541,7 +1540,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   static const char* names[vgs_context::NK] = {
       "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_head_flags + scan + k_head_write + k_voxel_keys",
       "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
-      "adjacency fill: k_adj_fill", "weight rows: k_rows_cursor + k_rows_fill", "weight rows: k_rows_sort", "local graphs: k_local_graph_rows",
+      "adjacency fill: k_adj_fill", "weight rows: k_rows_fill", "weight rows: k_rows_sort", "local graphs: k_local_graph_rows",
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",
       "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels"};
   const int64_t N = h->n, V = h->nu, E = h->n_adj, R = h->n_rows, MW = h->mwords;
@@ -1550,7 +1549,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   // algorithmic bytes = compulsory HBM traffic with inputs / outputs materialised once
   const int64_t bytes[vgs_context::NK] = {
       12 * N, 12 * N + (KB + 4) * N, (int64_t)passes * 2 * (KB + 4) * N, KB * N + 4 * N + 28 * V, 16 * N + 64 * V, 32 * V, 13 * V + 2 * h->grid_bytes,
-      20 * V, 16 * V + 6 * E, 64 * V + 8 * R, 16 * R, 6 * E + 8 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
+      20 * V, 16 * V + 6 * E, 64 * V + 16 * R, 32 * R, 6 * E + 16 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
   int c = 0;
   for (int i = 0; i < vgs_context::NK && out && c < *n; i++) {
     if (h->k_launches[i] == 0 && h->k_ms[i] == 0.f) continue;

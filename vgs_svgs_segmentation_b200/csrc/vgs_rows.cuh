@@ -88,15 +88,15 @@ __host__ __device__ __forceinline__ uint32_t pack5(int x, int y, int z) { return
 __host__ __device__ __forceinline__ uint32_t pack6(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 6) | ((uint32_t)z << 12); }
 
 // ---- stage 3a: neighbour count of every voxel (all-voxel grid, radius stencil, float test on the centres computed
-//      from the keys) and, for used voxels, the length of its weight row (used-voxel grid, pair stencil: partners in
-//      the lexicographically positive half are evaluated by this voxel, those in the negative half by the partner).
+//      from the keys) and, for used voxels, the length of its weight row (used-voxel grid, pair stencil: a voxel files
+//      the pairs with its partners in the lexicographically positive half; the other half is filed by the partners).
 //      One warp per voxel, lanes over stencil columns (dx, dy, mask of dz). ----
 struct CountStats { unsigned long long sum_nn, max_n, n_long, n_used; };
 __global__ void __launch_bounds__(256) k_adj_count(const uint32_t* __restrict__ key3, const uint8_t* __restrict__ uflags, int64_t nv,
                                                  LatticeGeom lg, BitGrid g, const uint32_t* __restrict__ bm_all,
                                                  const uint32_t* __restrict__ bm_used, const int4* __restrict__ adj_cols, int n_adj_cols,
                                                  const int4* __restrict__ pc_cols, int n_pc_cols, uint32_t* __restrict__ adj_cnt,
-                                                 uint32_t* __restrict__ row_len, uint16_t* __restrict__ row_npos, int long_len,
+                                                 uint32_t* __restrict__ row_len, int long_len,
                                                  uint32_t* __restrict__ long_rows, CountStats* __restrict__ stats) {
   __shared__ unsigned long long s_sum[8];
   __shared__ unsigned s_max[8], s_used[8];
@@ -120,25 +120,20 @@ __global__ void __launch_bounds__(256) k_adj_count(const uint32_t* __restrict__ 
       }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    int npos = 0, nneg = 0;
+    int npos = 0;
     const bool used = (uflags[v] & F_USED) != 0;
     if (used) {
       const int span = 2 * lg.r2c + 1;
       for (int ci = lane; ci < n_pc_cols; ci += 32) {
         const int4 o = pc_cols[ci];
         npos += __popc(bg_run(bm_used, bg_bit(g, kx + o.x, ky + o.y, kz - lg.r2c), span) & (uint32_t)o.z);
-        // mirrored column: partners whose positive half contains this voxel
-        const uint32_t mm = __brev((uint32_t)o.z) >> (32 - span);
-        nneg += __popc(bg_run(bm_used, bg_bit(g, kx - o.x, ky - o.y, kz - lg.r2c), span) & mm);
       }
       npos = __reduce_add_sync(0xffffffffu, npos);
-      nneg = __reduce_add_sync(0xffffffffu, nneg);
     }
     if (lane == 0) {
       adj_cnt[v] = (uint32_t)cnt;
-      const uint32_t len = (uint32_t)(npos + nneg);
+      const uint32_t len = (uint32_t)npos;
       row_len[v] = len;
-      row_npos[v] = (uint16_t)npos;
       if ((int)len > long_len) long_rows[atomicAdd(&stats->n_long, 1ull)] = (uint32_t)v;
       my_sum = used ? (unsigned long long)cnt * (unsigned long long)(cnt - 1) : 0ull;
       my_max = (unsigned)cnt; my_used = used ? 1u : 0u;
@@ -211,15 +206,21 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
     nq += __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();
-  for (int e = lane; e < nq; e += 32) {
-    const int c = q[e];
-    const int dz = c % S - rho, dy = (c / S) % S - rho, dx = c / (S * S) - rho;
-    const float d2 = flann_d2(qx, qy, qz, centre_of(kx + dx, lg.res_f, lg.mnx), centre_of(ky + dy, lg.res_f, lg.mny),
-                              centre_of(kz + dz, lg.res_f, lg.mnz));
-    if (!(d2 < lg.r2)) continue;
-    const int id = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
-    if (id < 0) { atomicOr(err, 1u); continue; }     // grid and hash table disagree: cannot happen
-    skey[tb.slot_of_code[c]] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+  for (int e0 = 0; e0 < nq; e0 += 32) {
+    const int e = e0 + lane;
+    int id = -1, c = 0;
+    float d2 = 0.f;
+    if (e < nq) {
+      c = q[e];
+      const int dz = c % S - rho, dy = (c / S) % S - rho, dx = c / (S * S) - rho;
+      d2 = flann_d2(qx, qy, qz, centre_of(kx + dx, lg.res_f, lg.mnx), centre_of(ky + dy, lg.res_f, lg.mny), centre_of(kz + dz, lg.res_f, lg.mnz));
+      if (d2 < lg.r2) {
+        id = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+        if (id < 0) atomicOr(err, 1u);               // grid and hash table disagree: cannot happen
+      }
+    }
+    __syncwarp();     // the probe loops end at different iterations
+    if (id >= 0) skey[tb.slot_of_code[c]] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
   }
   __syncwarp();
   {   // presence words + running counts
@@ -248,11 +249,13 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
   }
 }
 
-// ---- stage 4: weight rows.  Entry = (float weight, cell << 18 | pack6(d + r2c)): the directed weight w(a -> b) lives in
-//      the row of a, keyed by the lattice offset d = key_b - key_a.  cell = floor((1 - w) * 1024) orders a row coarsely
-//      (k_rows_sort); the consumer sorts exactly inside the cells it takes. ----
+// ---- stage 4: weight rows.  One 16-byte entry per UNORDERED pair {a, b} of used voxels that can meet in a local graph,
+//      filed in the row of the voxel a whose offset to b is lexicographically positive:
+//        .x = w(a -> b)   .y = w(b -> a)   .z = cell(max weight) << 18 | pack6(d + r2c), d = key_b - key_a   .w = cell(min weight)
+//      cell(w) = floor((1 - w) * 1024) orders a row coarsely (k_rows_sort); the consumer sorts exactly inside the cells
+//      it takes.  A row is written by one warp only: no atomics, no scattered stores. ----
 constexpr int ROW_CELLS = 1024;
-constexpr int ROWS_SHORT_CAP = 512;   // rows up to this length are sorted four per CTA; longer ones one per CTA
+constexpr int ROWS_SHORT_CAP = 256;   // rows up to this length are sorted four per CTA; longer ones one per CTA
 __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
   // monotone non-increasing in w; NaN and w <= 0 fall into the last cell
   if (!(w > 0.f)) return ROW_CELLS - 1;
@@ -262,19 +265,12 @@ __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
 // every weight of a cell >= c is <= this bound (1 - w is exact for w >= 0.5, else off by <= 2^-25; the slack covers it)
 __device__ __forceinline__ float row_cell_upper(int c) { return (1.0f - (float)c * (1.0f / (float)ROW_CELLS)) + 1.2e-7f; }
 
-// cursor[v] = first free slot of the incoming (negative-half) part of row v
-__global__ void __launch_bounds__(256) k_rows_cursor(const uint32_t* __restrict__ row_off, const uint16_t* __restrict__ row_npos, int64_t nv,
-                                                   uint32_t* __restrict__ cursor) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < nv) cursor[v] = row_off[v] + row_npos[v];
-}
-
 constexpr int RF_QCAP = 32 + 32 * 32;   // a lane queues at most one z-run (<= 32 hits) per column step
 __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
                                                  BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
                                                  const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv, uint64_t hmask,
                                                  PairParams pp, const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ row_off,
-                                                 uint32_t* __restrict__ cursor, uint2* __restrict__ rows, unsigned* __restrict__ err) {
+                                                 uint4* __restrict__ rows, unsigned* __restrict__ err) {
   __shared__ unsigned short pend[4][RF_QCAP];
   __shared__ float s_ra[4][REC_FLOATS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -288,22 +284,25 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
   const uint32_t my_row = row_off[v];
   int npend = 0, done = 0;
   auto process = [&](int first, int cnt) {
-    if (lane < cnt) {
+    const bool act = lane < cnt;
+    int b = -1, dx = 0, dy = 0, dz = 0;
+    if (act) {
       const int c = pend[w][first + lane];              // ((dx+r2)*S + (dy+r2))*S + (dz+r2)
-      const int dz = c % S - r2, dy = (c / S) % S - r2, dx = c / (S * S) - r2;
-      const int b = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
-      if (b < 0) { atomicOr(err, 4u); }
-      else {
-        float rb[REC_FLOATS];
-        const float4* src = reinterpret_cast<const float4*>(rec + (int64_t)b * REC_FLOATS);
+      dz = c % S - r2; dy = (c / S) % S - r2; dx = c / (S * S) - r2;
+      b = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+      if (b < 0) atomicOr(err, 4u);
+    }
+    __syncwarp();     // the probe loops end at different iterations: reconverge before the long pair evaluation
+    if (act && b >= 0) {
+      float rb[REC_FLOATS];
+      const float4* src = reinterpret_cast<const float4*>(rec + (int64_t)b * REC_FLOATS);
 #pragma unroll
-        for (int qd = 0; qd < 4; qd++) { float4 t = __ldg(src + qd); rb[4 * qd] = t.x; rb[4 * qd + 1] = t.y; rb[4 * qd + 2] = t.z; rb[4 * qd + 3] = t.w; }
-        float w_ab, w_ba;
-        pair_weights(s_ra[w], rb, pp, w_ab, w_ba);
-        rows[my_row + done + lane] = make_uint2(__float_as_uint(w_ab), (row_cell(w_ab) << 18) | pack6(dx + r2, dy + r2, dz + r2));
-        const uint32_t slot = atomicAdd(&cursor[b], 1u);
-        rows[slot] = make_uint2(__float_as_uint(w_ba), (row_cell(w_ba) << 18) | pack6(r2 - dx, r2 - dy, r2 - dz));
-      }
+      for (int qd = 0; qd < 4; qd++) { float4 t = __ldg(src + qd); rb[4 * qd] = t.x; rb[4 * qd + 1] = t.y; rb[4 * qd + 2] = t.z; rb[4 * qd + 3] = t.w; }
+      float w_ab, w_ba;
+      pair_weights(s_ra[w], rb, pp, w_ab, w_ba);
+      const uint32_t ca = row_cell(w_ab), cb = row_cell(w_ba);
+      rows[my_row + done + lane] = make_uint4(__float_as_uint(w_ab), __float_as_uint(w_ba),
+                                              (min(ca, cb) << 18) | pack6(dx + r2, dy + r2, dz + r2), max(ca, cb));
     }
     done += cnt;
   };
@@ -335,11 +334,11 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
 // ---- rows ordered by weight cell: LSD radix sort (2 passes x 5 bits) of one row per warp in shared memory ----
 constexpr int RS2_WARPS = 4;
 __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __restrict__ row_off, int64_t nv, const uint32_t* __restrict__ list,
-                                                            uint32_t nlist, int cap, uint2* __restrict__ rows) {
+                                                            uint32_t nlist, int cap, uint4* __restrict__ rows) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint2* A = reinterpret_cast<uint2*>(smraw) + (size_t)w * 2 * cap;
-  uint2* B = A + cap;
+  uint4* A = reinterpret_cast<uint4*>(smraw) + (size_t)w * 2 * cap;
+  uint4* B = A + cap;
   __shared__ unsigned s_cnt[RS2_WARPS][32];
   int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
   if (list) { if (v >= (int64_t)nlist) return; v = list[v]; }
@@ -356,7 +355,7 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
       const int i = i0 + lane;
-      const unsigned d = i < len ? ((A[i].y >> shift) & 31u) : 0xffffu;
+      const unsigned d = i < len ? ((A[i].z >> shift) & 31u) : 0xffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
       __syncwarp();
@@ -368,9 +367,9 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
       const int i = i0 + lane;
-      uint2 e = make_uint2(0, 0);
+      uint4 e = make_uint4(0, 0, 0, 0);
       unsigned d = 0xffffu;
-      if (i < len) { e = A[i]; d = (e.y >> shift) & 31u; }
+      if (i < len) { e = A[i]; d = (e.z >> shift) & 31u; }
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       unsigned pos = 0;
       if (i < len) pos = s_cnt[w][d] + __popc(peers & lt);
@@ -379,57 +378,60 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
       if (i < len) B[pos] = e;
       __syncwarp();
     }
-    uint2* t = A; A = B; B = t;
+    uint4* t = A; A = B; B = t;
   }
   for (int i = lane; i < len; i += 32) rows[off + i] = A[i];
 }
 
-// ---- stage 5a: cutGraphSegmentation (VS.h:1913-2029) of one voxel per warp from the weight rows.
+// ---- stage 5a: cutGraphSegmentation (VS.h:1913-2029) of one voxel per warp (= per CTA) from the weight rows.
 //      The reference sorts all n^2 weights of the neighbourhood; the merge loop only ever acts on an entry whose two
 //      vertices lie in different segments, and the emitted segment (that of local vertex 0) is final once the next
 //      weight is <= thr(S0) = Int(S0) - k/|S0| (S0 rule, exact).  Here the warp walks the rows of its used neighbours
-//      in rounds of descending weight cells [c0, c1): an entry of row j is w(j -> partner at lattice offset d); it
-//      belongs to this local graph iff the partner lies inside the neighbourhood (offset table lookup), and it is staged
-//      iff the two vertices are in different segments.  Staged entries are sorted exactly (w desc, flat index asc) and
-//      merged like the reference does; the round size adapts to the number of staged entries.
+//      in rounds of descending weight cells [c0, c1): an entry of row j is the pair {j, partner at lattice offset d};
+//      it belongs to this local graph iff the partner lies inside the neighbourhood (offset table lookup), and its two
+//      directed weights are staged iff the two vertices are in different segments (the lighter direction waits in a small
+//      deferred list when its cell is not part of the round).  Staged entries are sorted exactly (w desc, flat index asc)
+//      and merged like the reference does; the round size adapts to the number of staged entries.
 //      Output: lattice-offset bit mask of the connect list (+ its size); units this kernel cannot handle (staging
-//      overflow inside one cell) go to the fallback list of the general kernel. ----
-constexpr int LR_WARPS = 4;
+//      overflow inside one cell, deferred list full) go to the fallback list of the general kernel. ----
 constexpr int LR_NCAP = 184;     // used neighbours of one voxel (MAX_NEIGH = 181)
 constexpr int LR_CS = 256;       // staging capacity (entries)
-constexpr int LR_TARGET = 28;    // staged entries aimed at per round (<= 32: sorted in registers)
-__host__ __device__ inline size_t lr_slice_bytes(int lbits, int mwords) {
-  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_mask (4 B) | C_f, s_nc (2 B) | s_seg, s_size, s_loc (1 B)
-  size_t b = (size_t)LR_CS * 4 + (size_t)LR_NCAP * 4 * 5 + (size_t)mwords * 4 + (size_t)LR_CS * 2 + (size_t)LR_NCAP * 2 +
-             (size_t)LR_NCAP * 2 + ((size_t)1 << (3 * lbits));
+constexpr int LR_TARGET = 40;    // staged entries aimed at per round (<= 64: sorted in registers)
+constexpr int LR_DEF = 16;       // deferred entries (lighter direction of a pair whose cells straddle a round boundary)
+__host__ __device__ inline size_t lr_smem_bytes(int lbits, int mwords) {
+  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_kn, s_mask, s_dw (4 B) | C_f, s_nc, s_df (2 B) | s_seg, s_size, s_loc (1 B)
+  size_t b = (size_t)LR_CS * 4 + (size_t)LR_NCAP * 4 * 6 + (size_t)mwords * 4 + (size_t)LR_DEF * 4 + (size_t)LR_CS * 2 + (size_t)LR_NCAP * 2 +
+             (size_t)LR_DEF * 4 + (size_t)LR_NCAP * 2 + ((size_t)1 << (3 * lbits));
   return (b + 15) & ~(size_t)15;
 }
-__global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
-                                                                     const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
-                                                                     const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords,
-                                                                     const uint32_t* __restrict__ row_off, const uint2* __restrict__ rows,
-                                                                     const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
-                                                                     uint32_t* __restrict__ conn_mask, uint32_t* __restrict__ fallback,
-                                                                     uint32_t* __restrict__ fallback_count, int force_fb_mod,
-                                                                     unsigned long long* __restrict__ dbg) {
+__global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
+                                                            const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
+                                                            const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords,
+                                                            const uint32_t* __restrict__ row_off, const uint4* __restrict__ rows,
+                                                            const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
+                                                            uint32_t* __restrict__ conn_mask, uint32_t* __restrict__ fallback,
+                                                            uint32_t* __restrict__ fallback_count, int force_fb_mod,
+                                                            unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const int64_t u = first + (int64_t)blockIdx.x * LR_WARPS + wq;
+  const int lane = threadIdx.x;
+  const int64_t u = first + (int64_t)blockIdx.x;
   if (u >= last) return;
-  unsigned char* base = smraw + (size_t)wq * lr_slice_bytes(lbits, mwords);
-  float* C_w = reinterpret_cast<float*>(base);                          // LR_CS
+  float* C_w = reinterpret_cast<float*>(smraw);                         // LR_CS
   float* s_thr = C_w + LR_CS;                                           // NCAP: Int(C) - k/|C| of segment C
-  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_thr + LR_NCAP);      // NCAP: pack6(o + rho) of the vertex
+  float* s_kn = s_thr + LR_NCAP;                                        // NCAP: k / n, n = 1 .. NCAP
+  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_kn + LR_NCAP);       // NCAP: pack6(o + rho) of the vertex
   uint32_t* s_cur = s_off6 + LR_NCAP;                                   // NCAP: next unread entry of the vertex's row
   uint32_t* s_end = s_cur + LR_NCAP;                                    // NCAP
   uint32_t* s_sav = s_end + LR_NCAP;                                    // NCAP: cursors at the start of the round
   uint32_t* s_mask = s_sav + LR_NCAP;                                   // mwords: output mask
-  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_mask + mwords);   // LR_CS
+  float* s_dw = reinterpret_cast<float*>(s_mask + mwords);              // LR_DEF: deferred weights
+  unsigned short* C_f = reinterpret_cast<unsigned short*>(s_dw + LR_DEF);     // LR_CS
   unsigned short* s_nc = C_f + LR_CS;                                   // NCAP: cell of the next unread entry (ROW_CELLS = exhausted)
-  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_nc + LR_NCAP);    // NCAP
+  unsigned short* s_df = s_nc + LR_NCAP;                                // LR_DEF x 2: deferred (flat index, cell)
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_df + 2 * LR_DEF); // NCAP
   unsigned char* s_size = s_seg + LR_NCAP;                              // NCAP
   unsigned char* s_loc = s_size + LR_NCAP;                              // 1 << 3*lbits: lattice offset -> local vertex, 0xff = none
-  __shared__ int s_cnt[LR_WARPS];
+  __shared__ int s_cnt, s_ndef;
   const uint32_t lt = (1u << lane) - 1u;
   const int nloc = 1 << (3 * lbits);
   const uint32_t lmask = (1u << lbits) - 1u;
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
     return;
   }
   for (int i = lane; i < nloc / 4; i += 32) reinterpret_cast<uint32_t*>(s_loc)[i] = 0xffffffffu;
+  if (lane == 0) s_ndef = 0;
   __syncwarp();
   const uint32_t off = adj_off[u];
   const int n = (int)(adj_off[u + 1] - off);
@@ -468,8 +471,9 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
         s_loc[ox | (oy << lbits) | (oz << (2 * lbits))] = (unsigned char)j;
         const uint32_t r0 = __ldg(row_off + gq), r1 = __ldg(row_off + gq + 1);
         s_cur[j] = r0; s_end[j] = r1;
-        s_nc[j] = r0 < r1 ? (unsigned short)(__ldg(&rows[r0].y) >> 18) : (unsigned short)ROW_CELLS;
+        s_nc[j] = r0 < r1 ? (unsigned short)(__ldg(&rows[r0].z) >> 18) : (unsigned short)ROW_CELLS;
         s_seg[j] = (unsigned char)j; s_size[j] = 1; s_thr[j] = 1.0f - k / 1.0f;
+        s_kn[j] = k / (float)(j + 1);        // k / |C| of the merge threshold (VS.h:1963: float / int)
       }
     }
     nv += __popc(bal);
@@ -480,6 +484,8 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
   if (force_fb_mod > 0 && (u % force_fb_mod) == 0) to_fallback = true;   // test knob VGS_B200_FORCE_FALLBACK
   int nseg = nv;
   bool stop = false;
+  // one batch of <= 32 entries in descending order, one per lane: the first mergeable entry merges,
+  // the later ones are re-evaluated against the new state (cutGraphSegmentation VS.h:1955-2001)
   auto merge_batch = [&](float w, int f, bool valid) {
     const int v1 = f >> 8, v2 = f & 255;
     uint32_t todo = __ballot_sync(0xffffffffu, valid);
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
       for (int v = lane; v < nv; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
       if (lane == 0) {
         const int nsz = (int)s_size[keepl] + (int)s_size[drop];
-        s_thr[keepl] = wl - k / (float)nsz; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
+        s_thr[keepl] = wl - s_kn[nsz - 1]; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
       }
       nseg--;
       __syncwarp();
@@ -521,10 +527,12 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
     c0 = __reduce_min_sync(0xffffffffu, c0);
     int span = 4;
     while (!stop && c0 < ROW_CELLS) {
-      // S0 rule on the cell bound: every unread entry has a weight <= row_cell_upper(c0)
+      // S0 rule on the cell bound: every unread or deferred entry has a weight <= row_cell_upper(c0)
       if (!(row_cell_upper(c0) > s_thr[s_seg[0]])) break;
       const int c1 = min(ROW_CELLS, c0 + span);
-      if (lane == 0) s_cnt[wq] = 0;
+      const int ndef0 = s_ndef;
+      __syncwarp();
+      if (lane == 0) s_cnt = 0;
       __syncwarp();
       int cmin = ROW_CELLS;
       for (int j = lane; j < nv; j += 32) {
@@ -536,18 +544,28 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
         const uint32_t oj = s_off6[j];
         const int sj = s_seg[j];
         while (true) {
-          const uint2 en = __ldg(&rows[c]);
-          if ((int)(en.y >> 18) >= c1) { nc = (int)(en.y >> 18); break; }
+          const uint4 en = __ldg(&rows[c]);
+          if ((int)(en.z >> 18) >= c1) { nc = (int)(en.z >> 18); break; }
           c++;
-          const uint32_t sum = oj + (en.y & 0x3ffffu);
+          const uint32_t sum = oj + (en.z & 0x3ffffu);
           const bool inside = (((sum + add_hi) & G) == 0u) && ((((sum | G) - sub_lo) & G) == G);
           if (inside) {
             const uint32_t p = sum - sub_lo;
             const int i = s_loc[(p & lmask) | (((p >> 6) & lmask) << lbits) | (((p >> 12) & lmask) << (2 * lbits))];
             if (i != 0xff && s_seg[i] != sj) {
-              const int slot = atomicAdd(&s_cnt[wq], 1);
-              // entry (row j, col i) = weight(idx[j] -> idx[i]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
-              if (slot < LR_CS) { C_w[slot] = __uint_as_float(en.x); C_f[slot] = (unsigned short)((i << 8) | j); }
+              // entry (row a, col b) = weight(idx[a] -> idx[b]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
+              const float w_ji = __uint_as_float(en.x), w_ij = __uint_as_float(en.y);
+              const unsigned short f_ji = (unsigned short)((i << 8) | j), f_ij = (unsigned short)((j << 8) | i);
+              if ((int)en.w < c1) {       // both directions belong to this round
+                const int slot = atomicAdd(&s_cnt, 2);
+                if (slot + 1 < LR_CS) { C_w[slot] = w_ji; C_f[slot] = f_ji; C_w[slot + 1] = w_ij; C_f[slot + 1] = f_ij; }
+              } else {                    // the lighter direction waits for its cell
+                const bool ji_heavy = row_cell(w_ji) <= row_cell(w_ij);
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < LR_CS) { C_w[slot] = ji_heavy ? w_ji : w_ij; C_f[slot] = ji_heavy ? f_ji : f_ij; }
+                const int ds = atomicAdd(&s_ndef, 1);
+                if (ds < LR_DEF) { s_dw[ds] = ji_heavy ? w_ij : w_ji; s_df[2 * ds] = ji_heavy ? f_ij : f_ji; s_df[2 * ds + 1] = (unsigned short)en.w; }
+              }
             }
           }
           if (c >= e) { nc = ROW_CELLS; break; }
@@ -557,37 +575,77 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
         cmin = min(cmin, nc);
       }
       __syncwarp();
-      const int kept = s_cnt[wq];
+      if (s_ndef > LR_DEF) { to_fallback = true; break; }
+      // deferred entries whose cell has come up join the round (those added in this round have cells >= c1)
+      int took_cell = -1;     // cell of the deferred entry this lane consumed in this round (for a roll-back)
+      {
+        const int nd = min(s_ndef, LR_DEF);
+        if (lane < nd) {
+          const int dc = (int)s_df[2 * lane + 1];
+          if (lane < ndef0 && dc < c1) {
+            const int f = (int)s_df[2 * lane];
+            if (s_seg[f >> 8] != s_seg[f & 255]) {
+              const int slot = atomicAdd(&s_cnt, 1);
+              if (slot < LR_CS) { C_w[slot] = s_dw[lane]; C_f[slot] = (unsigned short)f; }
+            }
+            took_cell = dc;
+            s_df[2 * lane + 1] = (unsigned short)0xffff;     // consumed (kept in place: the list is tiny)
+          } else if (dc != 0xffff) cmin = min(cmin, dc);     // still waiting: the next round must not start behind it
+        }
+      }
+      __syncwarp();
+      const int kept = s_cnt;
       if (kept > LR_CS) {
         if (span == 1) { to_fallback = true; break; }       // one cell alone overflows the staging buffer
-        // roll the cursors back and retry with a narrower round
+        // roll the cursors and the deferred list back and retry with a narrower round
         for (int j = lane; j < nv; j += 32) {
           const uint32_t sv = s_sav[j];
-          if (s_cur[j] != sv) { s_cur[j] = sv; s_nc[j] = (unsigned short)(__ldg(&rows[sv].y) >> 18); }
+          if (s_cur[j] != sv) { s_cur[j] = sv; s_nc[j] = (unsigned short)(__ldg(&rows[sv].z) >> 18); }
         }
+        if (took_cell >= 0) s_df[2 * lane + 1] = (unsigned short)took_cell;
+        if (lane == 0) s_ndef = ndef0;
         __syncwarp();
         span = max(1, span / 4);
         continue;
       }
       if (dbg && lane == 0) { atomicAdd(&dbg[0], 1ull); atomicAdd(&dbg[2], (unsigned long long)kept); }
       if (kept > 0) {
-        if (kept <= 32) {
-          float rw = lane < kept ? C_w[lane] : -1.0f;
-          int rf = lane < kept ? (int)C_f[lane] : 0xffff;
-#pragma unroll
-          for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
+        if (kept <= 64) {
+          // two entries per lane: bitonic sort across the warp in registers, (w desc, packed index asc)
+          float w0 = lane < kept ? C_w[lane] : -1.0f, w1 = lane + 32 < kept ? C_w[lane + 32] : -1.0f;
+          int f0 = lane < kept ? (int)C_f[lane] : 0xffff, f1 = lane + 32 < kept ? (int)C_f[lane + 32] : 0xffff;
+          auto before = [](float wa, int fa, float wb, int fb) { return (wa > wb) || (wa == wb && fa < fb); };
+          const int nreg = kept <= 32 ? 1 : 2;
+          const int top = nreg == 1 ? 32 : 64;
+#pragma unroll 1
+          for (int kk = 2; kk <= top; kk <<= 1) {
+#pragma unroll 1
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-              const float wo = __shfl_xor_sync(0xffffffffu, rw, jj);
-              const int fo = __shfl_xor_sync(0xffffffffu, rf, jj);
-              const bool other_first = (wo > rw) || (wo == rw && fo < rf);
-              const bool up = (lane & kk) == 0, lower = (lane & jj) == 0;
-              if ((up == lower) ? other_first : !other_first) { rw = wo; rf = fo; }
+              if (jj == 32) {      // partner = the other register of the same lane (element index lane + 32); kk == 64: ascending run
+                if (!before(w0, f0, w1, f1)) { const float tw = w0; w0 = w1; w1 = tw; const int tf = f0; f0 = f1; f1 = tf; }
+              } else {
+                const bool lower = (lane & jj) == 0;
+                {
+                  const float wo = __shfl_xor_sync(0xffffffffu, w0, jj);
+                  const int fo = __shfl_xor_sync(0xffffffffu, f0, jj);
+                  const bool up = (lane & kk) == 0;          // element index = lane
+                  const bool other_first = before(wo, fo, w0, f0);
+                  if ((up == lower) ? other_first : !other_first) { w0 = wo; f0 = fo; }
+                }
+                if (nreg == 2) {
+                  const float wo = __shfl_xor_sync(0xffffffffu, w1, jj);
+                  const int fo = __shfl_xor_sync(0xffffffffu, f1, jj);
+                  const bool up = ((lane + 32) & kk) == 0;   // element index = lane + 32
+                  const bool other_first = before(wo, fo, w1, f1);
+                  if ((up == lower) ? other_first : !other_first) { w1 = wo; f1 = fo; }
+                }
+              }
             }
           }
-          merge_batch(rw, rf, lane < kept);
+          merge_batch(w0, f0, lane < kept);
+          if (nreg == 2 && !stop) merge_batch(w1, f1, lane + 32 < kept);
         } else {
-          int P = 64;
+          int P = 128;
           while (P < kept) P <<= 1;
           for (int i = kept + lane; i < P; i += 32) { C_w[i] = -1.0f; C_f[i] = 0xffff; }
           __syncwarp();
@@ -613,7 +671,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 8) k_local_graph_rows(int64_t f
           }
         }
       }
-      // next round: first cell that still holds an unread entry; size adapted to the yield of this one
+      // next round: first cell that still holds an unread / deferred entry; size adapted to the yield of this one
       c0 = __reduce_min_sync(0xffffffffu, cmin);
       span = min(256, max(1, (span * (LR_TARGET + 4)) / (kept + 4)));
     }
