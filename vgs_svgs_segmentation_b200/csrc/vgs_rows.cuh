@@ -11,6 +11,7 @@
 //                                       once the next weight is <= Int(S0) - k/|S0|)
 //   stage 5b k_mutual_mask            : crossValidation (VS.h:2111-2179) on lattice-offset bit masks
 #pragma once
+#include <type_traits>
 #include "vgs_kernels.cuh"
 
 namespace vgs {
@@ -252,9 +253,9 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
 // ---- stage 4: weight rows.  One 16-byte entry per UNORDERED pair {a, b} of used voxels that can meet in a local graph,
 //      filed in the row of the voxel a whose offset to b is lexicographically positive:
 //        .x = w(a -> b)   .y = w(b -> a)   .z = cell(max weight) << 18 | pack6(d + r2c), d = key_b - key_a   .w = cell(min weight)
-//      cell(w) = floor((1 - w) * 1024) orders a row coarsely (k_rows_sort); the consumer sorts exactly inside the cells
+//      cell(w) = floor((1 - w) * 4096) orders a row coarsely (k_rows_sort); the consumer sorts exactly inside the cells
 //      it takes.  A row is written by one warp only: no atomics, no scattered stores. ----
-constexpr int ROW_CELLS = 1024;
+constexpr int ROW_CELLS = 4096;
 constexpr int ROWS_SHORT_CAP = 256;   // rows up to this length are sorted four per CTA; longer ones one per CTA
 __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
   // monotone non-increasing in w; NaN and w <= 0 fall into the last cell
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
   process(0, npend);
 }
 
-// ---- rows ordered by weight cell: LSD radix sort (2 passes x 5 bits) of one row per warp in shared memory ----
+// ---- rows ordered by weight cell: LSD radix sort (2 passes x 6 bits) of one row per warp in shared memory ----
 constexpr int RS2_WARPS = 4;
 __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __restrict__ row_off, int64_t nv, const uint32_t* __restrict__ list,
                                                             uint32_t nlist, int cap, uint4* __restrict__ rows) {
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint4* A = reinterpret_cast<uint4*>(smraw) + (size_t)w * 2 * cap;
   uint4* B = A + cap;
-  __shared__ unsigned s_cnt[RS2_WARPS][32];
+  __shared__ unsigned s_cnt[RS2_WARPS][64];
   int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
   if (list) { if (v >= (int64_t)nlist) return; v = list[v]; }
   else if (v >= nv) return;
@@ -350,26 +351,29 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
-    const int shift = 18 + 5 * pass;
-    s_cnt[w][lane] = 0;
+    const int shift = 18 + 6 * pass;
+    s_cnt[w][lane] = 0; s_cnt[w][lane + 32] = 0;
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
       const int i = i0 + lane;
-      const unsigned d = i < len ? ((A[i].z >> shift) & 31u) : 0xffffu;
+      const unsigned d = i < len ? ((A[i].z >> shift) & 63u) : 0xffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
       __syncwarp();
     }
-    const unsigned c = s_cnt[w][lane];
-    const unsigned inc = warp_incl_scan(c, lane);
-    __syncwarp();
-    s_cnt[w][lane] = inc - c;
+    {   // exclusive prefix sums over the 64 counters: lane owns bins 2*lane, 2*lane + 1
+      const unsigned c0 = s_cnt[w][2 * lane], c1 = s_cnt[w][2 * lane + 1];
+      const unsigned inc = warp_incl_scan(c0 + c1, lane);
+      __syncwarp();
+      s_cnt[w][2 * lane] = inc - c0 - c1;
+      s_cnt[w][2 * lane + 1] = inc - c1;
+    }
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
       const int i = i0 + lane;
       uint4 e = make_uint4(0, 0, 0, 0);
       unsigned d = 0xffffu;
-      if (i < len) { e = A[i]; d = (e.z >> shift) & 31u; }
+      if (i < len) { e = A[i]; d = (e.z >> shift) & 63u; }
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       unsigned pos = 0;
       if (i < len) pos = s_cnt[w][d] + __popc(peers & lt);
@@ -394,6 +398,40 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
 //      and merged like the reference does; the round size adapts to the number of staged entries.
 //      Output: lattice-offset bit mask of the connect list (+ its size); units this kernel cannot handle (staging
 //      overflow inside one cell, deferred list full) go to the fallback list of the general kernel. ----
+// bitonic sort of 32 * NR (weight, flat index) entries held NR per lane (element e = lane + 32 r) into the order
+// (w desc, f asc): shuffles for partner distances < 32, register swaps inside the lane above
+template <int NR>
+__device__ __forceinline__ void warp_bitonic(float (&w)[NR], int (&f)[NR], int lane) {
+  auto before = [](float wa, int fa, float wb, int fb) { return (wa > wb) || (wa == wb && fa < fb); };
+#pragma unroll 1
+  for (int kk = 2; kk <= 32 * NR; kk <<= 1) {
+#pragma unroll 1
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      if (jj >= 32) {
+        const int dr = jj >> 5;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          if ((r & dr) == 0) {
+            const bool up = ((32 * r) & kk) == 0;       // lane < 32 <= jj < kk: only the register index decides
+            const bool ok = up ? !before(w[r | dr], f[r | dr], w[r], f[r]) : !before(w[r], f[r], w[r | dr], f[r | dr]);
+            if (!ok) { const float tw = w[r]; w[r] = w[r | dr]; w[r | dr] = tw; const int tf = f[r]; f[r] = f[r | dr]; f[r | dr] = tf; }
+          }
+        }
+      } else {
+        const bool lower = (lane & jj) == 0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          const float wo = __shfl_xor_sync(0xffffffffu, w[r], jj);
+          const int fo = __shfl_xor_sync(0xffffffffu, f[r], jj);
+          const bool up = ((lane + 32 * r) & kk) == 0;
+          const bool other_first = before(wo, fo, w[r], f[r]);
+          if ((up == lower) ? other_first : !other_first) { w[r] = wo; f[r] = fo; }
+        }
+      }
+    }
+  }
+}
+
 constexpr int LR_NCAP = 184;     // used neighbours of one voxel (MAX_NEIGH = 181)
 constexpr int LR_CS = 256;       // staging capacity (entries)
 constexpr int LR_TARGET = 40;    // staged entries aimed at per round (<= 64: sorted in registers)
@@ -525,7 +563,7 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
     int c0 = ROW_CELLS;
     for (int j = lane; j < nv; j += 32) c0 = min(c0, (int)s_nc[j]);
     c0 = __reduce_min_sync(0xffffffffu, c0);
-    int span = 4;
+    int span = ROW_CELLS / 256;
     while (!stop && c0 < ROW_CELLS) {
       // S0 rule on the cell bound: every unread or deferred entry has a weight <= row_cell_upper(c0)
       if (!(row_cell_upper(c0) > s_thr[s_seg[0]])) break;
@@ -611,39 +649,22 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
       if (dbg && lane == 0) { atomicAdd(&dbg[0], 1ull); atomicAdd(&dbg[2], (unsigned long long)kept); }
       if (kept > 0) {
         if (kept <= 64) {
-          // two entries per lane: bitonic sort across the warp in registers, (w desc, packed index asc)
-          float w0 = lane < kept ? C_w[lane] : -1.0f, w1 = lane + 32 < kept ? C_w[lane + 32] : -1.0f;
-          int f0 = lane < kept ? (int)C_f[lane] : 0xffff, f1 = lane + 32 < kept ? (int)C_f[lane + 32] : 0xffff;
-          auto before = [](float wa, int fa, float wb, int fb) { return (wa > wb) || (wa == wb && fa < fb); };
-          const int nreg = kept <= 32 ? 1 : 2;
-          const int top = nreg == 1 ? 32 : 64;
-#pragma unroll 1
-          for (int kk = 2; kk <= top; kk <<= 1) {
-#pragma unroll 1
-            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-              if (jj == 32) {      // partner = the other register of the same lane (element index lane + 32); kk == 64: ascending run
-                if (!before(w0, f0, w1, f1)) { const float tw = w0; w0 = w1; w1 = tw; const int tf = f0; f0 = f1; f1 = tf; }
-              } else {
-                const bool lower = (lane & jj) == 0;
-                {
-                  const float wo = __shfl_xor_sync(0xffffffffu, w0, jj);
-                  const int fo = __shfl_xor_sync(0xffffffffu, f0, jj);
-                  const bool up = (lane & kk) == 0;          // element index = lane
-                  const bool other_first = before(wo, fo, w0, f0);
-                  if ((up == lower) ? other_first : !other_first) { w0 = wo; f0 = fo; }
-                }
-                if (nreg == 2) {
-                  const float wo = __shfl_xor_sync(0xffffffffu, w1, jj);
-                  const int fo = __shfl_xor_sync(0xffffffffu, f1, jj);
-                  const bool up = ((lane + 32) & kk) == 0;   // element index = lane + 32
-                  const bool other_first = before(wo, fo, w1, f1);
-                  if ((up == lower) ? other_first : !other_first) { w1 = wo; f1 = fo; }
-                }
-              }
+          // up to two entries per lane: bitonic sort across the warp in registers, (w desc, packed index asc)
+          auto run = [&](auto tag) {
+            constexpr int NR = decltype(tag)::value;
+            float w[NR]; int f[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+              const int e = lane + 32 * r;
+              w[r] = e < kept ? C_w[e] : -1.0f;
+              f[r] = e < kept ? (int)C_f[e] : 0xffff;
             }
-          }
-          merge_batch(w0, f0, lane < kept);
-          if (nreg == 2 && !stop) merge_batch(w1, f1, lane + 32 < kept);
+            warp_bitonic<NR>(w, f, lane);
+#pragma unroll
+            for (int r = 0; r < NR; r++) if (!stop && 32 * r < kept) merge_batch(w[r], f[r], lane + 32 * r < kept);
+          };
+          if (kept <= 32) run(std::integral_constant<int, 1>{});
+          else run(std::integral_constant<int, 2>{});
         } else {
           int P = 128;
           while (P < kept) P <<= 1;
@@ -673,7 +694,7 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
       }
       // next round: first cell that still holds an unread / deferred entry; size adapted to the yield of this one
       c0 = __reduce_min_sync(0xffffffffu, cmin);
-      span = min(256, max(1, (span * (LR_TARGET + 4)) / (kept + 4)));
+      span = min(ROW_CELLS / 4, max(1, (span * (LR_TARGET + 4)) / (kept + 4)));
     }
     if (dbg && lane == 0) { atomicAdd(&dbg[3], 1ull); atomicAdd(&dbg[5], (unsigned long long)nseg); atomicAdd(&dbg[6], (unsigned long long)nv); }
   }
