@@ -22,7 +22,10 @@ A "step" = one full segmentation of one synthetic scene through the C ABI of lib
 on the SAME scene with all host threads, and checks its labels against one run of the CUDA path when a GPU is present.
 
 N > 1 (torchrun, one rank per GPU): `--mode slabs` (default for VGS) segments ONE scene split into spatial slabs with halo
-voxels, cross-slab component merge over NCCL (strong scaling); `--mode replicas` runs one independent tile per rank.
+voxels, global PCL origin, closest-check rounds and cross-slab component merge over NCCL (vgs_group_run), and checks the
+labels against one single-GPU run of the whole scene.  site10m / town2m: the scene has N parts of the config's size on
+sqrt(N) times the extent (weak scaling, N = 1 is the single-GPU workload); urban100m: the same 100 M-point scene for every N
+(strong scaling).  `--mode replicas` runs one independent scene per rank (no exchange).
 """
 from __future__ import annotations
 
@@ -249,6 +252,7 @@ def main():
     ap.add_argument("--ref-points", type=int, default=0, help="--impl reference: 0 = the full scene of the config")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N>1 slabs: skip the comparison with one single-GPU run of the whole scene")
     ap.add_argument("--mode", default=None, choices=["slabs", "replicas"],
                     help="N>1: 'slabs' = ONE scene split into spatial slabs with halo voxels + cross-slab merge over NCCL (strong scaling); "
                          "'replicas' = one independent tile per rank (weak scaling, no exchange)")
@@ -278,7 +282,7 @@ def main():
     cfg = args.config
     cmode = CONFIGS[cfg]["mode"]
     pd = params_of(cfg)
-    mode = args.mode or "replicas"
+    mode = args.mode or ("slabs" if cmode == 0 else "replicas")
     slabs = mode == "slabs" and world > 1 and cmode == 0
 
     def barrier():
@@ -290,7 +294,7 @@ def main():
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")  # 512 MB > 126 MB L2
     if slabs:
         from vgs_svgs_segmentation_b200 import slabs as slabmod
-        out = slabmod.bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, make_scene, measured_peak, CONFIGS)
+        out = slabmod.bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, measured_peak, CONFIGS)
         if rank == 0:
             if not args.no_cpu:
                 out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample)

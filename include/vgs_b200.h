@@ -171,6 +171,42 @@ typedef struct vgs_kernel_timing {
 } vgs_kernel_timing;
 vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n);
 
+/* ---- ONE scene on several GPUs: spatial slabs of the voxel lattice + halo layers, cross-slab component merge
+ *      (DESIGN.md section 6).  The reference is single-process: segmentVoxelCloudWithGraphModel
+ *      (VS.h:372-421) on the whole cloud; a group reproduces ITS labels bit for bit — global PCL origin (growth epochs in
+ *      global insertion order), global voxel order for closestCheck (VS.h:2181-2303, incl. the COUNT slot read as a voxel
+ *      id, VS.h:2243), components merged over voxel keys.  VGS only.
+ *      Rank r holds the points [first_r, first_r + n_r) of the cloud (slices in rank order = index order) and gets
+ *      back the canonical labels of exactly those points (label = smallest GLOBAL point index of the cluster, -1 none).
+ *      Two transports: NCCL (one rank per process; libnccl.so.2 is bound at run time with dlopen) and a loopback group
+ *      (all ranks in this process on one device; exchanges are device copies) for single-GPU testing / tiling. ---- */
+typedef struct vgs_group_s* vgs_group;
+typedef struct vgs_group_counts {
+  int64_t n_ranks, n_points, n_tile_points /* owned + halo, all ranks */, n_tile_voxels, n_adjacency, n_singles,
+      n_clusters_exported, n_cross_pairs, octree_depth, halo, axis, origin_rounds, closest_rounds;
+  int64_t cuts[17];            /* slab r owns key[axis] in [cuts[r], cuts[r+1]) */
+  int64_t reserved[2];
+} vgs_group_counts;
+typedef struct vgs_group_timings {   /* CUDA-event milliseconds on the group's stream (this process) */
+  float origin_ms, cuts_ms, route_ms, tiles_ms, low_ms, closest_ms, components_ms, merge_ms, labels_ms, total_ms;
+  int64_t kernel_launches;
+  float reserved[4];
+} vgs_group_timings;
+/* rank 0 makes the 128-byte id (ncclGetUniqueId); the caller ships it to the other ranks (torch.distributed, MPI, a file) */
+vgs_status vgs_group_unique_id(void* id128);
+vgs_status vgs_group_create_nccl(vgs_group* out, const vgs_config* cfg, int nranks, int rank, const void* id128);
+vgs_status vgs_group_create_local(vgs_group* out, const vgs_config* cfg, int nranks);
+void vgs_group_destroy(vgs_group g);
+const char* vgs_group_last_error(vgs_group g);   /* g may be NULL: error of the last failed create */
+/* xyz / n / labels: one entry per LOCAL rank (1 for an NCCL group, nranks for a loopback group).  A collective call. */
+vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* xyz, const int64_t* n, int stride_bytes,
+                         int on_device, int32_t* const* labels);
+vgs_status vgs_group_get_counts(vgs_group g, vgs_group_counts* out);
+vgs_status vgs_group_get_timings(vgs_group g, vgs_group_timings* out);
+vgs_handle vgs_group_handle(vgs_group g, int local_rank);   /* the rank's handle: per-kernel timings / counts of its tile */
+/* host-only: the slab cuts the group derives from per-axis key histograms hist[axis * nbins + (key >> shift)] */
+vgs_status vgs_slab_choose_cuts(const uint64_t* hist, int nbins, int shift, int nranks, int* axis, int* cuts /* nranks + 1 */);
+
 #ifdef __cplusplus
 }
 #endif

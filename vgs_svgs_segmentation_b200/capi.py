@@ -53,6 +53,17 @@ class Counts(C.Structure):
                                          "closest_rounds", "max_neighbours")] + [("reserved", C.c_int64 * 2)]
 
 
+class GroupCounts(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_ranks", "n_points", "n_tile_points", "n_tile_voxels", "n_adjacency", "n_singles",
+                                         "n_clusters_exported", "n_cross_pairs", "octree_depth", "halo", "axis", "origin_rounds",
+                                         "closest_rounds")] + [("cuts", C.c_int64 * 17), ("reserved", C.c_int64 * 2)]
+
+
+class GroupTimings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("origin_ms", "cuts_ms", "route_ms", "tiles_ms", "low_ms", "closest_ms", "components_ms",
+                                         "merge_ms", "labels_ms", "total_ms")] + [("kernel_launches", C.c_int64), ("reserved", C.c_float * 4)]
+
+
 BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np.uint32), UNIT_CENTER=(4, np.float32),
              UNIT_OFFSETS=(5, np.int64), UNIT_POINTS=(6, np.int32), RECORDS=(7, np.float32), ADJ_OFFSETS=(11, np.int64),
              ADJ_IDX=(12, np.int32), CONN0_COUNT=(13, np.int32), CONN0_IDX=(14, np.int32), CONN1_COUNT=(15, np.int32),
@@ -61,7 +72,9 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
 EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
             "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_make_supervoxels_vccs", "vgs_get_supervoxel_labels", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
-            "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get", "vgs_kernel_timings"]
+            "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get", "vgs_kernel_timings",
+            "vgs_group_unique_id", "vgs_group_create_nccl", "vgs_group_create_local", "vgs_group_destroy", "vgs_group_last_error",
+            "vgs_group_run", "vgs_group_get_counts", "vgs_group_get_timings", "vgs_group_handle", "vgs_slab_choose_cuts"]
 
 _lib = None
 
@@ -101,8 +114,118 @@ def load():
         L.vgs_stage_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.vgs_debug_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]
         L.vgs_kernel_timings.argtypes = [C.c_void_p, C.POINTER(KernelTiming), C.POINTER(C.c_int)]
+        L.vgs_group_unique_id.argtypes = [C.c_void_p]
+        L.vgs_group_create_nccl.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_int, C.c_int, C.c_void_p]
+        L.vgs_group_create_local.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_int]
+        L.vgs_group_destroy.argtypes = [C.c_void_p]
+        L.vgs_group_last_error.restype = C.c_char_p
+        L.vgs_group_last_error.argtypes = [C.c_void_p]
+        L.vgs_group_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vgs_group_get_counts.argtypes = [C.c_void_p, C.POINTER(GroupCounts)]
+        L.vgs_group_get_timings.argtypes = [C.c_void_p, C.POINTER(GroupTimings)]
+        L.vgs_group_handle.restype = C.c_void_p
+        L.vgs_group_handle.argtypes = [C.c_void_p, C.c_int]
+        L.vgs_slab_choose_cuts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         _lib = L
     return _lib
+
+
+def choose_cuts(hist: np.ndarray, shift: int, nranks: int):
+    """host-only: (axis, cuts[nranks + 1]) the slab group derives from per-axis key histograms hist[3, nbins]"""
+    L = load()
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    assert hist.ndim == 2 and hist.shape[0] == 3
+    axis = C.c_int(0)
+    cuts = np.zeros(nranks + 1, np.int32)
+    st = L.vgs_slab_choose_cuts(hist.ctypes.data, hist.shape[1], shift, nranks, C.byref(axis), cuts.ctypes.data)
+    if st != 0:
+        raise VgsError(st, "vgs_slab_choose_cuts: bad argument")
+    return int(axis.value), cuts
+
+
+class Group:
+    """One scene on several ranks (vgs_group): `nccl_id` given -> NCCL group with ONE local rank (this process);
+    else a loopback group with `nranks` local ranks on one device."""
+
+    def __init__(self, nranks, rank=0, nccl_id: bytes | None = None, device=0, stream=None, leaf_order=0):
+        self.L = load()
+        self.g = C.c_void_p()
+        if stream == 0:
+            stream = 1
+        cfg = Config(VGS_MODE_VGS, device, stream, leaf_order)
+        if nccl_id is not None:
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            st = self.L.vgs_group_create_nccl(C.byref(self.g), C.byref(cfg), nranks, rank, buf)
+            self.nlocal = 1
+        else:
+            st = self.L.vgs_group_create_local(C.byref(self.g), C.byref(cfg), nranks)
+            self.nlocal = nranks
+        if st != 0:
+            raise VgsError(st, self.L.vgs_group_last_error(None).decode())
+        self.nranks = nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        L = load()
+        buf = C.create_string_buffer(128)
+        st = L.vgs_group_unique_id(buf)
+        if st != 0:
+            raise VgsError(st, L.vgs_group_last_error(None).decode())
+        return buf.raw
+
+    def close(self):
+        if self.g:
+            self.L.vgs_group_destroy(self.g)
+            self.g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise VgsError(st, self.L.vgs_group_last_error(self.g).decode())
+
+    def run_ptrs(self, params: Params, xyz_ptrs, ns, stride_bytes, on_device, label_ptrs):
+        """raw pointers, one per local rank"""
+        k = self.nlocal
+        assert len(xyz_ptrs) == k and len(ns) == k and len(label_ptrs) == k
+        xp = (C.c_void_p * k)(*[C.c_void_p(int(p)) for p in xyz_ptrs])
+        lp = (C.c_void_p * k)(*[C.c_void_p(int(p)) for p in label_ptrs])
+        nn = (C.c_int64 * k)(*[int(n) for n in ns])
+        self._ck(self.L.vgs_group_run(self.g, C.byref(params), xp, nn, stride_bytes, 1 if on_device else 0, lp))
+
+    def run(self, params: Params, slices):
+        """host numpy slices (one per local rank, in rank order) -> list of int32 label arrays"""
+        slices = [np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3) for x in slices]
+        labels = [np.empty(max(x.shape[0], 1), np.int32) for x in slices]
+        self.run_ptrs(params, [x.ctypes.data if x.shape[0] else 0 for x in slices], [x.shape[0] for x in slices], 12, False,
+                      [l.ctypes.data for l in labels])
+        return [l[:x.shape[0]] for l, x in zip(labels, slices)]
+
+    def counts(self) -> dict:
+        c = GroupCounts()
+        self._ck(self.L.vgs_group_get_counts(self.g, C.byref(c)))
+        d = {k: getattr(c, k) for k, _ in GroupCounts._fields_ if k not in ("reserved", "cuts")}
+        d["cuts"] = [int(c.cuts[i]) for i in range(self.nranks + 1)]
+        return d
+
+    def timings(self) -> dict:
+        t = GroupTimings()
+        self._ck(self.L.vgs_group_get_timings(self.g, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in GroupTimings._fields_ if k != "reserved"}
+
+    def handle(self, local_rank=0) -> "Handle":
+        """the rank's own handle (owned by the group): kernel_timings(), counts(), timings() of its tile"""
+        h = Handle.__new__(Handle)
+        h.L = self.L
+        h.h = C.c_void_p(self.L.vgs_group_handle(self.g, local_rank))
+        h.n = 0
+        h._keep = None
+        h.close = lambda: None          # not ours to destroy
+        return h
 
 
 def make_params(voxel_size=0.15, graph_size=0.5, sig_p=0.2, sig_n=0.2, sig_o=0.2, sig_e=0.2, sig_c=0.2, sig_w=2.0,

@@ -302,6 +302,42 @@ vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* 
   return VGS_OK;
 }
 
+// Growth epochs of PCL's dynamic bounding box: every point that falls outside the current box (in insertion order)
+// grows it and starts an epoch; later growth events shift the keys of earlier epochs (the old root becomes a child).
+// Shared by vgs_voxelize (one device) and the slab group (global insertion order over all ranks).
+struct OriginBuilder {
+  OctState st;
+  EpochTable ep;
+  std::vector<size_t> events_before;   // #growth events before each epoch started
+  void begin(double res) { st = OctState(); st.res = res; ep.n = 0; events_before.clear(); }
+  // the point with (global) index idx violates the current box
+  const char* add(long long idx, const float p[3]) {
+    st.adopt(p);
+    if (st.depth > 21) return "octree depth > 21 bits per axis (extent / voxel_size too large)";
+    if (ep.n >= MAX_EPOCHS) return "too many bounding-box growth epochs";
+    ep.viol[ep.n] = idx;
+    for (int a = 0; a < 3; a++) ep.mn[ep.n][a] = st.mn[a];
+    events_before.push_back(st.events.size());
+    ep.n++;
+    return nullptr;
+  }
+  void finish() {   // growth events after an epoch move its keys by 1 << depth_old on lowered axes
+    for (int e = 0; e < ep.n; e++) {
+      for (int a = 0; a < 3; a++) ep.shift[e][a] = 0;
+      for (size_t k = events_before[e]; k < st.events.size(); k++)
+        for (int a = 0; a < 3; a++)
+          if ((st.events[k].lowered >> a) & 1u) ep.shift[e][a] += 1u << st.events[k].depth_old;
+    }
+  }
+  void install(vgs_handle h) const {
+    h->ep = ep;
+    for (int a = 0; a < 3; a++) { h->box.mn[a] = st.mn[a]; h->box.mx[a] = st.mx[a]; }
+    for (int a = 0; a < 3; a++) { h->bb_f[a] = (float)st.mn[a]; h->bb_f[3 + a] = (float)st.mx[a]; }
+    h->have_geometry = false;
+    h->depth = (int)st.depth;
+  }
+};
+
 // Stage timers: CUDA events recorded on the handle's stream WITHOUT a host synchronisation (a sync per
 // stage costs a host round trip and exposes the step to host scheduling noise); the elapsed times are
 // read when somebody asks for them (vgs_stage_timings, end of vgs_run), after one synchronisation.
@@ -501,70 +537,17 @@ vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* labels, int32_
   return VGS_OK;
 }
 
-vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
-  if (!h) return VGS_ERR_INVALID;
-  if (!h->d_xyz) return h->fail(VGS_ERR_STATE, "vgs_voxelize: call vgs_set_points first");
-  if (!(voxel_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: voxel_size must be > 0");
-  CK(cudaSetDevice(h->device));
+// ---- stage 1: keys, sort, voxel table (the epoch table / box / depth of stage 0 are installed in the handle).
+//      gidx_w: the points are 16-byte records whose 4th word is the point's GLOBAL index (slab tiles). ----
+static vgs_status voxelize_sorted(vgs_handle h, int gidx_w) {
   const int64_t n = h->n;
-  h->voxel_size = voxel_size;
-  h->voxelized = false;
-  h->have_units = h->have_features = h->have_adj = h->have_segments = false;   // the sort buffers are shared
-  h->units_external = false;
-  CK(h->small.reserve(4096));
-
-  // ---- stage 0: PCL dynamic bounding box (origin) ----
-  OctState st;
-  st.res = (double)voxel_size;
-  EpochTable& ep = h->ep;
-  ep.n = 0;
-  std::vector<OctState::Ev> ev_at_epoch_end;
-  std::vector<size_t> events_before;  // #growth events before each epoch started
-  {
-    StageTimer t(h, &h->tm.origin_ms, 1);
-    KTimer kt(h, K_ORIGIN);
-    int64_t cursor = 0;
-    while (true) {
-      int64_t idx;
-      vgs_status s = find_next(h, cursor, st, &idx);
-      if (s) return s;
-      if (idx >= n) break;
-      float p[3];
-      CK(cudaMemcpyAsync(p, h->d_xyz + idx * h->stride, 12, cudaMemcpyDeviceToHost, h->stream));
-      CK(stream_wait(h->stream));
-      st.adopt(p);
-      if (st.depth > 21) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: octree depth > 21 bits per axis (extent / voxel_size too large)");
-      if (ep.n >= MAX_EPOCHS) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: too many bounding-box growth epochs");
-      ep.viol[ep.n] = idx;
-      for (int a = 0; a < 3; a++) ep.mn[ep.n][a] = st.mn[a];
-      events_before.push_back(st.events.size());
-      ep.n++;
-      cursor = idx + 1;
-    }
-    if (!st.defined) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: no finite point in the cloud");
-    // shifts: growth events after an epoch move its keys by 1<<depth_old on lowered axes
-    for (int e = 0; e < ep.n; e++) {
-      for (int a = 0; a < 3; a++) ep.shift[e][a] = 0;
-      for (size_t k = events_before[e]; k < st.events.size(); k++)
-        for (int a = 0; a < 3; a++)
-          if ((st.events[k].lowered >> a) & 1u) ep.shift[e][a] += 1u << st.events[k].depth_old;
-    }
-    kt.stop();
-    t.stop();
-  }
-  for (int a = 0; a < 3; a++) { h->box.mn[a] = st.mn[a]; h->box.mx[a] = st.mx[a]; }
-  for (int a = 0; a < 3; a++) { h->bb_f[a] = (float)st.mn[a]; h->bb_f[3 + a] = (float)st.mx[a]; }
-  h->have_geometry = false;
-  h->depth = (int)st.depth;
-
-  // ---- stage 1: keys, sort, voxel table ----
   {
     StageTimer t(h, &h->tm.voxelize_ms, 2);
     CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
     CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
     KTimer kq(h, K_QUANTISE);
-    LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, ep, st.res, h->depth,
-           h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr);
+    LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth,
+           h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr, gidx_w);
     kq.stop();
     uint64_t* ks; uint32_t* vs;
     KTimer ksrt(h, K_SORT);
@@ -606,6 +589,45 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   }
   h->voxelized = true;
   return VGS_OK;
+}
+
+vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
+  if (!h) return VGS_ERR_INVALID;
+  if (!h->d_xyz) return h->fail(VGS_ERR_STATE, "vgs_voxelize: call vgs_set_points first");
+  if (!(voxel_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: voxel_size must be > 0");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  h->voxel_size = voxel_size;
+  h->voxelized = false;
+  h->have_units = h->have_features = h->have_adj = h->have_segments = false;   // the sort buffers are shared
+  h->units_external = false;
+  CK(h->small.reserve(4096));
+
+  // ---- stage 0: PCL dynamic bounding box (origin) ----
+  OriginBuilder ob;
+  ob.begin((double)voxel_size);
+  {
+    StageTimer t(h, &h->tm.origin_ms, 1);
+    KTimer kt(h, K_ORIGIN);
+    int64_t cursor = 0;
+    while (true) {
+      int64_t idx;
+      vgs_status s = find_next(h, cursor, ob.st, &idx);
+      if (s) return s;
+      if (idx >= n) break;
+      float p[3];
+      CK(cudaMemcpyAsync(p, h->d_xyz + idx * h->stride, 12, cudaMemcpyDeviceToHost, h->stream));
+      CK(stream_wait(h->stream));
+      if (const char* why = ob.add(idx, p)) return h->fail(VGS_ERR_LIMIT, std::string("vgs_voxelize: ") + why);
+      cursor = idx + 1;
+    }
+    if (!ob.st.defined) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: no finite point in the cloud");
+    ob.finish();
+    kt.stop();
+    t.stop();
+  }
+  ob.install(h);
+  return voxelize_sorted(h, 0);
 }
 
 vgs_status vgs_get_bounding_box(vgs_handle h, double out6[6]) {
@@ -1327,6 +1349,25 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
   return VGS_OK;
 }
 
+// ---- stage 5b: mutual filter (crossValidation VS.h:2111-2179) ----
+static vgs_status stage_mutual(vgs_handle h) {
+  const int64_t nu = h->nu;
+  const size_t E = (size_t)h->n_adj;
+  CK(h->conn1_cnt.reserve((size_t)nu * 4)); CK(h->conn1_idx.reserve(E * 4 + 16));
+  StageTimer t(h, &h->tm.mutual_ms, 6);
+  KTimer km(h, K_MUTUAL);
+  if (h->conn0_is_mask)
+    LAUNCH(k_mutual_mask, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(),
+           h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(), nu, h->lgeo.rho, h->mwords, h->conn1_cnt.as<uint32_t>(),
+           h->conn1_idx.as<int32_t>());
+  else
+    LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
+           h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
+  km.stop();
+  t.stop();
+  return VGS_OK;
+}
+
 static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
@@ -1334,23 +1375,8 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
   gp.cut = cut_thred;
-  const size_t E = (size_t)h->n_adj;
-  CK(h->conn1_cnt.reserve((size_t)nu * 4)); CK(h->conn1_idx.reserve(E * 4 + 16));
   CK(h->attach.reserve((size_t)nu * 4)); CK(h->parent.reserve((size_t)nu * 4)); CK(h->root.reserve((size_t)nu * 4));
-  // ---- stage 5b: mutual filter ----
-  {
-    StageTimer t(h, &h->tm.mutual_ms, 6);
-    KTimer km(h, K_MUTUAL);
-    if (h->conn0_is_mask)
-      LAUNCH(k_mutual_mask, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(),
-             h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(), nu, h->lgeo.rho, h->mwords, h->conn1_cnt.as<uint32_t>(),
-             h->conn1_idx.as<int32_t>());
-    else
-      LAUNCH(k_mutual, (unsigned)cdiv(nu * 32, 128), 128, 0, h->adj_off.as<uint32_t>(), h->conn0_cnt.as<uint32_t>(),
-             h->conn0_idx.as<int32_t>(), nu, h->conn1_cnt.as<uint32_t>(), h->conn1_idx.as<int32_t>());
-    km.stop();
-    t.stop();
-  }
+  { vgs_status s_ = stage_mutual(h); if (s_) return s_; }
   // ---- stage 5c: closest check ----
   {
     StageTimer t(h, &h->tm.closest_ms, 7);
@@ -1643,3 +1669,5 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
 }
 
 }  // extern "C"
+
+#include "vgs_group.inl"

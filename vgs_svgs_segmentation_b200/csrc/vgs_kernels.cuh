@@ -63,12 +63,14 @@ __global__ void __launch_bounds__(256) k_find_outside(const float* __restrict__ 
 //      key.a = (unsigned)((p.a - min_a)/res) in double (genOctreeKeyforPoint).  12 B read, 12 B written. ----
 __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz, int stride, int64_t n, EpochTable ep, double res,
                                                 int depth, int descending, uint64_t* __restrict__ keys,
-                                                uint32_t* __restrict__ vals, uint32_t* __restrict__ key3_out) {
+                                                uint32_t* __restrict__ vals, uint32_t* __restrict__ key3_out, int gidx_w = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = xyz + i * stride;
   float x = p[0], y = p[1], z = p[2];
   vals[i] = (uint32_t)i;
+  // slab tiles (vgs_tiles.cuh): the insertion epoch is decided by the point's GLOBAL index, carried in the record
+  const long long gi = gidx_w ? (long long)__float_as_uint(p[3]) : (long long)i;
   const uint64_t mask = (depth * 3 >= 64) ? ~0ull : ((1ull << (3 * depth)) - 1ull);
   if (!finite3(x, y, z)) {
     keys[i] = 1ull << (3 * depth);  // sorts after every real key
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz,
     return;
   }
   int e = ep.n - 1;
-  while (e > 0 && i < ep.viol[e]) e--;
+  while (e > 0 && gi < ep.viol[e]) e--;
   uint32_t kx = (uint32_t)(((double)x - ep.mn[e][0]) / res) + ep.shift[e][0];
   uint32_t ky = (uint32_t)(((double)y - ep.mn[e][1]) / res) + ep.shift[e][1];
   uint32_t kz = (uint32_t)(((double)z - ep.mn[e][2]) / res) + ep.shift[e][2];
@@ -737,10 +739,13 @@ __global__ void __launch_bounds__(256) k_iota(int* __restrict__ p, int64_t n) {
 // partner), which already performs one union per unit without any atomics.  One warp per unit.
 __global__ void __launch_bounds__(128) k_cc_init(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1,
                                                const int32_t* __restrict__ idx1, const int32_t* __restrict__ attach, int64_t nu,
-                                               int* __restrict__ parent) {
+                                               int* __restrict__ parent, const uint8_t* __restrict__ own = nullptr) {
   const int lane = threadIdx.x & 31;
   int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= nu) return;
+  // slab tiles: only the links of OWNED voxels are trusted (halo voxels have truncated neighbourhoods); the partner
+  // of an owned single may be named by global id (>= 0x40000000): that link is merged across slabs by key
+  if (own && !(own[u] & 1)) { if (lane == 0) parent[u] = (int)u; return; }
   const uint32_t off = adj_off[u];
   const int c = (int)cnt1[u];
   int p = (int)u;
@@ -748,7 +753,7 @@ __global__ void __launch_bounds__(128) k_cc_init(const uint32_t* __restrict__ ad
   p = __reduce_min_sync(0xffffffffu, p);
   if (lane == 0) {
     const int a = attach[u];
-    if (a >= 0) p = min(p, a);
+    if (a >= 0 && (!own || a < 0x40000000)) p = min(p, a);
     parent[u] = p;
   }
 }
@@ -762,17 +767,18 @@ __global__ void __launch_bounds__(256) k_cc_jump(int* parent, int64_t n) {
 }
 __global__ void __launch_bounds__(128) k_cc_hook(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1,
                                                const int32_t* __restrict__ idx1, const int32_t* __restrict__ attach, int64_t nu,
-                                               int* parent) {
+                                               int* parent, const uint8_t* __restrict__ own = nullptr) {
   const int lane = threadIdx.x & 31;
   int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= nu) return;
+  if (own && !(own[u] & 1)) return;
   const uint32_t off = adj_off[u];
   const int c = (int)cnt1[u];
   for (int e = lane; e < c; e += 32) {
     int j = idx1[off + e];
     if (j > (int)u) uf_union(parent, (int)u, j);
   }
-  if (lane == 0) { int a = attach[u]; if (a >= 0) uf_union(parent, (int)u, a); }
+  if (lane == 0) { int a = attach[u]; if (a >= 0 && (!own || a < 0x40000000)) uf_union(parent, (int)u, a); }
 }
 __global__ void __launch_bounds__(256) k_cc_flatten(int* parent, int64_t n, int* __restrict__ root) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
