@@ -779,7 +779,7 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
       unsigned long long* d_np = t.tsmall.as<unsigned long long>() + 32;
       CK(cudaMemsetAsync(d_np, 0, 32, st));
       CK(t.pairs.reserve(((size_t)h->nu + (size_t)t.n_singles) * 16 + 16));
-      LAUNCH(k_pairs_export, (unsigned)cdiv(h->nu, 256), 256, 0, t.own.as<uint8_t>(), h->root.as<int>(), h->plainm.as<unsigned long long>(),
+      LAUNCH(k_pairs_export, (unsigned)cdiv(h->nu, 256), 256, 0, t.own.as<uint8_t>(), t.gidlo.as<uint16_t>(), h->root.as<int>(), h->plainm.as<unsigned long long>(),
              h->attach.as<int32_t>(), t.low_glob.as<LowEntry>(), h->nu, t.pairs.as<unsigned long long>(), d_np);
       CK(cudaMemcpyAsync(&mine[lr], d_np, 8, cudaMemcpyDeviceToHost, st));
       CK(stream_wait(st));

@@ -261,16 +261,18 @@ __global__ void k_low_attached(const LowEntry* __restrict__ low, int n_low, cons
 }
 
 // ---- cross-slab merge ----
-// (key(v), key(root(v))) of every shared voxel that is not its own root, and (key(i), key of the far partner) of the
-// owned singles attached through the count slot
-__global__ void __launch_bounds__(256) k_pairs_export(const uint8_t* __restrict__ own, const int* __restrict__ root,
+// (key(v), key(root(v))) of every voxel another rank can name and that is not its own root — the shared voxels, and the
+// owned ones among the globally first LOW_IDS voxels (named by neighbour counts) — plus (key(i), key of the far
+// partner) of the owned singles attached through the count slot
+__global__ void __launch_bounds__(256) k_pairs_export(const uint8_t* __restrict__ own, const uint16_t* __restrict__ gidlo, const int* __restrict__ root,
                                                     const unsigned long long* __restrict__ plain, const int32_t* __restrict__ attach,
                                                     const LowEntry* __restrict__ low, int64_t nu, unsigned long long* __restrict__ pairs,
                                                     unsigned long long* __restrict__ n_pairs) {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nu) return;
   const int r = root[u];
-  if ((own[u] & 2) && r != (int)u) {
+  const bool named = (own[u] & 2) || ((own[u] & 1) && gidlo[u] != 0xffff);
+  if (named && r != (int)u) {
     const unsigned long long s = atomicAdd(n_pairs, 1ull);
     pairs[2 * s] = plain[u]; pairs[2 * s + 1] = plain[r];
   }
