@@ -136,7 +136,8 @@ class ClockSampler:
 
 def make_scene(cfg, n_points=None, tile=0):
     """the config's scene at n_points (default: its full size); extents scale with sqrt(points) so the density stays that of
-    the full scene; tile > 0 shifts a replica (its own seed) by 80 m in x"""
+    the full scene; tile > 0 shifts a replica (its own seed) by 80 m in x.  The 100 M-point urban scene is defined as 8 parts of
+    12.5 M points (seeds 2..9) on the same 320 m ground, so that every GPU count segments the same cloud (slabs.scene_parts)."""
     from vgs_svgs_segmentation_b200 import scenes
     c = CONFIGS[cfg]
     n = int(n_points or c["points"])
@@ -144,7 +145,9 @@ def make_scene(cfg, n_points=None, tile=0):
         return scenes.construction_site(n, seed=1 + tile, extent=70.0 * (n / 10_000_000) ** 0.5, offset=(80.0 * tile, 0.0, 0.0))
     if c["scene"] == "town":
         return scenes.town(n, seed=20170610 + tile, extent=60.0 * (n / 2_000_000) ** 0.5, offset=(80.0 * tile, 0.0, 0.0))
-    return scenes.urban(n, seed=2 + tile, extent=320.0 * (n / 100_000_000) ** 0.5, offset=(400.0 * tile, 0.0, 0.0))
+    import numpy as np
+    ext = 320.0 * (n / 100_000_000) ** 0.5
+    return np.concatenate([scenes.urban(n // 8, seed=2 + j + 8 * tile, extent=ext, offset=(400.0 * tile, 0.0, 0.0)) for j in range(8)], axis=0)
 
 
 def params_of(cfg):

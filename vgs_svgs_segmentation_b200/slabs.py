@@ -71,6 +71,8 @@ def bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, measu
     nparts, ppp, extent = scene_parts(cfg, CONFIGS, world)
     if args.points:
         ppp = max(1, args.points // nparts)
+        if CONFIGS[cfg]["scene"] == "urban":
+            extent = 320.0 * (args.points / 100_000_000) ** 0.5
     assert nparts % world == 0, "the scene's parts must divide over the ranks"
     my_parts = list(range(rank * nparts // world, (rank + 1) * nparts // world))
     pts = np.concatenate([make_part(cfg, CONFIGS, j, ppp, extent) for j in my_parts], axis=0)
