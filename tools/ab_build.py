@@ -18,6 +18,7 @@ for path in paths:
     hs.append(capi.Handle(stream=torch.cuda.current_stream().cuda_stream))
 keys = ("total_ms", "graph_ms", "pair_cache_ms", "adjacency_ms", "mutual_ms", "components_ms", "labels_ms", "voxelize_ms")
 res = [{k: [] for k in keys} for _ in paths]
+kres = [{} for _ in paths]
 for it in range(13):
     for i, h in enumerate(hs):
         h.set_points_device(dev.data_ptr(), n, 12)
@@ -27,6 +28,10 @@ for it in range(13):
             t = h.timings()
             for k in keys:
                 res[i][k].append(t[k])
+            for kt in h.kernel_timings():
+                kres[i].setdefault(kt["name"].split(":")[1].strip()[:28], []).append(kt["ms"])
 for i, path in enumerate(paths):
     print(os.path.basename(path), {k: (round(statistics.median(v), 2), round(min(v), 2)) for k, v in res[i].items()})
+for i, path in enumerate(paths):
+    print(os.path.basename(path), "kernels", {k: round(statistics.median(v), 3) for k, v in kres[i].items()})
 print("labels equal:", all(bool((labs[0] == l).all()) for l in labs[1:]))

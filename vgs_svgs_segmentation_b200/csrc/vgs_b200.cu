@@ -110,6 +110,7 @@ struct vgs_context {
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph (general kernel; VGS_B200_NO_PAIR_CACHE)
   int cc_jumps = 6;                 // pointer-jumping rounds over the initial component forest
+  int lr_target = LR_TARGET;        // staged entries the local-graph rounds aim at (VGS_B200_LR_TARGET)
   int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
@@ -442,6 +443,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   if (const char* e_cs = getenv("VGS_B200_CLASS_STREAMS")) { int v = atoi(e_cs); if (v >= 1 && v <= 1 + vgs_context::N_AUX) h->class_streams = v; }
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   if (const char* e_ff = getenv("VGS_B200_FORCE_FALLBACK")) { int v = atoi(e_ff); if (v >= 1) h->force_fallback = v; }
+  if (const char* e_lt = getenv("VGS_B200_LR_TARGET")) { int v = atoi(e_lt); if (v >= 8 && v <= 200) h->lr_target = v; }
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
   {
@@ -1257,10 +1259,11 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(h->conn_mask.reserve((size_t)nu * mw * 4 + 16));
     CK(h->fallback.reserve((size_t)nu * 4 + 16));
     KTimer kgr(h, K_GRAPH_ROWS);
-    LAUNCH(k_local_graph_rows, (unsigned)nu, 32, lr_smem_bytes(h->lbits, mw), (int64_t)0, nu,
-           h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw,
+    const int ncap = (int)std::min<int64_t>(LR_NCAP, (h->max_n + 3) & ~(int64_t)3);   // vertices of the largest neighbourhood
+    LAUNCH(k_local_graph_rows, (unsigned)cdiv(nu, LR_WARPS), 32 * LR_WARPS, LR_WARPS * lr_smem_bytes(h->lbits, mw, ncap), (int64_t)0, nu,
+           h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw, ncap,
            h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
-           h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, d_dbg);
+           h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, h->lr_target, d_dbg);
     kgr.stop();
     uint32_t fe[2] = {0, 0};   // [0] = error bits of the fill kernels, [1] = units handed back
     CK(cudaMemcpyAsync(fe, d_err, 8, cudaMemcpyDeviceToHost, h->stream));

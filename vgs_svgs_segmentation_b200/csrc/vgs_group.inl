@@ -608,9 +608,14 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
       CK(t.low_att.reserve(LOW_IDS * 4)); CK(t.low_att_out.reserve(LOW_IDS * 4));
       CK(cudaMemsetAsync(t.low_loc.p, 0xff, (size_t)LOW_IDS * sizeof(LowEntry), st));     // absent entries sort last
       CK(cudaMemsetAsync(t.low_att.p, 0, LOW_IDS * 4, st));
-      if (h->nu > 0)
-        LAUNCH(k_low_export, 1, 32, 0, t.own.as<uint8_t>(), h->ukey.as<unsigned long long>(), h->plainm.as<unsigned long long>(), h->rec.as<float>(),
-               h->conn1_cnt.as<uint32_t>(), h->nu, t.low_loc.as<LowEntry>(), t.tsmall.as<int>());
+      if (h->nu > 0) {
+        CK(h->flags.reserve((size_t)h->nu * 4)); CK(h->scan.reserve((size_t)h->nu * 4));
+        LAUNCH(k_own_flags, (unsigned)cdiv(h->nu, 256), 256, 0, t.own.as<uint8_t>(), h->nu, h->flags.as<uint32_t>());
+        vgs_status s_ = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), h->nu, nullptr);
+        if (s_) return s_;
+        LAUNCH(k_low_export, (unsigned)cdiv(h->nu, 256), 256, 0, t.own.as<uint8_t>(), h->scan.as<uint32_t>(), h->ukey.as<unsigned long long>(),
+               h->plainm.as<unsigned long long>(), h->rec.as<float>(), h->conn1_cnt.as<uint32_t>(), h->nu, t.low_loc.as<LowEntry>());
+      }
       sp[lr] = t.low_loc.p; rp[lr] = t.low_all.p;
       return VGS_OK;
     });

@@ -408,13 +408,18 @@ __device__ __forceinline__ void warp_bitonic(float (&w)[NR], int (&f)[NR], int l
 #pragma unroll 1
     for (int jj = kk >> 1; jj > 0; jj >>= 1) {
       if (jj >= 32) {
-        const int dr = jj >> 5;
+        // partner = another register of the same lane; the register distance is a compile-time constant in every copy
 #pragma unroll
-        for (int r = 0; r < NR; r++) {
-          if ((r & dr) == 0) {
-            const bool up = ((32 * r) & kk) == 0;       // lane < 32 <= jj < kk: only the register index decides
-            const bool ok = up ? !before(w[r | dr], f[r | dr], w[r], f[r]) : !before(w[r], f[r], w[r | dr], f[r | dr]);
-            if (!ok) { const float tw = w[r]; w[r] = w[r | dr]; w[r | dr] = tw; const int tf = f[r]; f[r] = f[r | dr]; f[r | dr] = tf; }
+        for (int dr = 1; dr < NR; dr <<= 1) {
+          if (jj == 32 * dr) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+              if ((r & dr) == 0) {
+                const bool up = ((32 * r) & kk) == 0;       // lane < 32 <= jj < kk: only the register index decides
+                const bool ok = up ? !before(w[r | dr], f[r | dr], w[r], f[r]) : !before(w[r], f[r], w[r | dr], f[r | dr]);
+                if (!ok) { const float tw = w[r]; w[r] = w[r | dr]; w[r | dr] = tw; const int tf = f[r]; f[r] = f[r | dr]; f[r | dr] = tf; }
+              }
+            }
           }
         }
       } else {
@@ -436,40 +441,44 @@ constexpr int LR_NCAP = 184;     // used neighbours of one voxel (MAX_NEIGH = 18
 constexpr int LR_CS = 256;       // staging capacity (entries)
 constexpr int LR_TARGET = 40;    // staged entries aimed at per round (<= 64: sorted in registers)
 constexpr int LR_DEF = 16;       // deferred entries (lighter direction of a pair whose cells straddle a round boundary)
-__host__ __device__ inline size_t lr_smem_bytes(int lbits, int mwords) {
-  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_kn, s_mask, s_dw (4 B) | C_f, s_nc, s_df (2 B) | s_seg, s_size, s_loc (1 B)
-  size_t b = (size_t)LR_CS * 4 + (size_t)LR_NCAP * 4 * 6 + (size_t)mwords * 4 + (size_t)LR_DEF * 4 + (size_t)LR_CS * 2 + (size_t)LR_NCAP * 2 +
-             (size_t)LR_DEF * 4 + (size_t)LR_NCAP * 2 + ((size_t)1 << (3 * lbits));
+__host__ __device__ inline size_t lr_smem_bytes(int lbits, int mwords, int ncap) {
+  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_mask, s_dw (4 B) | C_f, s_nc, s_df (2 B) | s_seg, s_size, s_loc (1 B);
+  // ncap = vertex capacity (multiple of 4, >= the largest neighbourhood of the scene, <= LR_NCAP)
+  size_t b = (size_t)LR_CS * 4 + (size_t)ncap * 4 * 5 + (size_t)mwords * 4 + (size_t)LR_DEF * 4 + (size_t)LR_CS * 2 + (size_t)ncap * 2 +
+             (size_t)LR_DEF * 4 + (size_t)ncap * 2 + ((size_t)1 << (3 * lbits));
   return (b + 15) & ~(size_t)15;
 }
-__global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
+constexpr int LR_WARPS = 2;      // voxels per CTA (independent warps, no block barrier): lifts the 32-CTA-per-SM limit
+__global__ void __launch_bounds__(32 * LR_WARPS, 18) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
                                                             const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
-                                                            const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords,
+                                                            const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords, int ncap,
                                                             const uint32_t* __restrict__ row_off, const uint4* __restrict__ rows,
                                                             const float* __restrict__ wempty, uint32_t* __restrict__ conn_cnt,
                                                             uint32_t* __restrict__ conn_mask, uint32_t* __restrict__ fallback,
-                                                            uint32_t* __restrict__ fallback_count, int force_fb_mod,
+                                                            uint32_t* __restrict__ fallback_count, int force_fb_mod, int target,
                                                             unsigned long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int lane = threadIdx.x;
-  const int64_t u = first + (int64_t)blockIdx.x;
+  extern __shared__ __align__(16) unsigned char smraw_all[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t u = first + (int64_t)blockIdx.x * LR_WARPS + wid;
   if (u >= last) return;
+  unsigned char* smraw = smraw_all + (size_t)wid * lr_smem_bytes(lbits, mwords, ncap);
   float* C_w = reinterpret_cast<float*>(smraw);                         // LR_CS
-  float* s_thr = C_w + LR_CS;                                           // NCAP: Int(C) - k/|C| of segment C
-  float* s_kn = s_thr + LR_NCAP;                                        // NCAP: k / n, n = 1 .. NCAP
-  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_kn + LR_NCAP);       // NCAP: pack6(o + rho) of the vertex
-  uint32_t* s_cur = s_off6 + LR_NCAP;                                   // NCAP: next unread entry of the vertex's row
-  uint32_t* s_end = s_cur + LR_NCAP;                                    // NCAP
-  uint32_t* s_sav = s_end + LR_NCAP;                                    // NCAP: cursors at the start of the round
-  uint32_t* s_mask = s_sav + LR_NCAP;                                   // mwords: output mask
+  float* s_thr = C_w + LR_CS;                                           // ncap: Int(C) - k/|C| of segment C
+  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_thr + ncap);         // ncap: pack6(o + rho) of the vertex
+  uint32_t* s_cur = s_off6 + ncap;                                      // ncap: next unread entry of the vertex's row
+  uint32_t* s_end = s_cur + ncap;                                       // ncap
+  uint32_t* s_sav = s_end + ncap;                                       // ncap: cursors at the start of the round
+  uint32_t* s_mask = s_sav + ncap;                                      // mwords: output mask
   float* s_dw = reinterpret_cast<float*>(s_mask + mwords);              // LR_DEF: deferred weights
   unsigned short* C_f = reinterpret_cast<unsigned short*>(s_dw + LR_DEF);     // LR_CS
-  unsigned short* s_nc = C_f + LR_CS;                                   // NCAP: cell of the next unread entry (ROW_CELLS = exhausted)
-  unsigned short* s_df = s_nc + LR_NCAP;                                // LR_DEF x 2: deferred (flat index, cell)
-  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_df + 2 * LR_DEF); // NCAP
-  unsigned char* s_size = s_seg + LR_NCAP;                              // NCAP
-  unsigned char* s_loc = s_size + LR_NCAP;                              // 1 << 3*lbits: lattice offset -> local vertex, 0xff = none
-  __shared__ int s_cnt, s_ndef;
+  unsigned short* s_nc = C_f + LR_CS;                                   // ncap: cell of the next unread entry (ROW_CELLS = exhausted)
+  unsigned short* s_df = s_nc + ncap;                                   // LR_DEF x 2: deferred (flat index, cell)
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_df + 2 * LR_DEF); // ncap
+  unsigned char* s_size = s_seg + ncap;                                 // ncap
+  unsigned char* s_loc = s_size + ncap;                                 // 1 << 3*lbits: lattice offset -> local vertex, 0xff = none
+  __shared__ int s_cnt_w[LR_WARPS], s_ndef_w[LR_WARPS];
+  int& s_cnt = s_cnt_w[wid];
+  int& s_ndef = s_ndef_w[wid];
   const uint32_t lt = (1u << lane) - 1u;
   const int nloc = 1 << (3 * lbits);
   const uint32_t lmask = (1u << lbits) - 1u;
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
     const uint32_t bal = __ballot_sync(0xffffffffu, us);
     if (us) {
       const int j = nv + __popc(bal & lt);
-      if (j < LR_NCAP) {
+      if (j < ncap) {
         const uint32_t ox = c5 & 31u, oy = (c5 >> 5) & 31u, oz = (c5 >> 10) & 31u;
         s_off6[j] = pack6((int)ox, (int)oy, (int)oz);
         s_loc[ox | (oy << lbits) | (oz << (2 * lbits))] = (unsigned char)j;
@@ -511,14 +520,13 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
         s_cur[j] = r0; s_end[j] = r1;
         s_nc[j] = r0 < r1 ? (unsigned short)(__ldg(&rows[r0].z) >> 18) : (unsigned short)ROW_CELLS;
         s_seg[j] = (unsigned char)j; s_size[j] = 1; s_thr[j] = 1.0f - k / 1.0f;
-        s_kn[j] = k / (float)(j + 1);        // k / |C| of the merge threshold (VS.h:1963: float / int)
       }
     }
     nv += __popc(bal);
   }
   __syncwarp();
   const float lb = (float)(1.0 - 2.0 * (double)k + (double)k / (double)n - 4e-7 * (double)(n + 8));
-  bool to_fallback = (wempty[0] > lb) || nv > LR_NCAP;     // empty pairs could merge / too many vertices: general kernel
+  bool to_fallback = (wempty[0] > lb) || nv > ncap;     // empty pairs could merge / too many vertices: general kernel
   if (force_fb_mod > 0 && (u % force_fb_mod) == 0) to_fallback = true;   // test knob VGS_B200_FORCE_FALLBACK
   int nseg = nv;
   bool stop = false;
@@ -526,32 +534,34 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
   // the later ones are re-evaluated against the new state (cutGraphSegmentation VS.h:1955-2001)
   auto merge_batch = [&](float w, int f, bool valid) {
     const int v1 = f >> 8, v2 = f & 255;
-    uint32_t todo = __ballot_sync(0xffffffffu, valid);
+    // the lane's two segments live in registers and follow the merges of this batch
+    int sa = 0, sb = 0;
+    float m1 = 0.f, m2 = 0.f;
+    if (valid) { sa = s_seg[v1]; sb = s_seg[v2]; m1 = s_thr[sa]; m2 = s_thr[sb]; }
+    uint32_t todo = __ballot_sync(0xffffffffu, valid && sa != sb);
     while (todo) {
-      bool pred = false, a_wins = true;
-      int sa = 0, sb = 0;
-      if ((todo >> lane) & 1u) {
-        sa = s_seg[v1]; sb = s_seg[v2];
-        if (sa != sb) {
-          const float m1 = s_thr[sa], m2 = s_thr[sb];
-          a_wins = (m1 >= m2);
-          pred = w > (a_wins ? m1 : m2);
-        }
-      }
+      const bool mine = (todo >> lane) & 1u;
+      const bool a_wins = (m1 >= m2);
+      const bool pred = mine && w > (a_wins ? m1 : m2);
       const uint32_t bal = __ballot_sync(0xffffffffu, pred);
       if (!bal) break;
       const int Lm = __ffs(bal) - 1;
-      const int keepl = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
-      const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
+      const int packed = __shfl_sync(0xffffffffu, a_wins ? (sa | (sb << 8)) : (sb | (sa << 8)), Lm);
+      const int keepl = packed & 255, drop = packed >> 8;
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
       for (int v = lane; v < nv; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
-      if (lane == 0) {
-        const int nsz = (int)s_size[keepl] + (int)s_size[drop];
-        s_thr[keepl] = wl - s_kn[nsz - 1]; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0;
-      }
+      const int nsz = (int)s_size[keepl] + (int)s_size[drop];
+      const float nthr = wl - k / (float)nsz;        // Int(C) - k/|C| (VS.h:1963: float / int)
+      __syncwarp();
+      if (lane == 0) { s_thr[keepl] = nthr; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0; }
+      if (sa == drop) sa = keepl;
+      if (sb == drop) sb = keepl;
+      if (sa == keepl) m1 = nthr;
+      if (sb == keepl) m2 = nthr;
       nseg--;
       __syncwarp();
       todo &= ~((2u << Lm) - 1u);
+      todo &= __ballot_sync(0xffffffffu, sa != sb);
       if (nseg <= 1) { stop = true; break; }
     }
   };
@@ -581,10 +591,12 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
         const uint32_t e = s_end[j];
         const uint32_t oj = s_off6[j];
         const int sj = s_seg[j];
+        uint4 en = __ldg(&rows[c]);
         while (true) {
-          const uint4 en = __ldg(&rows[c]);
           if ((int)(en.z >> 18) >= c1) { nc = (int)(en.z >> 18); break; }
           c++;
+          uint4 nx = en;
+          if (c < e) nx = __ldg(&rows[c]);        // the next entry is in flight while this one is filed
           const uint32_t sum = oj + (en.z & 0x3ffffu);
           const bool inside = (((sum + add_hi) & G) == 0u) && ((((sum | G) - sub_lo) & G) == G);
           if (inside) {
@@ -607,6 +619,7 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
             }
           }
           if (c >= e) { nc = ROW_CELLS; break; }
+          en = nx;
         }
         s_cur[j] = c;
         s_nc[j] = (unsigned short)nc;
@@ -648,53 +661,35 @@ __global__ void __launch_bounds__(32, 24) k_local_graph_rows(int64_t first, int6
       }
       if (dbg && lane == 0) { atomicAdd(&dbg[0], 1ull); atomicAdd(&dbg[2], (unsigned long long)kept); }
       if (kept > 0) {
-        if (kept <= 64) {
-          // up to two entries per lane: bitonic sort across the warp in registers, (w desc, packed index asc)
-          auto run = [&](auto tag) {
-            constexpr int NR = decltype(tag)::value;
-            float w[NR]; int f[NR];
+        // entries sorted across the warp in registers, NR per lane, (w desc, packed index asc), written back in order
+        // and merged in batches of 32 (one copy of the merge loop: the kernel has to stay inside the instruction cache)
+        auto sort_regs = [&](auto tag) {
+          constexpr int NR = decltype(tag)::value;
+          float w[NR]; int f[NR];
 #pragma unroll
-            for (int r = 0; r < NR; r++) {
-              const int e = lane + 32 * r;
-              w[r] = e < kept ? C_w[e] : -1.0f;
-              f[r] = e < kept ? (int)C_f[e] : 0xffff;
-            }
-            warp_bitonic<NR>(w, f, lane);
+          for (int r = 0; r < NR; r++) {
+            const int e = lane + 32 * r;
+            w[r] = e < kept ? C_w[e] : -1.0f;
+            f[r] = e < kept ? (int)C_f[e] : 0xffff;
+          }
+          warp_bitonic<NR>(w, f, lane);
 #pragma unroll
-            for (int r = 0; r < NR; r++) if (!stop && 32 * r < kept) merge_batch(w[r], f[r], lane + 32 * r < kept);
-          };
-          if (kept <= 32) run(std::integral_constant<int, 1>{});
-          else run(std::integral_constant<int, 2>{});
-        } else {
-          int P = 128;
-          while (P < kept) P <<= 1;
-          for (int i = kept + lane; i < P; i += 32) { C_w[i] = -1.0f; C_f[i] = 0xffff; }
-          __syncwarp();
-          for (int kk = 2; kk <= P; kk <<= 1) {
-            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-              for (int i = lane; i < P; i += 32) {
-                const int x = i ^ jj;
-                if (x > i) {
-                  const float wi = C_w[i], wx = C_w[x];
-                  const unsigned short fi = C_f[i], fx = C_f[x];
-                  const bool x_before_i = (wx > wi) || (wx == wi && fx < fi);
-                  const bool up = (i & kk) == 0;
-                  if (x_before_i == up) { C_w[i] = wx; C_w[x] = wi; C_f[i] = fx; C_f[x] = fi; }
-                }
-              }
-              __syncwarp();
-            }
-          }
-          for (int bs = 0; bs < kept && !stop; bs += 32) {
-            const int e = bs + lane;
-            const bool valid = e < kept;
-            merge_batch(valid ? C_w[e] : 0.f, valid ? (int)C_f[e] : 0, valid);
-          }
+          for (int r = 0; r < NR; r++) { C_w[lane + 32 * r] = w[r]; C_f[lane + 32 * r] = (unsigned short)f[r]; }
+        };
+        if (kept <= 32) sort_regs(std::integral_constant<int, 1>{});
+        else if (kept <= 64) sort_regs(std::integral_constant<int, 2>{});
+        else if (kept <= 128) sort_regs(std::integral_constant<int, 4>{});
+        else sort_regs(std::integral_constant<int, 8>{});
+        __syncwarp();
+#pragma unroll 1
+        for (int bs = 0; bs < kept && !stop; bs += 32) {
+          const int e = bs + lane;
+          merge_batch(C_w[e], (int)C_f[e], e < kept);
         }
       }
       // next round: first cell that still holds an unread / deferred entry; size adapted to the yield of this one
       c0 = __reduce_min_sync(0xffffffffu, cmin);
-      span = min(ROW_CELLS / 4, max(1, (span * (LR_TARGET + 4)) / (kept + 4)));
+      span = min(ROW_CELLS / 4, max(1, (span * (target + 4)) / (kept + 4)));
     }
     if (dbg && lane == 0) { atomicAdd(&dbg[3], 1ull); atomicAdd(&dbg[5], (unsigned long long)nseg); atomicAdd(&dbg[6], (unsigned long long)nv); }
   }

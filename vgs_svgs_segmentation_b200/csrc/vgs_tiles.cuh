@@ -151,26 +151,23 @@ struct LowEntry {
   uint32_t cnt1;                 // connect-list size after the mutual filter
   int32_t local;                 // local id on the contributing rank
 };
-__global__ void k_low_export(const uint8_t* __restrict__ own, const unsigned long long* __restrict__ ukey, const unsigned long long* __restrict__ plain,
-                             const float* __restrict__ rec, const uint32_t* __restrict__ cnt1, int64_t nu, LowEntry* __restrict__ out,
-                             int* __restrict__ n_out) {
-  // single warp: walks the voxels in id order and keeps the first LOW_IDS owned ones
-  const int lane = threadIdx.x;
-  int got = 0;
-  for (int64_t b = 0; b < nu && got < LOW_IDS; b += 32) {
-    const int64_t u = b + lane;
-    const bool ok = u < nu && (own[u] & 1);
-    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-    const int pos = got + __popc(bal & ((1u << lane) - 1u));
-    if (ok && pos < LOW_IDS) {
-      LowEntry e;
-      e.sort_key = ukey[u]; e.plain = plain[u]; e.cnt1 = cnt1[u]; e.local = (int32_t)u;
-      for (int q = 0; q < REC_FLOATS; q++) e.rec[q] = rec[u * REC_FLOATS + q];
-      out[pos] = e;
-    }
-    got += __popc(bal);
-  }
-  if (lane == 0) *n_out = min(got, LOW_IDS);
+__global__ void __launch_bounds__(256) k_own_flags(const uint8_t* __restrict__ own, int64_t nu, uint32_t* __restrict__ flags) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < nu) flags[u] = own[u] & 1u;
+}
+// rank[u] = number of owned voxels before u (exclusive scan of the flags): the first LOW_IDS owned voxels are exported
+__global__ void __launch_bounds__(256) k_low_export(const uint8_t* __restrict__ own, const uint32_t* __restrict__ rank,
+                                                  const unsigned long long* __restrict__ ukey, const unsigned long long* __restrict__ plain,
+                                                  const float* __restrict__ rec, const uint32_t* __restrict__ cnt1, int64_t nu,
+                                                  LowEntry* __restrict__ out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu || !(own[u] & 1)) return;
+  const uint32_t pos = rank[u];
+  if (pos >= (uint32_t)LOW_IDS) return;
+  LowEntry e;
+  e.sort_key = ukey[u]; e.plain = plain[u]; e.cnt1 = cnt1[u]; e.local = (int32_t)u;
+  for (int q = 0; q < REC_FLOATS; q++) e.rec[q] = rec[u * REC_FLOATS + q];
+  out[pos] = e;
 }
 // gidlo[u] = global voxel id if u is one of the globally first LOW_IDS voxels, else 0xffff
 __global__ void k_low_import(const LowEntry* __restrict__ low, int n_low, const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
