@@ -180,6 +180,16 @@ def test_vgs_row_kernel_fallback_units(built_lib, monkeypatch):
     _compare_vgs(xyz, g, oracle.run(xyz, math=1))
 
 
+def test_vgs_hash_lookups_without_id_grid(built_lib, monkeypatch):
+    """VGS_B200_IDGRID_MB=0: neighbour ids through the Morton hash table (the path of scenes whose occupied key range is too
+    large for a dense id grid) — adjacency lists, weight rows and labels must not change."""
+    monkeypatch.setenv("VGS_B200_IDGRID_MB", "0")
+    xyz = _scene("town")
+    g = gpu_stages(xyz)
+    monkeypatch.delenv("VGS_B200_IDGRID_MB")
+    _compare_vgs(xyz, g, oracle.run(xyz, math=1))
+
+
 def test_vgs_single_stream_classes(built_lib, monkeypatch):
     """VGS_B200_CLASS_STREAMS=1 with the general kernel: all size-class launches on the handle's stream (default: 6
     streams, forked / joined with events); the connect lists do not depend on how the launches overlap."""

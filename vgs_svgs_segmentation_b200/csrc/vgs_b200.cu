@@ -103,7 +103,9 @@ struct vgs_context {
   BitGrid grid{};
   LatticeGeom lgeo{};
   DBuf d_adj_cols, d_pc_cols, tb_slot, tb_code5, tb_first, tb_last;
-  DBuf bm_all, bm_used, row_len, row_off, rows, long_rows, cstats, conn_mask;
+  DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
+  bool use_idgrid = false;
+  uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
   DBuf fallback, uflags, singles;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
@@ -443,6 +445,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   if (const char* e_cs = getenv("VGS_B200_CLASS_STREAMS")) { int v = atoi(e_cs); if (v >= 1 && v <= 1 + vgs_context::N_AUX) h->class_streams = v; }
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   if (const char* e_ff = getenv("VGS_B200_FORCE_FALLBACK")) { int v = atoi(e_ff); if (v >= 1) h->force_fallback = v; }
+  if (const char* e_ig = getenv("VGS_B200_IDGRID_MB")) { long long v = atoll(e_ig); if (v >= 0) h->idgrid_budget = (uint64_t)v << 20; }
   if (const char* e_lt = getenv("VGS_B200_LR_TARGET")) { int v = atoi(e_lt); if (v >= 8 && v <= 200) h->lr_target = v; }
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
@@ -481,7 +484,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->conn0_idx, &h->conn1_cnt, &h->conn1_idx, &h->attach, &h->parent, &h->root, &h->csize, &h->cminpt,
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
-                 &h->tb_last, &h->bm_all, &h->bm_used, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
+                 &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
                  &h->cstats, &h->conn_mask};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
@@ -948,7 +951,7 @@ static vgs_status build_lattice_tables(vgs_handle h, float graph_size, double no
   for (const int4& o : st) rho = std::max(rho, std::max(std::abs(o.x), std::max(std::abs(o.y), std::abs(o.z))));
   if (rho > 15) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
   const int nst = (int)st.size();
-  if (nst >= 65535 || adj_fill_smem(nst) > 200 * 1024) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
+  if (nst >= 65535 || adj_fill_smem(nst, 2 * rho + 1) > 200 * 1024) return h->fail(VGS_ERR_LIMIT, "vgs_find_adjacency: graph_size / voxel_size too large for the stencil search");
   auto columns = [](const std::vector<int4>& offs, int reach) {
     std::vector<int4> cols;
     for (const int4& o : offs) {
@@ -963,12 +966,17 @@ static vgs_status build_lattice_tables(vgs_handle h, float graph_size, double no
   h->adj_cols_host = columns(st, rho);
   // slot tables
   const int S = 2 * rho + 1;
-  std::vector<uint16_t> slot_of_code((size_t)S * S * S, 0xffff), code5(nst), cf(nst), cl(nst);
+  std::vector<uint32_t> code_lut((size_t)S * S * S);
+  std::vector<uint16_t> code5(nst), cf(nst), cl(nst);
+  for (int x = 0; x < S; x++)
+    for (int y = 0; y < S; y++)
+      for (int z = 0; z < S; z++) code_lut[(size_t)(x * S + y) * S + z] = 0xffffu | ((uint32_t)x << 16) | ((uint32_t)y << 21) | ((uint32_t)z << 26);
   // distance classes are only trusted when they are far apart compared with the float noise of dist2
   const double res = (double)h->voxel_size;
   const bool classes_ok = noise * 4.0 < res * res;
   for (int s = 0; s < nst; s++) {
-    slot_of_code[(size_t)((st[s].x + rho) * S + (st[s].y + rho)) * S + (st[s].z + rho)] = (uint16_t)s;
+    uint32_t& e = code_lut[(size_t)((st[s].x + rho) * S + (st[s].y + rho)) * S + (st[s].z + rho)];
+    e = (e & 0xffff0000u) | (uint32_t)s;
     code5[s] = (uint16_t)pack5(st[s].x + rho, st[s].y + rho, st[s].z + rho);
   }
   for (int s = 0; s < nst;) {
@@ -1005,9 +1013,9 @@ static vgs_status build_lattice_tables(vgs_handle h, float graph_size, double no
   CK(h->d_pc_cols.reserve(h->pc_cols_host.size() * sizeof(int4) + 16));
   if (!h->pc_cols_host.empty())
     CK(cudaMemcpyAsync(h->d_pc_cols.p, h->pc_cols_host.data(), h->pc_cols_host.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-  CK(h->tb_slot.reserve(slot_of_code.size() * 2 + 16)); CK(h->tb_code5.reserve((size_t)nst * 2 + 16));
+  CK(h->tb_slot.reserve(code_lut.size() * 4 + 16)); CK(h->tb_code5.reserve((size_t)nst * 2 + 16));
   CK(h->tb_first.reserve((size_t)nst * 2 + 16)); CK(h->tb_last.reserve((size_t)nst * 2 + 16));
-  CK(cudaMemcpyAsync(h->tb_slot.p, slot_of_code.data(), slot_of_code.size() * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->tb_slot.p, code_lut.data(), code_lut.size() * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->tb_code5.p, code5.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->tb_first.p, cf.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->tb_last.p, cl.data(), (size_t)nst * 2, cudaMemcpyHostToDevice, h->stream));
@@ -1125,8 +1133,16 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(cudaMemsetAsync(h->bm_used.p, 0, bm_bytes, h->stream));
   LAUNCH(k_bitgrid_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), h->uflags.as<uint8_t>(), nu, g, h->bm_all.as<uint32_t>(),
          h->bm_used.as<uint32_t>());
+  // dense id grid (4 B per cell) when it fits the budget: neighbour ids by one load instead of hash probes
+  h->use_idgrid = false;
+  if (nbits * 4 <= h->idgrid_budget) {
+    CK(h->idgrid.reserve((size_t)nbits * 4 + 64));
+    CK(cudaMemsetAsync(h->idgrid.p, 0xff, (size_t)nbits * 4, h->stream));
+    LAUNCH(k_idgrid_set, (unsigned)cdiv(nu, 256), 256, 0, h->key3.as<uint32_t>(), nu, g, h->idgrid.as<int32_t>());
+    h->use_idgrid = true;
+  }
   kgrid.stop();
-  h->grid_bytes = (int64_t)bm_bytes;
+  h->grid_bytes = (int64_t)bm_bytes + (h->use_idgrid ? (int64_t)nbits * 2 : 0);
   LatticeGeom& lg = h->lgeo;
   lg.res_f = res_f; lg.mnx = h->bb_f[0]; lg.mny = h->bb_f[1]; lg.mnz = h->bb_f[2];
   { double r = (double)graph_size; lg.r2 = (float)(r * r); }
@@ -1166,10 +1182,11 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
   CK(h->adj_idx.reserve((size_t)h->n_adj * 4 + 16)); CK(h->adj_code.reserve((size_t)h->n_adj * 2 + 16));
   unsigned* d_err = h->small.as<unsigned>() + 200;
   CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
-  AdjTables tb{h->tb_slot.as<uint16_t>(), h->tb_code5.as<uint16_t>(), h->tb_first.as<uint16_t>(), h->tb_last.as<uint16_t>()};
+  AdjTables tb{h->tb_slot.as<uint32_t>(), h->tb_code5.as<uint16_t>(), h->tb_first.as<uint16_t>(), h->tb_last.as<uint16_t>()};
+  const int32_t* d_idg = h->use_idgrid ? h->idgrid.as<int32_t>() : nullptr;
   KTimer kfill(h, K_ADJ_FILL);
-  LAUNCH(k_adj_fill, (unsigned)cdiv(nu, ADJ_WARPS), ADJ_WARPS * 32, adj_fill_smem(nst), h->key3.as<uint32_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
-         h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), tb, nst, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask,
+  LAUNCH(k_adj_fill, (unsigned)cdiv(nu, ADJ_WARPS), ADJ_WARPS * 32, adj_fill_smem(nst, 2 * rho + 1), h->key3.as<uint32_t>(), nu, lg, g, h->bm_all.as<uint32_t>(),
+         h->d_adj_cols.as<int4>(), (int)h->adj_cols_host.size(), tb, nst, d_idg, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask,
          h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), d_err);
   kfill.stop();
   h->have_adj = true;
@@ -1240,7 +1257,8 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       CK(h->rows.reserve((size_t)h->n_rows * 16 + 64));
       KTimer krf(h, K_ROWS_FILL);
       LAUNCH(k_rows_fill, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg, h->grid, h->bm_used.as<uint32_t>(),
-             h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, gp.pp,
+             h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->use_idgrid ? h->idgrid.as<int32_t>() : nullptr, h->tk.as<unsigned long long>(),
+             h->tv.as<uint32_t>(), h->hmask, gp.pp,
              h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_err);
       krf.stop();
       KTimer krs(h, K_ROWS_SORT);

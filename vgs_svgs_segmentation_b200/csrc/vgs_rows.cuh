@@ -151,44 +151,68 @@ __global__ void __launch_bounds__(256) k_adj_count(const uint32_t* __restrict__ 
   }
 }
 
+// dense voxel-id grid over the cells of the BitGrid (4 B per cell, -1 = empty): a neighbour's id is ONE load (a z-run of
+// the stencil shares a sector) instead of a Morton encode + hash probes.  Used when the grid fits the budget.
+__global__ void __launch_bounds__(256) k_idgrid_set(const uint32_t* __restrict__ key3, int64_t nv, BitGrid g, int32_t* __restrict__ idg) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  idg[bg_bit(g, (int)key3[3 * v], (int)key3[3 * v + 1], (int)key3[3 * v + 2])] = (int32_t)v;
+}
+__device__ __forceinline__ int voxel_at(const int32_t* __restrict__ idg, const BitGrid& g, const unsigned long long* __restrict__ tk,
+                                        const uint32_t* __restrict__ tv, uint64_t hmask, int x, int y, int z) {
+  if (idg) return __ldg(idg + bg_bit(g, x, y, z));
+  return hash_lookup(tk, tv, hmask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+}
+
 // ---- stage 3b: ordered neighbour lists straight into the CSR.  Candidates are keyed by their stencil slot (slots are
 //      sorted by integer distance class on the host); inside a class the order is FLANN's (float dist2, id), found by a
-//      rank count over the class only — the classes are >= res^2 apart, far above the float noise of dist2 (the host
-//      passes ONE class = a full rank sort when the cloud is so far from the origin that this is not certain).
-//      adj_code = 5-bit packed offset of the neighbour (pack5), used by the graph and mutual-filter kernels. ----
+//      rank count over the PRESENT members of the class only — the classes are >= res^2 apart, far above the float noise
+//      of dist2 (the host passes ONE class = a full rank sort when the cloud is so far from the origin that this is not
+//      certain).  adj_code = 5-bit packed offset of the neighbour (pack5), used by the graph and mutual-filter kernels. ----
 struct AdjTables {
-  const uint16_t* slot_of_code;   // ((dx+rho)*S + (dy+rho))*S + (dz+rho) -> stencil slot (0xffff = not in the stencil)
+  const uint32_t* code_lut;       // ((dx+rho)*S + (dy+rho))*S + (dz+rho) -> slot | (dx+rho) << 16 | (dy+rho) << 21 | (dz+rho) << 26 (slot 0xffff: none)
   const uint16_t* slot_code5;     // slot -> pack5(dx+rho, dy+rho, dz+rho)
   const uint16_t* cls_first;      // slot -> first slot of its distance class
   const uint16_t* cls_last;       // slot -> last slot of its distance class
 };
 constexpr int ADJ_WARPS = 4;
-__host__ __device__ inline size_t adj_fill_smem(int nst) {
-  const int nst8 = (nst + 7) & ~7;
-  return (size_t)ADJ_WARPS * ((size_t)nst8 * 10 + (size_t)(nst8 / 32 + 2) * 8);
+__host__ __device__ inline size_t adj_fill_smem(int nst, int S) {
+  const int nst8 = (nst + 7) & ~7, S4 = (S + 3) & ~3;
+  // per warp: slot keys + compacted keys (8 B), hit queue / present-slot list (2 B), presence words + counts, axis centres
+  return (size_t)ADJ_WARPS * ((size_t)nst8 * 18 + (size_t)(nst8 / 32 + 2) * 8 + (size_t)S4 * 12);
 }
 __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __restrict__ key3, int64_t nv, LatticeGeom lg, BitGrid g,
                                                            const uint32_t* __restrict__ bm_all, const int4* __restrict__ adj_cols,
-                                                           int n_adj_cols, AdjTables tb, int nst, const unsigned long long* __restrict__ tk,
-                                                           const uint32_t* __restrict__ tv, uint64_t hmask,
-                                                           const uint32_t* __restrict__ adj_off, int32_t* __restrict__ adj_idx,
+                                                           int n_adj_cols, AdjTables tb, int nst, const int32_t* __restrict__ idg,
+                                                           const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
+                                                           uint64_t hmask, const uint32_t* __restrict__ adj_off, int32_t* __restrict__ adj_idx,
                                                            uint16_t* __restrict__ adj_code, unsigned* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int rho = lg.rho, S = 2 * rho + 1, S4 = (S + 3) & ~3;
   const int nst8 = (nst + 7) & ~7, nblk = nst8 / 32 + 2;
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smraw) + (size_t)w * nst8;   // per slot: (d2 bits << 32) | id, ~0 = absent
-  unsigned short* q = reinterpret_cast<unsigned short*>(smraw + (size_t)ADJ_WARPS * nst8 * 8) + (size_t)w * nst8;   // hit queue
-  unsigned* sP = reinterpret_cast<unsigned*>(smraw + (size_t)ADJ_WARPS * nst8 * 10) + (size_t)w * nblk * 2;        // presence words
-  unsigned* sC = sP + nblk;                                                                                       // present slots before the word
+  unsigned char* base = smraw;
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(base) + (size_t)w * nst8;   // per slot: (d2 bits << 32) | id, ~0 = absent
+  base += (size_t)ADJ_WARPS * nst8 * 8;
+  unsigned long long* pkey = reinterpret_cast<unsigned long long*>(base) + (size_t)w * nst8;   // keys of the present slots, slot order
+  base += (size_t)ADJ_WARPS * nst8 * 8;
+  unsigned short* q = reinterpret_cast<unsigned short*>(base) + (size_t)w * nst8;             // hit queue, then present-slot list
+  base += (size_t)ADJ_WARPS * nst8 * 2;
+  unsigned* sP = reinterpret_cast<unsigned*>(base) + (size_t)w * nblk * 2;                     // presence words
+  unsigned* sC = sP + nblk;                                                                   // present slots before the word
+  base += (size_t)ADJ_WARPS * nblk * 8;
+  float* cax = reinterpret_cast<float*>(base) + (size_t)w * 3 * S4;                            // centre coordinates of the S cells per axis
   const int64_t v = (int64_t)blockIdx.x * ADJ_WARPS + w;
   if (v >= nv) return;
   const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
-  const float qx = centre_of(kx, lg.res_f, lg.mnx), qy = centre_of(ky, lg.res_f, lg.mny), qz = centre_of(kz, lg.res_f, lg.mnz);
-  const int rho = lg.rho, S = 2 * rho + 1;
+  for (int t = lane; t < 3 * S; t += 32) {
+    const int a = t / S, d = t - a * S;
+    cax[a * S4 + d] = a == 0 ? centre_of(kx - rho + d, lg.res_f, lg.mnx) : (a == 1 ? centre_of(ky - rho + d, lg.res_f, lg.mny) : centre_of(kz - rho + d, lg.res_f, lg.mnz));
+  }
   for (int s = lane; s < nst; s += 32) skey[s] = ~0ull;
   int nq = 0;
-  for (int base = 0; base < n_adj_cols; base += 32) {
-    const int ci = base + lane;
+  for (int b0 = 0; b0 < n_adj_cols; b0 += 32) {
+    const int ci = b0 + lane;
     uint32_t hits = 0;
     int cbase = 0;
     if (ci < n_adj_cols) {
@@ -207,46 +231,53 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
     nq += __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();
+  const float qx = cax[rho], qy = cax[S4 + rho], qz = cax[2 * S4 + rho];
   for (int e0 = 0; e0 < nq; e0 += 32) {
     const int e = e0 + lane;
-    int id = -1, c = 0;
+    int id = -1, slot = 0;
     float d2 = 0.f;
     if (e < nq) {
-      c = q[e];
-      const int dz = c % S - rho, dy = (c / S) % S - rho, dx = c / (S * S) - rho;
-      d2 = flann_d2(qx, qy, qz, centre_of(kx + dx, lg.res_f, lg.mnx), centre_of(ky + dy, lg.res_f, lg.mny), centre_of(kz + dz, lg.res_f, lg.mnz));
+      const uint32_t lut = __ldg(tb.code_lut + q[e]);
+      const int ox = (lut >> 16) & 31, oy = (lut >> 21) & 31, oz = (lut >> 26) & 31;
+      slot = (int)(lut & 0xffffu);
+      d2 = flann_d2(qx, qy, qz, cax[ox], cax[S4 + oy], cax[2 * S4 + oz]);
       if (d2 < lg.r2) {
-        id = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
-        if (id < 0) atomicOr(err, 1u);               // grid and hash table disagree: cannot happen
+        id = voxel_at(idg, g, tk, tv, hmask, kx + ox - rho, ky + oy - rho, kz + oz - rho);
+        if (id < 0) atomicOr(err, 1u);               // grid and voxel table disagree: cannot happen
       }
     }
     __syncwarp();     // the probe loops end at different iterations
-    if (id >= 0) skey[tb.slot_of_code[c]] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+    if (id >= 0) skey[slot] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
   }
   __syncwarp();
-  {   // presence words + running counts
-    unsigned run = 0;
-    for (int s0 = 0; s0 < nst; s0 += 32) {
-      const int s = s0 + lane;
-      const uint32_t bal = __ballot_sync(0xffffffffu, s < nst && skey[s] != ~0ull);
-      if (lane == 0) { sP[s0 >> 5] = bal; sC[s0 >> 5] = run; }
-      run += __popc(bal);
+  // presence words + running counts; present slots and their keys compacted in slot order
+  int np = 0;
+  for (int s0 = 0; s0 < nst; s0 += 32) {
+    const int s = s0 + lane;
+    const unsigned long long me = s < nst ? skey[s] : ~0ull;
+    const uint32_t bal = __ballot_sync(0xffffffffu, me != ~0ull);
+    if (lane == 0) { sP[s0 >> 5] = bal; sC[s0 >> 5] = (unsigned)np; }
+    if (me != ~0ull) {
+      const int p = np + __popc(bal & ((1u << lane) - 1u));
+      pkey[p] = me; q[p] = (unsigned short)s;
     }
+    np += __popc(bal);
   }
   __syncwarp();
   const uint32_t off = adj_off[v];
   const uint32_t total = adj_off[v + 1] - off;
-  for (int s = lane; s < nst; s += 32) {
-    const unsigned long long me = skey[s];
-    if (me == ~0ull) continue;
-    const int f = tb.cls_first[s], l = tb.cls_last[s];
+  if ((uint32_t)np != total) { if (lane == 0) atomicOr(err, 2u); return; }   // count and fill disagree: cannot happen
+  for (int e = lane; e < np; e += 32) {
+    const unsigned long long me = pkey[e];
+    const int s = q[e];
+    const int f = tb.cls_first[s], l = tb.cls_last[s] + 1;
+    // present members of the class = compacted entries [pb, pe)
+    const int pb = (int)sC[f >> 5] + __popc(sP[f >> 5] & ((1u << (f & 31)) - 1u));
+    const int pe = l >= nst ? np : (int)sC[l >> 5] + __popc(sP[l >> 5] & ((1u << (l & 31)) - 1u));
     int rank = 0;
-    for (int t = f; t <= l; t++) rank += skey[t] < me ? 1 : 0;     // absent slots hold ~0: never smaller
-    const uint32_t p = sC[f >> 5] + __popc(sP[f >> 5] & ((1u << (f & 31)) - 1u)) + (uint32_t)rank;
-    if (p < total) {
-      adj_idx[off + p] = (int32_t)(unsigned)(me & 0xffffffffull);
-      adj_code[off + p] = tb.slot_code5[s];
-    } else atomicOr(err, 2u);                       // count and fill disagree: cannot happen
+    for (int t = pb; t < pe; t++) rank += pkey[t] < me ? 1 : 0;
+    adj_idx[off + pb + rank] = (int32_t)(unsigned)(me & 0xffffffffull);
+    adj_code[off + pb + rank] = tb.slot_code5[s];
   }
 }
 
@@ -269,7 +300,8 @@ __device__ __forceinline__ float row_cell_upper(int c) { return (1.0f - (float)c
 constexpr int RF_QCAP = 32 + 32 * 32;   // a lane queues at most one z-run (<= 32 hits) per column step
 __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
                                                  BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
-                                                 const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv, uint64_t hmask,
+                                                 const int32_t* __restrict__ idg, const unsigned long long* __restrict__ tk,
+                                                 const uint32_t* __restrict__ tv, uint64_t hmask,
                                                  PairParams pp, const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ row_off,
                                                  uint4* __restrict__ rows, unsigned* __restrict__ err) {
   __shared__ unsigned short pend[4][RF_QCAP];
@@ -290,7 +322,7 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
     if (act) {
       const int c = pend[w][first + lane];              // ((dx+r2)*S + (dy+r2))*S + (dz+r2)
       dz = c % S - r2; dy = (c / S) % S - r2; dx = c / (S * S) - r2;
-      b = hash_lookup(tk, tv, hmask, morton_encode((uint32_t)(kx + dx), (uint32_t)(ky + dy), (uint32_t)(kz + dz)));
+      b = voxel_at(idg, g, tk, tv, hmask, kx + dx, ky + dy, kz + dz);
       if (b < 0) atomicOr(err, 4u);
     }
     __syncwarp();     // the probe loops end at different iterations: reconverge before the long pair evaluation
@@ -442,14 +474,20 @@ constexpr int LR_CS = 256;       // staging capacity (entries)
 constexpr int LR_TARGET = 40;    // staged entries aimed at per round (<= 64: sorted in registers)
 constexpr int LR_DEF = 16;       // deferred entries (lighter direction of a pair whose cells straddle a round boundary)
 __host__ __device__ inline size_t lr_smem_bytes(int lbits, int mwords, int ncap) {
-  // C_w, s_thr, s_off6, s_cur, s_end, s_sav, s_mask, s_dw (4 B) | C_f, s_nc, s_df (2 B) | s_seg, s_size, s_loc (1 B);
+  // C_w, s_thr, s_kn, s_off6, s_cur, s_end, s_sav, s_mask, s_dw (4 B) | C_f, s_nc, s_df (2 B) | s_seg, s_size, s_loc (1 B);
   // ncap = vertex capacity (multiple of 4, >= the largest neighbourhood of the scene, <= LR_NCAP)
-  size_t b = (size_t)LR_CS * 4 + (size_t)ncap * 4 * 5 + (size_t)mwords * 4 + (size_t)LR_DEF * 4 + (size_t)LR_CS * 2 + (size_t)ncap * 2 +
+  size_t b = (size_t)LR_CS * 4 + (size_t)ncap * 4 * 6 + (size_t)mwords * 4 + (size_t)LR_DEF * 4 + (size_t)LR_CS * 2 + (size_t)ncap * 2 +
              (size_t)LR_DEF * 4 + (size_t)ncap * 2 + ((size_t)1 << (3 * lbits));
   return (b + 15) & ~(size_t)15;
 }
-constexpr int LR_WARPS = 2;      // voxels per CTA (independent warps, no block barrier): lifts the 32-CTA-per-SM limit
-__global__ void __launch_bounds__(32 * LR_WARPS, 18) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
+#ifndef VGS_LR_WARPS
+#define VGS_LR_WARPS 1        // measured: 1 voxel per CTA 6.07 ms, 2 per CTA 6.7-7.2 ms (10 M-point site)
+#endif
+#ifndef VGS_LR_MINB
+#define VGS_LR_MINB 24
+#endif
+constexpr int LR_WARPS = VGS_LR_WARPS;      // voxels per CTA (independent warps, no block barrier)
+__global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
                                                             const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
                                                             const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords, int ncap,
                                                             const uint32_t* __restrict__ row_off, const uint4* __restrict__ rows,
@@ -464,7 +502,8 @@ __global__ void __launch_bounds__(32 * LR_WARPS, 18) k_local_graph_rows(int64_t 
   unsigned char* smraw = smraw_all + (size_t)wid * lr_smem_bytes(lbits, mwords, ncap);
   float* C_w = reinterpret_cast<float*>(smraw);                         // LR_CS
   float* s_thr = C_w + LR_CS;                                           // ncap: Int(C) - k/|C| of segment C
-  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_thr + ncap);         // ncap: pack6(o + rho) of the vertex
+  float* s_kn = s_thr + ncap;                                           // ncap: k / n, n = 1 .. ncap (VS.h:1963: float / int)
+  uint32_t* s_off6 = reinterpret_cast<uint32_t*>(s_kn + ncap);          // ncap: pack6(o + rho) of the vertex
   uint32_t* s_cur = s_off6 + ncap;                                      // ncap: next unread entry of the vertex's row
   uint32_t* s_end = s_cur + ncap;                                       // ncap
   uint32_t* s_sav = s_end + ncap;                                       // ncap: cursors at the start of the round
@@ -520,6 +559,7 @@ __global__ void __launch_bounds__(32 * LR_WARPS, 18) k_local_graph_rows(int64_t 
         s_cur[j] = r0; s_end[j] = r1;
         s_nc[j] = r0 < r1 ? (unsigned short)(__ldg(&rows[r0].z) >> 18) : (unsigned short)ROW_CELLS;
         s_seg[j] = (unsigned char)j; s_size[j] = 1; s_thr[j] = 1.0f - k / 1.0f;
+        s_kn[j] = k / (float)(j + 1);
       }
     }
     nv += __popc(bal);
@@ -551,7 +591,7 @@ __global__ void __launch_bounds__(32 * LR_WARPS, 18) k_local_graph_rows(int64_t 
       const float wl = __shfl_sync(0xffffffffu, w, Lm);
       for (int v = lane; v < nv; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned char)keepl;
       const int nsz = (int)s_size[keepl] + (int)s_size[drop];
-      const float nthr = wl - k / (float)nsz;        // Int(C) - k/|C| (VS.h:1963: float / int)
+      const float nthr = wl - s_kn[nsz - 1];          // Int(C) - k/|C|; a table: an IEEE division here doubles the kernel time
       __syncwarp();
       if (lane == 0) { s_thr[keepl] = nthr; s_size[keepl] = (unsigned char)nsz; s_size[drop] = 0; }
       if (sa == drop) sa = keepl;
