@@ -10,6 +10,7 @@ A "step" = one full segmentation of one synthetic scene through the C ABI of lib
            town2m            : configs[0] stand-in (Town_Test.pcd is not distributed), 2 M points, VGS
            town2m_svgs       : configs[1] stand-in, 2 M points, SVGS
            urban100m         : configs[3], 100 M-point urban scene, VGS (one GPU: fits in 180 GB)
+           city1b            : configs[4], 1 B-point city scene, VGS, only with --gpus 8 (slab split; 125 M points per GPU)
 
   value    : whole-job points/s, point cloud already resident in HBM (device pointer in, device labels out), CUDA events
              around every step on the launching stream, a 512 MB buffer written between steps (L2 flush).
@@ -57,6 +58,9 @@ CONFIGS = {
                              "supervoxels by the CUDA VCCS generator inside the step"),
     "urban100m": dict(scene="urban", points=100_000_000, mode=0,
                       what="VGS, synthetic Semantic3D-scale urban scene (configs[3]), Task_File_VGS.txt parameters"),
+    "city1b": dict(scene="urban", points=1_000_000_000, mode=0,
+                   what="VGS, synthetic 1 B-point tiled city scene (configs[4]: 80 urban tiles of 12.5 M points on one 1012 m ground), "
+                        "Task_File_VGS.txt parameters; needs the slab split over several GPUs"),
 }
 
 
@@ -147,7 +151,8 @@ def make_scene(cfg, n_points=None, tile=0):
         return scenes.town(n, seed=20170610 + tile, extent=60.0 * (n / 2_000_000) ** 0.5, offset=(80.0 * tile, 0.0, 0.0))
     import numpy as np
     ext = 320.0 * (n / 100_000_000) ** 0.5
-    return np.concatenate([scenes.urban(n // 8, seed=2 + j + 8 * tile, extent=ext, offset=(400.0 * tile, 0.0, 0.0)) for j in range(8)], axis=0)
+    parts = max(1, n // 12_500_000)
+    return np.concatenate([scenes.urban(n // parts, seed=2 + j + 1000 * tile, extent=ext, offset=(4000.0 * tile, 0.0, 0.0)) for j in range(parts)], axis=0)
 
 
 def params_of(cfg):

@@ -463,6 +463,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
     if (r == cudaSuccess) r = optin((const void*)k_local_graph_rows, kMax);
     if (r == cudaSuccess) r = optin((const void*)k_adj_fill, 200 * 1024);
     if (r == cudaSuccess) r = optin((const void*)k_rows_sort, 200 * 1024);
+    if (r == cudaSuccess) r = optin((const void*)k_rows_fill, 200 * 1024);
     if (r != cudaSuccess) {
       g_create_error = std::string("kernel attribute setup failed (is this an sm_100 device?): ") + cudaGetErrorString(r);
       cudaGetLastError();
@@ -1256,20 +1257,19 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
       CK(h->rows.reserve((size_t)h->n_rows * 16 + 64));
       KTimer krf(h, K_ROWS_FILL);
-      LAUNCH(k_rows_fill, (unsigned)cdiv(nu, 4), 128, 0, h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg, h->grid, h->bm_used.as<uint32_t>(),
+      LAUNCH(k_rows_fill, (unsigned)cdiv(nu, RF_WARPS), RF_WARPS * 32, RF_WARPS * rows_fill_smem_warp(2 * lg.r2c + 1), h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg,
+             h->grid, h->bm_used.as<uint32_t>(),
              h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->use_idgrid ? h->idgrid.as<int32_t>() : nullptr, h->tk.as<unsigned long long>(),
              h->tv.as<uint32_t>(), h->hmask, gp.pp,
              h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_err);
       krf.stop();
-      KTimer krs(h, K_ROWS_SORT);
-      LAUNCH(k_rows_sort, (unsigned)cdiv(nu, RS2_WARPS), RS2_WARPS * 32, (size_t)RS2_WARPS * 2 * ROWS_SHORT_CAP * 16, h->row_off.as<uint32_t>(), nu,
-             (const uint32_t*)nullptr, 0u, ROWS_SHORT_CAP, h->rows.as<uint4>());
-      if (h->n_long > 0) {
+      if (h->n_long > 0) {   // rows longer than the shared-memory assembly of k_rows_fill
+        KTimer krs(h, K_ROWS_SORT);
         const int cap_long = (int)((h->max_row_len + 63) & ~(int64_t)63);
         LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 16, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
                (uint32_t)h->n_long, cap_long, h->rows.as<uint4>());
+        krs.stop();
       }
-      krs.stop();
       tpc.stop();
     }
     // ---- stage 5a: one warp per voxel ----
@@ -1587,7 +1587,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   static const char* names[vgs_context::NK] = {
       "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_head_flags + scan + k_head_write + k_voxel_keys",
       "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
-      "adjacency fill: k_adj_fill", "weight rows: k_rows_fill", "weight rows: k_rows_sort", "local graphs: k_local_graph_rows",
+      "adjacency fill: k_adj_fill", "weight rows: k_rows_fill (evaluate, order by weight cell, write once)", "weight rows: k_rows_sort (rows longer than 256 entries)", "local graphs: k_local_graph_rows",
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",
       "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels"};
   const int64_t N = h->n, V = h->nu, E = h->n_adj, R = h->n_rows, MW = h->mwords;
@@ -1596,7 +1596,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   // algorithmic bytes = compulsory HBM traffic with inputs / outputs materialised once
   const int64_t bytes[vgs_context::NK] = {
       12 * N, 12 * N + (KB + 4) * N, (int64_t)passes * 2 * (KB + 4) * N, KB * N + 4 * N + 28 * V, 16 * N + 64 * V, 32 * V, 13 * V + 2 * h->grid_bytes,
-      20 * V, 16 * V + 6 * E, 64 * V + 16 * R, 32 * R, 6 * E + 16 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
+      20 * V, 16 * V + 6 * E, 64 * V + 16 * R, 32 * h->n_long * h->max_row_len, 6 * E + 16 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
   int c = 0;
   for (int i = 0; i < vgs_context::NK && out && c < *n; i++) {
     if (h->k_launches[i] == 0 && h->k_ms[i] == 0.f) continue;

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
 //      cell(w) = floor((1 - w) * 4096) orders a row coarsely (k_rows_sort); the consumer sorts exactly inside the cells
 //      it takes.  A row is written by one warp only: no atomics, no scattered stores. ----
 constexpr int ROW_CELLS = 4096;
-constexpr int ROWS_SHORT_CAP = 256;   // rows up to this length are sorted four per CTA; longer ones one per CTA
+constexpr int ROWS_SHORT_CAP = 256;   // rows up to this length are assembled and ordered in shared memory by k_rows_fill; longer ones by k_rows_sort
 __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
   // monotone non-increasing in w; NaN and w <= 0 fall into the last cell
   if (!(w > 0.f)) return ROW_CELLS - 1;
@@ -297,30 +297,45 @@ __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
 // every weight of a cell >= c is <= this bound (1 - w is exact for w >= 0.5, else off by <= 2^-25; the slack covers it)
 __device__ __forceinline__ float row_cell_upper(int c) { return (1.0f - (float)c * (1.0f / (float)ROW_CELLS)) + 1.2e-7f; }
 
-constexpr int RF_QCAP = 32 + 32 * 32;   // a lane queues at most one z-run (<= 32 hits) per column step
-__global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
+// One warp per used voxel.  Rows of up to ROWS_SHORT_CAP entries are assembled in shared memory, ordered by weight cell
+// there (LSD radix sort of (cell << 8 | position) words, 2 passes x 6 bits) and written once, in order; longer rows go out
+// unsorted and are ordered by k_rows_sort over the long-row list.
+constexpr int RF_WARPS = 4;
+__host__ __device__ inline size_t rows_fill_smem_warp(int S) {
+  const size_t qcap = 32 + 32 * (size_t)S;          // a lane queues at most one z-run (<= S hits) per column step
+  return (size_t)ROWS_SHORT_CAP * 16 + 2 * (size_t)ROWS_SHORT_CAP * 4 + 64 * 4 + ((qcap * 2 + 15) & ~(size_t)15) + REC_FLOATS * 4;
+}
+__global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
                                                  BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
                                                  const int32_t* __restrict__ idg, const unsigned long long* __restrict__ tk,
                                                  const uint32_t* __restrict__ tv, uint64_t hmask,
                                                  PairParams pp, const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ row_off,
                                                  uint4* __restrict__ rows, unsigned* __restrict__ err) {
-  __shared__ unsigned short pend[4][RF_QCAP];
-  __shared__ float s_ra[4][REC_FLOATS];
+  extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t v = (int64_t)blockIdx.x * 4 + w;
+  const int64_t v = (int64_t)blockIdx.x * RF_WARPS + w;
   if (v >= nv) return;
   if (!(uflags[v] & F_USED)) return;
-  if (lane < REC_FLOATS) s_ra[w][lane] = rec[v * REC_FLOATS + lane];
+  const int r2 = lg.r2c, S = 2 * r2 + 1;
+  unsigned char* mine = smraw + (size_t)w * rows_fill_smem_warp(S);
+  uint4* ent = reinterpret_cast<uint4*>(mine);                                  // ROWS_SHORT_CAP entries
+  uint32_t* kA = reinterpret_cast<uint32_t*>(ent + ROWS_SHORT_CAP);             // sort words (cell << 8 | position)
+  uint32_t* kB = kA + ROWS_SHORT_CAP;
+  unsigned* s_cnt = kB + ROWS_SHORT_CAP;                                        // 64 digit counters
+  unsigned short* pend = reinterpret_cast<unsigned short*>(s_cnt + 64);         // queue of stencil codes
+  float* s_ra = reinterpret_cast<float*>(mine + rows_fill_smem_warp(S) - REC_FLOATS * 4);
+  if (lane < REC_FLOATS) s_ra[lane] = rec[v * REC_FLOATS + lane];
   __syncwarp();
   const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
-  const int r2 = lg.r2c, S = 2 * r2 + 1;
   const uint32_t my_row = row_off[v];
+  const int len = (int)(row_off[v + 1] - my_row);
+  const bool in_smem = len <= ROWS_SHORT_CAP;
   int npend = 0, done = 0;
   auto process = [&](int first, int cnt) {
     const bool act = lane < cnt;
     int b = -1, dx = 0, dy = 0, dz = 0;
     if (act) {
-      const int c = pend[w][first + lane];              // ((dx+r2)*S + (dy+r2))*S + (dz+r2)
+      const int c = pend[first + lane];              // ((dx+r2)*S + (dy+r2))*S + (dz+r2)
       dz = c % S - r2; dy = (c / S) % S - r2; dx = c / (S * S) - r2;
       b = voxel_at(idg, g, tk, tv, hmask, kx + dx, ky + dy, kz + dz);
       if (b < 0) atomicOr(err, 4u);
@@ -332,10 +347,13 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
 #pragma unroll
       for (int qd = 0; qd < 4; qd++) { float4 t = __ldg(src + qd); rb[4 * qd] = t.x; rb[4 * qd + 1] = t.y; rb[4 * qd + 2] = t.z; rb[4 * qd + 3] = t.w; }
       float w_ab, w_ba;
-      pair_weights(s_ra[w], rb, pp, w_ab, w_ba);
+      pair_weights(s_ra, rb, pp, w_ab, w_ba);
       const uint32_t ca = row_cell(w_ab), cb = row_cell(w_ba);
-      rows[my_row + done + lane] = make_uint4(__float_as_uint(w_ab), __float_as_uint(w_ba),
-                                              (min(ca, cb) << 18) | pack6(dx + r2, dy + r2, dz + r2), max(ca, cb));
+      const uint4 e = make_uint4(__float_as_uint(w_ab), __float_as_uint(w_ba), (min(ca, cb) << 18) | pack6(dx + r2, dy + r2, dz + r2), max(ca, cb));
+      const int at = done + lane;
+      if (in_smem) {
+        if (at < ROWS_SHORT_CAP) { ent[at] = e; kA[at] = (min(ca, cb) << 8) | (uint32_t)at; }
+      } else rows[my_row + at] = e;
     }
     done += cnt;
   };
@@ -354,7 +372,7 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
     while (hits) {
       const int j = __ffs(hits) - 1;
       hits &= hits - 1;
-      pend[w][pos++] = (unsigned short)(cbase + j);
+      pend[pos++] = (unsigned short)(cbase + j);
     }
     npend += __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
@@ -362,6 +380,49 @@ __global__ void __launch_bounds__(128) k_rows_fill(const uint32_t* __restrict__ 
     __syncwarp();
   }
   process(0, npend);
+  if (!in_smem) return;
+  if (done != len) { if (lane == 0) atomicOr(err, 8u); return; }     // count and fill disagree: cannot happen
+  __syncwarp();
+  // ---- order the row by weight cell (stable LSD radix, 2 x 6 bits) and write it once ----
+  const uint32_t lt = (1u << lane) - 1u;
+  if (len > 1) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const int shift = 8 + 6 * pass;
+      s_cnt[lane] = 0; s_cnt[lane + 32] = 0;
+      __syncwarp();
+      for (int i0 = 0; i0 < len; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned d = i < len ? ((kA[i] >> shift) & 63u) : 0xffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (i < len && (peers & lt) == 0) s_cnt[d] += __popc(peers);
+        __syncwarp();
+      }
+      {   // exclusive prefix sums over the 64 counters: lane owns bins 2*lane, 2*lane + 1
+        const unsigned c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        const unsigned inc = warp_incl_scan(c0 + c1, lane);
+        __syncwarp();
+        s_cnt[2 * lane] = inc - c0 - c1;
+        s_cnt[2 * lane + 1] = inc - c1;
+      }
+      __syncwarp();
+      for (int i0 = 0; i0 < len; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t e = 0;
+        unsigned d = 0xffffu;
+        if (i < len) { e = kA[i]; d = (e >> shift) & 63u; }
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        unsigned pos = 0;
+        if (i < len) pos = s_cnt[d] + __popc(peers & lt);
+        __syncwarp();
+        if (i < len && (peers & lt) == 0) s_cnt[d] += __popc(peers);
+        if (i < len) kB[pos] = e;
+        __syncwarp();
+      }
+      uint32_t* t = kA; kA = kB; kB = t;
+    }
+  }
+  for (int i = lane; i < len; i += 32) rows[my_row + i] = ent[kA[i] & 255u];
 }
 
 // ---- rows ordered by weight cell: LSD radix sort (2 passes x 6 bits) of one row per warp in shared memory ----

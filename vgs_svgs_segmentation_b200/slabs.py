@@ -44,11 +44,12 @@ def create_group(dist, rank: int, world: int, device: int, stream=None) -> capi.
 def scene_parts(cfg_name, configs, n_gpus):
     """(number of parts, points per part, extent): the workload of bench.py's slab arm.
     site10m / town2m: N parts of the config's size on sqrt(N) times the extent (weak scaling: per-GPU work fixed; N = 1 is
-    exactly the single-GPU workload).  urban100m: always 8 parts of 12.5 M points on 320 m (strong scaling: the same scene
-    for every N)."""
+    exactly the single-GPU workload).  urban100m / city1b: always 8 / 80 parts of 12.5 M points on a 320 m / 1012 m ground
+    (strong scaling: the same scene for every N)."""
     c = configs[cfg_name]
     if c["scene"] == "urban":
-        return 8, c["points"] // 8, 320.0
+        parts = max(1, c["points"] // 12_500_000)
+        return parts, c["points"] // parts, 320.0 * (c["points"] / 100_000_000) ** 0.5
     base = {"construction_site": 70.0, "town": 60.0}[c["scene"]]
     return n_gpus, c["points"], base * n_gpus ** 0.5
 
@@ -144,7 +145,8 @@ def bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, measu
     launches_all = int(tl[0])
     same_all = int(tl[1]) == world
 
-    # ---- parity: the slab labels against ONE single-GPU run of the whole scene (rank 0) ----
+    # ---- parity: the slab labels against ONE single-GPU run of the whole scene (rank 0); scenes too large for one GPU:
+    #      the size-independent properties of canonical labels ----
     parity = None
     if not args.no_verify:
         sizes = [ppp * (nparts // world)] * world
@@ -152,15 +154,28 @@ def bench(args, cfg, pd, rank, world, local, flush, barrier, ClockSampler, measu
         dist.gather(dev_lab, gathered, dst=0)
         if rank == 0:
             try:
-                whole = np.concatenate([pts] + [make_part(cfg, CONFIGS, j, ppp, extent) for j in range(len(my_parts), nparts)], axis=0)
-                hs = capi.Handle(mode=0, device=local, stream=stream.cuda_stream)
-                hs.set_points(whole)
-                ref = hs.run(params)
-                c1 = hs.counts()
-                hs.close()
-                got = torch.cat(gathered).cpu().numpy()
-                parity = {"labels_equal_single_gpu": bool(np.array_equal(got, ref)), "points": int(whole.shape[0]),
-                          "clusters_single_gpu": int(c1["n_clusters_exported"]), "clusters_slabs": int(counts["n_clusters_exported"])}
+                got_dev = torch.cat(gathered)
+                del gathered
+                if n_total <= 250_000_000:
+                    whole = np.concatenate([pts] + [make_part(cfg, CONFIGS, j, ppp, extent) for j in range(len(my_parts), nparts)], axis=0)
+                    hs = capi.Handle(mode=0, device=local, stream=stream.cuda_stream)
+                    hs.set_points(whole)
+                    ref = hs.run(params)
+                    c1 = hs.counts()
+                    hs.close()
+                    got = got_dev.cpu().numpy()
+                    parity = {"labels_equal_single_gpu": bool(np.array_equal(got, ref)), "points": int(whole.shape[0]),
+                              "clusters_single_gpu": int(c1["n_clusters_exported"]), "clusters_slabs": int(counts["n_clusters_exported"])}
+                else:
+                    lab = got_dev.long()
+                    idx = torch.arange(lab.numel(), device="cuda")
+                    has = lab >= 0
+                    seeds = lab[has]
+                    parity = {"single_gpu_comparison": "skipped: the scene does not fit one GPU (the same split is compared with one GPU on "
+                                                       "urban100m and in tests/test_slabs_gpu.py)",
+                              "points": int(lab.numel()), "labelled_points": int(has.sum()),
+                              "label_is_min_index_of_its_cluster": bool((seeds <= idx[has]).all()) and bool((lab[seeds] == seeds).all()),
+                              "distinct_labels": int(torch.unique(seeds).numel()), "clusters_slabs": int(counts["n_clusters_exported"])}
             except Exception as e:  # noqa: BLE001
                 parity = {"error": str(e)[:300]}
     g.close()
