@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <limits>
+#include <optional>
 #include <string>
 #include <vector>
 
@@ -88,7 +89,7 @@ struct vgs_context {
   DBuf ustart, ukey, pos_unit, rec, key3, center, plainm, tk, tv, stencil;
   DBuf adj_cnt, adj_off, adj_idx, adj_code, class_count, class_list;
   DBuf conn0_cnt, conn0_idx, conn1_cnt, conn1_idx, attach, parent, root, csize, cminpt, labels_out, tmp;
-  uint64_t* d_keys = nullptr;   // sorted keys (points to keysA or keysB)
+  int sort_key_bytes = 8;       // width of the voxel sort keys of the last vgs_voxelize
   uint32_t* d_perm = nullptr;   // sorted point indices
   uint64_t hmask = 0;
   // lattice searches (VGS): host tables rebuilt only when (voxel_size, graph_size, float-noise bound) change
@@ -200,17 +201,18 @@ vgs_status scan_u32(vgs_handle h, const uint32_t* in, uint32_t* out, int64_t n, 
 }
 
 // stable LSD radix sort of (key,val) over the low nbits bits; result pointers returned
-vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out,
-                      uint64_t* ka = nullptr, uint64_t* kb = nullptr, uint32_t* va = nullptr, uint32_t* vb = nullptr) {
-  if (!ka) { ka = h->keysA.as<uint64_t>(); kb = h->keysB.as<uint64_t>(); va = h->valsA.as<uint32_t>(); vb = h->valsB.as<uint32_t>(); }
+template <class K>
+vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, K** keys_out, uint32_t** vals_out,
+                      K* ka = nullptr, K* kb = nullptr, uint32_t* va = nullptr, uint32_t* vb = nullptr) {
+  if (!ka) { ka = h->keysA.as<K>(); kb = h->keysB.as<K>(); va = h->valsA.as<uint32_t>(); vb = h->valsB.as<uint32_t>(); }
   int64_t nblk = cdiv(n, RS_TILE);
   if (nblk < 1) nblk = 1;
   CK(h->hist.reserve((size_t)nblk * 256 * 4));
   for (int shift = 0; shift < nbits; shift += 8) {
-    LAUNCH(k_rs_hist, (unsigned)nblk, RS_THREADS, 0, ka, n, shift, h->hist.as<uint32_t>(), nblk);
+    LAUNCH(k_rs_hist<K>, (unsigned)nblk, RS_THREADS, 0, ka, n, shift, h->hist.as<uint32_t>(), nblk);
     vgs_status s = scan_u32(h, h->hist.as<uint32_t>(), h->hist.as<uint32_t>(), nblk * 256, nullptr);
     if (s) return s;
-    LAUNCH(k_rs_scatter, (unsigned)nblk, RS_THREADS, 0, ka, va, kb, vb, n, shift, h->hist.as<uint32_t>(), nblk);
+    LAUNCH(k_rs_scatter<K>, (unsigned)nblk, RS_THREADS, 0, ka, va, kb, vb, n, shift, h->hist.as<uint32_t>(), nblk);
     std::swap(ka, kb); std::swap(va, vb);
   }
   *keys_out = ka; *vals_out = va;
@@ -218,21 +220,22 @@ vgs_status radix_sort(vgs_handle h, int64_t n, int nbits, uint64_t** keys_out, u
 }
 
 // sorted keys -> unit table.  n_valid = number of sorted positions with key < sentinel.
-vgs_status build_units(vgs_handle h, const uint64_t* keys, int64_t n_valid, int64_t* n_units, DBuf* ustart = nullptr,
+template <class K>
+vgs_status build_units(vgs_handle h, const K* keys, int64_t n_valid, int64_t* n_units, DBuf* ustart = nullptr,
                        DBuf* ukey = nullptr, DBuf* pos_unit = nullptr) {
   if (!ustart) { ustart = &h->ustart; ukey = &h->ukey; pos_unit = &h->pos_unit; }
   if (n_valid <= 0) { *n_units = 0; return VGS_OK; }
   CK(h->flags.reserve((size_t)n_valid * 4));
   CK(h->scan.reserve((size_t)n_valid * 4));
   CK(pos_unit->reserve((size_t)n_valid * 4));
-  LAUNCH(k_head_flags, (unsigned)cdiv(n_valid, 256), 256, 0, keys, n_valid, h->flags.as<uint32_t>());
+  LAUNCH(k_head_flags<K>, (unsigned)cdiv(n_valid, 256), 256, 0, keys, n_valid, h->flags.as<uint32_t>());
   unsigned long long total = 0;
   vgs_status s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid, &total);
   if (s) return s;
   *n_units = (int64_t)total;
   CK(ustart->reserve((size_t)(total + 1) * 4));
   CK(ukey->reserve((size_t)(total + 1) * 8));
-  LAUNCH(k_head_write, (unsigned)cdiv(n_valid, 256), 256, 0, keys, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid,
+  LAUNCH(k_head_write<K>, (unsigned)cdiv(n_valid, 256), 256, 0, keys, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid,
          ustart->as<uint32_t>(), ukey->as<uint64_t>(), pos_unit->as<uint32_t>());
   uint32_t endv = (uint32_t)n_valid;
   CK(cudaMemcpyAsync(ustart->as<uint32_t>() + total, &endv, 4, cudaMemcpyHostToDevice, h->stream));
@@ -551,20 +554,31 @@ static vgs_status voxelize_sorted(vgs_handle h, int gidx_w) {
     StageTimer t(h, &h->tm.voxelize_ms, 2);
     CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
     CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
-    KTimer kq(h, K_QUANTISE);
-    LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth,
-           h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr, gidx_w);
-    kq.stop();
-    uint64_t* ks; uint32_t* vs;
-    KTimer ksrt(h, K_SORT);
-    vgs_status s = radix_sort(h, n, 3 * h->depth + 1, &ks, &vs);
-    if (s) return s;
-    ksrt.stop();
-    KTimer kh(h, K_HEADS);
-    // number of finite points = first sorted position whose key has the sentinel bit: count via head scan
-    // (sentinel keys form at most one extra segment at the end)
+    const int desc = h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0;
+    const int nbits = 3 * h->depth + 1;
     int64_t nunits = 0;
-    s = build_units(h, ks, n, &nunits);
+    uint32_t* vs = nullptr;
+    vgs_status s;
+    std::optional<KTimer> kh;
+    // keys of <= 32 bits (octrees up to depth 10: 307 m at 0.15 m) are sorted as 32-bit words
+    auto run = [&](auto tag) -> vgs_status {
+      using K = decltype(tag);
+      KTimer kq(h, K_QUANTISE);
+      LAUNCH(k_quantise<K>, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
+             h->keysA.as<K>(), h->valsA.as<uint32_t>(), (uint32_t*)nullptr, gidx_w);
+      kq.stop();
+      K* ks;
+      KTimer ksrt(h, K_SORT);
+      vgs_status s_ = radix_sort<K>(h, n, nbits, &ks, &vs);
+      if (s_) return s_;
+      ksrt.stop();
+      h->sort_key_bytes = (int)sizeof(K);
+      kh.emplace(h, K_HEADS);
+      // number of finite points = first sorted position whose key has the sentinel bit: count via head scan
+      // (sentinel keys form at most one extra segment at the end)
+      return build_units<K>(h, ks, n, &nunits);
+    };
+    s = nbits <= 32 ? run(uint32_t{}) : run(uint64_t{});
     if (s) return s;
     // voxel keys + occupied key range (the extent of the occupancy grids of the lattice searches)
     uint32_t* d_kmm = h->small.as<uint32_t>() + 208;
@@ -579,7 +593,7 @@ static vgs_status voxelize_sorted(vgs_handle h, int gidx_w) {
     uint64_t lastkey = 0; uint32_t laststart = 0;
     CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
-    kh.stop();
+    kh->stop();
     CK(cudaMemcpyAsync(h->kminmax, d_kmm, sizeof(h->kminmax), cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
     int64_t n_fin = n;
@@ -587,7 +601,7 @@ static vgs_status voxelize_sorted(vgs_handle h, int gidx_w) {
     h->n_finite = n_fin;
     h->n_voxels = nunits;
     if (h->mode == VGS_MODE_VGS) {
-      h->d_keys = ks; h->d_perm = vs;
+      h->d_perm = vs;
       h->nu = nunits; h->n_valid = n_fin;
       h->have_units = true;
     }
@@ -659,10 +673,10 @@ static vgs_status build_svgs_units(vgs_handle h) {
   CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
   LAUNCH(k_label_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_labels, h->d_xyz, h->stride, n, ml, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>());
   uint64_t* ks; uint32_t* vs;
-  vgs_status s = radix_sort(h, n, 33, &ks, &vs);
+  vgs_status s = radix_sort<uint64_t>(h, n, 33, &ks, &vs);
   if (s) return s;
   int64_t nunits = 0;
-  s = build_units(h, ks, n, &nunits);
+  s = build_units<uint64_t>(h, ks, n, &nunits);
   if (s) return s;
   uint64_t lastkey = 0; uint32_t laststart = 0;
   CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
@@ -670,7 +684,7 @@ static vgs_status build_svgs_units(vgs_handle h) {
   CK(stream_wait(h->stream));
   int64_t nval = n;
   if (lastkey >> 32) { nval = laststart; nunits--; }
-  h->d_keys = ks; h->d_perm = vs;
+  h->d_perm = vs;
   h->nu = nunits; h->n_valid = nval;
   h->have_units = true;
   return VGS_OK;
@@ -688,10 +702,10 @@ vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
   LAUNCH(k_seed_cell_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->box.mn[0], h->box.mn[1], h->box.mn[2],
          (double)seed_size, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>());
   uint64_t* ks; uint32_t* vs;
-  vgs_status s = radix_sort(h, n, 64, &ks, &vs);
+  vgs_status s = radix_sort<uint64_t>(h, n, 64, &ks, &vs);
   if (s) return s;
   int64_t nunits = 0;
-  s = build_units(h, ks, n, &nunits);
+  s = build_units<uint64_t>(h, ks, n, &nunits);
   if (s) return s;
   uint64_t lastkey = 0; uint32_t laststart = 0;
   CK(cudaMemcpyAsync(&lastkey, h->ukey.as<uint64_t>() + (nunits - 1), 8, cudaMemcpyDeviceToHost, h->stream));
@@ -699,7 +713,7 @@ vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
   CK(stream_wait(h->stream));
   int64_t nval = n;
   if (lastkey >> 63) { nval = laststart; nunits--; }
-  h->d_keys = ks; h->d_perm = vs;
+  h->d_perm = vs;
   h->nu = nunits; h->n_valid = nval;
   h->have_units = true;
   h->units_external = true;
@@ -723,14 +737,14 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   // --- voxel table of its own (the shared sort buffers are reused by the unit builders) ---
   CK(c.keysA.reserve((size_t)n * 8)); CK(c.keysB.reserve((size_t)n * 8));
   CK(c.valsA.reserve((size_t)n * 4)); CK(c.valsB.reserve((size_t)n * 4));
-  LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
+  LAUNCH(k_quantise<uint64_t>, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
          c.keysA.as<uint64_t>(), c.valsA.as<uint32_t>(), (uint32_t*)nullptr);
   uint64_t* ks; uint32_t* vs;
-  vgs_status s = radix_sort(h, n, 3 * h->depth + 1, &ks, &vs, c.keysA.as<uint64_t>(), c.keysB.as<uint64_t>(), c.valsA.as<uint32_t>(),
+  vgs_status s = radix_sort<uint64_t>(h, n, 3 * h->depth + 1, &ks, &vs, c.keysA.as<uint64_t>(), c.keysB.as<uint64_t>(), c.valsA.as<uint32_t>(),
                             c.valsB.as<uint32_t>());
   if (s) return s;
   int64_t V = 0;
-  s = build_units(h, ks, n, &V, &c.start, &c.key, &c.pos);
+  s = build_units<uint64_t>(h, ks, n, &V, &c.start, &c.key, &c.pos);
   if (s) return s;
   {
     uint64_t lastkey = 0;
@@ -762,10 +776,10 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   LAUNCH(k_vccs_cell_keys, (unsigned)cdiv(V, 256), 256, 0, c.xyz.as<float>(), V, h->box.mn[0], h->box.mn[1], h->box.mn[2], seed_d,
          c.ckA.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cell3.as<int32_t>());
   uint64_t* cks; uint32_t* cvs;
-  s = radix_sort(h, V, 63, &cks, &cvs, c.ckA.as<uint64_t>(), c.ckB.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cvB.as<uint32_t>());
+  s = radix_sort<uint64_t>(h, V, 63, &cks, &cvs, c.ckA.as<uint64_t>(), c.ckB.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cvB.as<uint32_t>());
   if (s) return s;
   int64_t NC = 0;
-  s = build_units(h, cks, V, &NC, &c.cstart, &c.ckey, &c.cpos);
+  s = build_units<uint64_t>(h, cks, V, &NC, &c.cstart, &c.ckey, &c.cpos);
   if (s) return s;
   uint64_t ccap = 64;
   while (ccap < (uint64_t)NC * 2) ccap <<= 1;
@@ -1049,11 +1063,11 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     LAUNCH(k_cell_keys, (unsigned)cdiv(nu, 256), 256, 0, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
            h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
-    vgs_status s = radix_sort(h, nu, 63, &ks, &vs, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(), h->cvalsA.as<uint32_t>(),
+    vgs_status s = radix_sort<uint64_t>(h, nu, 63, &ks, &vs, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(), h->cvalsA.as<uint32_t>(),
                               h->cvalsB.as<uint32_t>());
     if (s) return s;
     int64_t ncells = 0;
-    s = build_units(h, ks, nu, &ncells, &h->cstart, &h->ckey, &h->cpos);
+    s = build_units<uint64_t>(h, ks, nu, &ncells, &h->cstart, &h->ckey, &h->cpos);
     if (s) return s;
     uint64_t capacity = 64;
     while (capacity < (uint64_t)ncells * 2) capacity <<= 1;
@@ -1330,7 +1344,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
   // class lists ordered by unit id: one stable 8-bit radix pass on (class, unit id)
   uint64_t* cls_keys; uint32_t* cls_sorted;
   {
-    vgs_status s_ = radix_sort(h, nu, 8, &cls_keys, &cls_sorted, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(),
+    vgs_status s_ = radix_sort<uint64_t>(h, nu, 8, &cls_keys, &cls_sorted, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(),
                                h->cvalsA.as<uint32_t>(), h->cvalsB.as<uint32_t>());
     if (s_) return s_;
   }
@@ -1591,7 +1605,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",
       "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels"};
   const int64_t N = h->n, V = h->nu, E = h->n_adj, R = h->n_rows, MW = h->mwords;
-  const int64_t KB = 8;     // bytes per sort key
+  const int64_t KB = h->sort_key_bytes;     // bytes per sort key
   const int passes = (3 * h->depth + 1 + 7) / 8;
   // algorithmic bytes = compulsory HBM traffic with inputs / outputs materialised once
   const int64_t bytes[vgs_context::NK] = {
@@ -1628,7 +1642,7 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
       // keys/vals scratch of a throw-away quantise pass (the sorted arrays stay untouched)
       DBuf sk, sv;
       CK(sk.reserve((size_t)n * 8)); CK(sv.reserve((size_t)n * 4));
-      LAUNCH(k_quantise, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth,
+      LAUNCH(k_quantise<uint64_t>, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth,
              h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0, sk.as<uint64_t>(), sv.as<uint32_t>(), k3);
       vgs_status s = copy_out(k3, (size_t)n * 12);
       sk.release(); sv.release();

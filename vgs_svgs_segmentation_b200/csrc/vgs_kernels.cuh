@@ -61,8 +61,11 @@ __global__ void __launch_bounds__(256) k_find_outside(const float* __restrict__ 
 
 // ---- stage 1a: octree key per point -> sortable 64-bit code, value = point index.
 //      key.a = (unsigned)((p.a - min_a)/res) in double (genOctreeKeyforPoint).  12 B read, 12 B written. ----
+//      K = uint32_t when the key (3 * depth bits + the sentinel bit) fits 32 bits: the sort then moves 8 instead of 12 bytes
+//      per point and pass.
+template <class K>
 __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz, int stride, int64_t n, EpochTable ep, double res,
-                                                int depth, int descending, uint64_t* __restrict__ keys,
+                                                int depth, int descending, K* __restrict__ keys,
                                                 uint32_t* __restrict__ vals, uint32_t* __restrict__ key3_out, int gidx_w = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz,
   const long long gi = gidx_w ? (long long)__float_as_uint(p[3]) : (long long)i;
   const uint64_t mask = (depth * 3 >= 64) ? ~0ull : ((1ull << (3 * depth)) - 1ull);
   if (!finite3(x, y, z)) {
-    keys[i] = 1ull << (3 * depth);  // sorts after every real key
+    keys[i] = (K)(1ull << (3 * depth));  // sorts after every real key
     if (key3_out) { key3_out[3 * i] = key3_out[3 * i + 1] = key3_out[3 * i + 2] = 0xffffffffu; }
     return;
   }
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz,
   uint32_t ky = (uint32_t)(((double)y - ep.mn[e][1]) / res) + ep.shift[e][1];
   uint32_t kz = (uint32_t)(((double)z - ep.mn[e][2]) / res) + ep.shift[e][2];
   uint64_t m = morton_encode(kx, ky, kz);
-  keys[i] = descending ? (~m & mask) : m;
+  keys[i] = (K)(descending ? (~m & mask) : m);
   if (key3_out) { key3_out[3 * i] = kx; key3_out[3 * i + 1] = ky; key3_out[3 * i + 2] = kz; }
 }
 
@@ -114,14 +117,16 @@ __global__ void __launch_bounds__(256) k_seed_cell_keys(const float* __restrict_
 }
 
 // ---- stage 1b: segment heads of the sorted keys ----
-__global__ void __launch_bounds__(256) k_head_flags(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
+template <class K>
+__global__ void __launch_bounds__(256) k_head_flags(const K* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
 }
 // scan[i] = exclusive scan of flags.  Writes unit start offsets, the unit's sort key and the
 // sorted-position -> unit id map.
-__global__ void __launch_bounds__(256) k_head_write(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags,
+template <class K>
+__global__ void __launch_bounds__(256) k_head_write(const K* __restrict__ keys, const uint32_t* __restrict__ flags,
                                                   const uint32_t* __restrict__ scan, int64_t n, uint32_t* __restrict__ ustart,
                                                   uint64_t* __restrict__ ukey, uint32_t* __restrict__ pos_unit) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(256) k_head_write(const uint64_t* __restrict__
   uint32_t f = flags[i];
   uint32_t u = scan[i] + f - 1u;
   pos_unit[i] = u;
-  if (f) { ustart[u] = (uint32_t)i; ukey[u] = keys[i]; }
+  if (f) { ustart[u] = (uint32_t)i; ukey[u] = (uint64_t)keys[i]; }
 }
 
 // ---- stage 2: per-unit record (centroid, scatter, eigen33, normal, 8 eigen features).

@@ -1,5 +1,5 @@
 // vgs_prims.cuh — device-wide building blocks written for this library (no CUB/Thrust):
-// exclusive scan (u32), stable LSD radix sort of (u64 key, u32 value), 64-bit open-addressing hash.
+// exclusive scan (u32), stable LSD radix sort of (u32 / u64 key, u32 value), 64-bit open-addressing hash.
 // All HBM-bound; grids are sized from the element count, tiles are 2-4 K elements per CTA.
 #pragma once
 #include <cuda_runtime.h>
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_down(const uint32_t* __rest
 }
 
 // ---- radix sort pass: per-tile digit histogram -> (scan, digit-major) -> stable scatter ----
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ keys, int64_t n, int shift,
                                                        uint32_t* __restrict__ hist, int64_t nblk) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
@@ -100,8 +101,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
   hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                                          uint64_t* __restrict__ kout, uint32_t* __restrict__ vout, int64_t n,
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                          K* __restrict__ kout, uint32_t* __restrict__ vout, int64_t n,
                                                           int shift, const uint32_t* __restrict__ offs, int64_t nblk) {
   __shared__ uint32_t wc[RS_WARPS][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   __syncthreads();
   // warp w owns the contiguous chunk [w*512, (w+1)*512) of the tile, 16 rounds of 32 (order kept)
   const int64_t cbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_TILE / RS_WARPS);
-  uint64_t k[RS_IPT];
+  K k[RS_IPT];
   uint32_t v[RS_IPT];
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
