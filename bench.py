@@ -187,6 +187,39 @@ def cpu_baseline(cfg, sample_points):
                       f"(glibc libm), single thread as the reference runs, {dt:.2f} s, {r.stats['pair_evals']} pair evaluations"}
 
 
+def dropin_e2e(cfg, pts, pd, runs=3):
+    """e2e through the reference-facing C++ class (include/vgs_dropin/voxel_segmentation.h) driven by the reference's call sequence
+    (test:51-76): pageable pcl::PointCloud (16-byte points) in, drawColorMapofPointsinClusters + getClusterIdx() (vector<vector<int>>)
+    out.  A separate process (tests/cpp/dropin_vgs.cpp, compiled here with g++); VGS only."""
+    import tempfile
+    exe = os.path.join(ROOT, "tests", "_build", "dropin_vgs")
+    try:
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        src = os.path.join(ROOT, "tests", "cpp", "dropin_vgs.cpp")
+        if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, src,
+                            "-L" + os.path.join(ROOT, "vgs_svgs_segmentation_b200"), "-lvgs_b200",
+                            "-Wl,-rpath," + os.path.join(ROOT, "vgs_svgs_segmentation_b200")], check=True, capture_output=True)
+        with tempfile.TemporaryDirectory() as td:
+            f = os.path.join(td, "x.f32")
+            pts.tofile(f)
+            args = [exe, f, str(pts.shape[0]), os.path.join(td, "l.i32")] + [str(pd[k]) for k in (
+                "voxel_size", "graph_size", "sig_p", "sig_n", "sig_o", "sig_e", "sig_c", "sig_w", "cut_thred", "points_min", "adjacency_min", "voxels_min")]
+            r = subprocess.run(args, capture_output=True, text=True, timeout=900, env=dict(os.environ, VGS_DROPIN_REPEAT=str(runs + 1)))
+            if r.returncode != 0:
+                return {"error": (r.stderr or r.stdout)[-300:]}
+            ms = [float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("dropin_ms")]
+            import numpy as np
+            lab = np.fromfile(os.path.join(td, "l.i32"), np.int32)
+        v = sum(ms) / len(ms)
+        return {"value": pts.shape[0] / (v / 1e3), "unit": "points/s", "ms_per_run": v, "runs": len(ms), "labels": lab,
+                "what": "pcl::VoxelBasedSegmentation drop-in class, the reference's call sequence (test:51-76) incl. getVoxelCenters, "
+                        "drawColorMapofPointsinClusters (an XYZRGB cloud of every clustered point) and getClusterIdx() (vector<vector<int>>); "
+                        "pageable host cloud, a fresh object per run"}
+    except Exception as e:   # noqa: BLE001
+        return {"error": str(e)[:300]}
+
+
 def gpu_step(h, capi, cfg, pd, labels_ptr_or_array, on_device):
     """one full segmentation on handle h (points already set) through the C-ABI calls"""
     if CONFIGS[cfg]["mode"] == 0:
@@ -260,6 +293,7 @@ def main():
     ap.add_argument("--ref-points", type=int, default=0, help="--impl reference: 0 = the full scene of the config")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin figure (the C++ drop-in class driven like the reference's test)")
     ap.add_argument("--no-verify", action="store_true", help="N>1 slabs: skip the comparison with one single-GPU run of the whole scene")
     ap.add_argument("--mode", default=None, choices=["slabs", "replicas"],
                     help="N>1: 'slabs' = ONE scene split into spatial slabs with halo voxels + cross-slab merge over NCCL (strong scaling); "
@@ -369,6 +403,12 @@ def main():
     ms_e2e = sum(te) / len(te)
     same = bool(torch.equal(host_lab.cuda(), dev_lab))     # the e2e labels must equal the resident-path labels
 
+    e2e_dropin = None
+    if world == 1 and cmode == 0 and not args.no_dropin:
+        e2e_dropin = dropin_e2e(cfg, pts, pd)
+        if "labels" in e2e_dropin:
+            e2e_dropin["labels_equal_resident_path"] = bool(np.array_equal(e2e_dropin.pop("labels"), dev_lab.cpu().numpy()))
+
     if world > 1:     # max over ranks
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -401,6 +441,7 @@ def main():
                        "clusters": counts["n_clusters_exported"], "octree_depth": counts["octree_depth"]},
             "e2e": {"value": total_points / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": 12 * n,
                     "d2h_bytes_per_step": 4 * n, "ms_per_step": ms_e2e, "labels_equal_resident_path": same},
+            "e2e_dropin": e2e_dropin,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                          "frac": dom["GBps"] / peak, "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes": dom["alg_bytes"],

@@ -2,6 +2,9 @@
 // sequence of the reference's usage snippet (reference file `test`, lines 51-76) using the drop-in
 // header, on a raw float32 xyz file, and writes canonical labels for comparison with the oracle.
 //   dropin_vgs <xyz.f32> <n> <labels.i32> voxel graph sig_p sig_n sig_o sig_e sig_c sig_w cut points_min adjacency_min voxels_min
+// VGS_DROPIN_REPEAT=k: the whole sequence k times (a fresh object each time); prints the wall-clock milliseconds of every run
+// after the first (bench.py's e2e_dropin: pageable 16-byte-stride cloud in, getClusterIdx() out).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -26,7 +29,11 @@ int main(int argc, char** argv) {
     fclose(f);
     for (long i = 0; i < n; i++) input_cloud->push_back(pcl::PointXYZ(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]));
   }
+  const char* rep_env = getenv("VGS_DROPIN_REPEAT");
+  const int repeat = rep_env ? atoi(rep_env) : 1;
   try {
+   for (int rep = 0; rep < repeat; rep++) {
+    const auto t0 = std::chrono::steady_clock::now();
     double min_x = 0, min_y = 0, min_z = 0, max_x = 0, max_y = 0, max_z = 0;
     pcl::PointCloud<pcl::PointXYZRGB>::Ptr clustered_cloud(new PCXYZRGB);
     std::vector<pcl::PointXYZ, Eigen::aligned_allocator<pcl::PointXYZ>> voxel_centers;
@@ -54,6 +61,8 @@ int main(int argc, char** argv) {
     // output (test:74-76)
     voxel_structure.drawColorMapofPointsinClusters(clustered_cloud);
     std::vector<std::vector<int>> clusters_points_idx = voxel_structure.getClusterIdx();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (repeat > 1) { if (rep > 0) printf("dropin_ms %.3f\n", ms); if (rep + 1 < repeat) continue; }
 
     std::vector<int> lab((size_t)n, -1);
     for (auto& cl : clusters_points_idx) {
@@ -66,6 +75,7 @@ int main(int argc, char** argv) {
     fclose(f);
     printf("voxels %d centers %zu clusters_all %d exported %zu coloured_points %zu\n", nvox, voxel_centers.size(),
            voxel_structure.getClusterNum(), clusters_points_idx.size(), clustered_cloud->size());
+   }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;

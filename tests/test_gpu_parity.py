@@ -382,6 +382,18 @@ def test_vgs_far_from_origin(built_lib):
     _compare_vgs(xyz, g, r)
 
 
+def test_vgs_deep_octree_two_sites(built_lib):
+    """two patches 700 m apart: a 13-level octree (> 32-bit sort keys, occupancy / id grids over a 4 700-cell range) — the
+    lattice searches must stay on the grid path and equal the oracle"""
+    a = scenes.construction_site(120_000, seed=1, extent=8.0)
+    b = scenes.construction_site(120_000, seed=2, extent=8.0) + np.array([700.0, 0.0, 0.0], np.float32)
+    xyz = np.concatenate([a, b], axis=0)
+    xyz = np.ascontiguousarray(xyz[np.random.default_rng(5).permutation(xyz.shape[0])])
+    g = gpu_stages(xyz)
+    assert g["counts"]["octree_depth"] >= 13
+    _compare_vgs(xyz, g, oracle.run(xyz, math=1))
+
+
 def test_svgs_tiny(built_lib):
     rng = np.random.default_rng(2)
     xyz = (rng.random((500, 3)) * np.array([2.0, 2.0, 0.02])).astype(np.float32) + 0.5

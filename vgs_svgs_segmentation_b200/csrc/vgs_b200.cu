@@ -80,6 +80,10 @@ struct vgs_context {
   int64_t n_used = 0, n_adj = 0, n_pairs = 0, max_n = 0, n_singles = 0, n_attached = 0, closest_rounds = 0;
   int last_voxels_min = std::numeric_limits<int>::min();
   bool have_cluster_stats = false;
+  bool have_csr = false;            // cluster export (vgs_get_clusters_csr) cached on the device
+  int csr_min_excl = 0;
+  int64_t csr_total = 0;
+  DBuf csr_off, csr_idx;
   int64_t n_clusters_all = 0, n_clusters_exp = 0;
   int points_min = 0;
   float graph_size = 0;
@@ -489,7 +493,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
   DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm,
@@ -1243,7 +1247,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
   h->have_segments = false;
-  h->have_cluster_stats = false;
+  h->have_cluster_stats = false; h->have_csr = false;
   h->conn0_is_mask = false;
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
@@ -1406,7 +1410,7 @@ static vgs_status stage_mutual(vgs_handle h) {
 static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_thred, int adjacency_min) {
   CK(cudaSetDevice(h->device));
   const int64_t nu = h->nu;
-  h->have_cluster_stats = false;
+  h->have_cluster_stats = false; h->have_csr = false;
   GraphParams gp;
   gp.pp = PairParams{sg->sig_p, sg->sig_n, sg->sig_o, sg->sig_e, sg->sig_c, sg->sig_w, h->mode == VGS_MODE_SVGS ? 1 : 0};
   gp.cut = cut_thred;
@@ -1522,37 +1526,44 @@ vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_cluster
   CK(cudaSetDevice(h->device));
   vgs_status s = ensure_cluster_stats(h, voxels_min);
   if (s) return s;
-  // Output formatting of a finished result: canonical labels come from the device; grouping the
-  // point indices by label into the reference's vector<vector<int>> layout is done here.
-  const int64_t n = h->n;
-  CK(stream_wait(h->stream));
-  // cluster order of the reference = ascending smallest voxel id (clusteringVoxels seeds, VS.h:2064);
-  // root ids are exactly those seeds.  Fetch per-point unit + per-unit root to order clusters.
-  std::vector<int32_t> root((size_t)h->nu);
-  CK(cudaMemcpy(root.data(), h->root.p, (size_t)h->nu * 4, cudaMemcpyDeviceToHost));
-  std::vector<uint32_t> csize((size_t)h->nu), ustart((size_t)h->nu + 1), perm((size_t)n);
-  CK(cudaMemcpy(csize.data(), h->csize.p, (size_t)h->nu * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ustart.data(), h->ustart.p, ((size_t)h->nu + 1) * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(perm.data(), h->d_perm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  // The grouping is done on the device (cluster rank by a scan over the exported roots, voxels ordered by cluster with one
+  // stable radix sort, point indices copied voxel by voxel) and cached: the size query and the fetch of the drop-in
+  // classes cost one pass.  Cluster order = ascending smallest voxel id = the seeds of clusteringVoxels (VS.h:2064).
   const int min_excl = h->mode == VGS_MODE_SVGS ? -1 : voxels_min;
-  std::vector<int64_t> cl_of_root((size_t)h->nu, -1);
-  std::vector<int64_t> sizes;
-  for (int64_t u = 0; u < h->nu; u++)
-    if (root[u] == (int32_t)u && (int)csize[u] > min_excl) { cl_of_root[u] = (int64_t)sizes.size(); sizes.push_back(0); }
-  for (int64_t u = 0; u < h->nu; u++) { int64_t c = cl_of_root[root[u]]; if (c >= 0) sizes[c] += ustart[u + 1] - ustart[u]; }
-  int64_t total = 0;
-  for (auto v : sizes) total += v;
-  if (n_clusters) *n_clusters = (int64_t)sizes.size();
-  if (n_points_total) *n_points_total = total;
+  const int64_t nu = h->nu;
+  if (!(h->have_csr && h->csr_min_excl == min_excl)) {
+    const uint32_t nc = (uint32_t)h->n_clusters_exp;
+    CK(h->flags.reserve((size_t)nu * 4 + 16)); CK(h->scan.reserve((size_t)nu * 4 + 16));
+    LAUNCH(k_export_flags, (unsigned)cdiv(nu, 256), 256, 0, h->root.as<int>(), h->csize.as<uint32_t>(), nu, min_excl, h->flags.as<uint32_t>());
+    if ((s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), nu, nullptr))) return s;
+    CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
+    CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
+    LAUNCH(k_export_keys, (unsigned)cdiv(nu, 256), 256, 0, h->root.as<int>(), h->csize.as<uint32_t>(), h->scan.as<uint32_t>(), nu, min_excl, nc,
+           h->ckeysA.as<uint32_t>(), h->cvalsA.as<uint32_t>());
+    int bits = 1;
+    while ((1ull << bits) <= (unsigned long long)nc) bits++;
+    uint32_t* sk; uint32_t* sv;
+    if ((s = radix_sort<uint32_t>(h, nu, bits, &sk, &sv, h->ckeysA.as<uint32_t>(), h->ckeysB.as<uint32_t>(), h->cvalsA.as<uint32_t>(),
+                                  h->cvalsB.as<uint32_t>()))) return s;
+    LAUNCH(k_export_sizes, (unsigned)cdiv(nu, 256), 256, 0, sk, sv, h->ustart.as<uint32_t>(), nu, nc, h->flags.as<uint32_t>());
+    unsigned long long total = 0;
+    if ((s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), nu, &total))) return s;
+    CK(h->csr_off.reserve(((size_t)nc + 1) * 8 + 16)); CK(h->csr_idx.reserve((size_t)total * 4 + 16));
+    LAUNCH(k_export_points, (unsigned)cdiv(nu * 32, 128), 128, 0, sk, sv, h->scan.as<uint32_t>(), h->ustart.as<uint32_t>(), h->d_perm, nu, nc,
+           h->csr_off.as<long long>(), h->csr_idx.as<int32_t>());
+    const long long tot = (long long)total;
+    CK(cudaMemcpyAsync(h->csr_off.as<long long>() + nc, &tot, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(stream_wait(h->stream));
+    h->csr_total = (int64_t)total;
+    h->have_csr = true; h->csr_min_excl = min_excl;
+  }
+  if (n_clusters) *n_clusters = h->n_clusters_exp;
+  if (n_points_total) *n_points_total = h->csr_total;
   if (offsets && point_idx) {
-    std::vector<int64_t> cur(sizes.size() + 1, 0);
-    for (size_t c = 0; c < sizes.size(); c++) cur[c + 1] = cur[c] + sizes[c];
-    for (size_t c = 0; c <= sizes.size(); c++) offsets[c] = cur[c];
-    for (int64_t u = 0; u < h->nu; u++) {
-      int64_t c = cl_of_root[root[u]];
-      if (c < 0) continue;
-      for (uint32_t p = ustart[u]; p < ustart[u + 1]; p++) point_idx[cur[c]++] = (int32_t)perm[p];
-    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
+    CK(cudaMemcpyAsync(offsets, h->csr_off.p, ((size_t)h->n_clusters_exp + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->csr_total > 0) CK(cudaMemcpyAsync(point_idx, h->csr_idx.p, (size_t)h->csr_total * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(stream_wait(h->stream));
   }
   return VGS_OK;
 }

@@ -838,4 +838,44 @@ __global__ void __launch_bounds__(256) k_point_labels(const uint32_t* __restrict
   if (point_unit) point_unit[i] = pu;
 }
 
+// ---- cluster export (drawColorMapofPointsinClusters VS.h:947-1014 / getClusterIdx VS.h:117) on the device:
+//      exported clusters in ascending seed (= root) id, voxels ascending inside a cluster, points ascending inside a voxel ----
+// flag of the exported roots (scanned into the cluster rank)
+__global__ void __launch_bounds__(256) k_export_flags(const int* __restrict__ root, const uint32_t* __restrict__ csize, int64_t nu, int min_size_excl,
+                                                    uint32_t* __restrict__ flag) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < nu) flag[u] = (root[u] == (int)u && (int)csize[u] > min_size_excl) ? 1u : 0u;
+}
+// sort key of a voxel = rank of its cluster (not exported: nclusters, sorts last); value = voxel id
+__global__ void __launch_bounds__(256) k_export_keys(const int* __restrict__ root, const uint32_t* __restrict__ csize, const uint32_t* __restrict__ rank,
+                                                   int64_t nu, int min_size_excl, uint32_t nclusters, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu) return;
+  const int r = root[u];
+  keys[u] = (int)csize[r] > min_size_excl ? rank[r] : nclusters;
+  vals[u] = (uint32_t)u;
+}
+// number of points of the voxel at every sorted position (0 for the voxels that are not exported)
+__global__ void __launch_bounds__(256) k_export_sizes(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svox, const uint32_t* __restrict__ ustart,
+                                                    int64_t nu, uint32_t nclusters, uint32_t* __restrict__ sz) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nu) return;
+  const uint32_t u = svox[p];
+  sz[p] = skeys[p] < nclusters ? ustart[u + 1] - ustart[u] : 0u;
+}
+// one warp per sorted position: the voxel's point indices to their place; the first voxel of a cluster files its offset
+__global__ void __launch_bounds__(128) k_export_points(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svox, const uint32_t* __restrict__ dst,
+                                                     const uint32_t* __restrict__ ustart, const uint32_t* __restrict__ perm, int64_t nu,
+                                                     uint32_t nclusters, long long* __restrict__ offsets, int32_t* __restrict__ point_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= nu) return;
+  const uint32_t c = skeys[p];
+  if (c >= nclusters) return;
+  const uint32_t u = svox[p], d = dst[p], s = ustart[u], n = ustart[u + 1] - s;
+  if (lane == 0 && (p == 0 || skeys[p - 1] != c)) offsets[c] = (long long)d;
+  for (uint32_t i = lane; i < n; i += 32) point_idx[d + i] = (int32_t)perm[s + i];
+}
+
 }  // namespace vgs
