@@ -119,18 +119,21 @@ class VoxelBasedSegmentation {
     std::vector<int32_t> idx((size_t)(nt > 0 ? nt : 1));
     ck(vgs_get_clusters_csr(h_, cluster_voxels_min_, &nc, &nt, off.data(), idx.data()));
     clusters_point_idx_.assign((size_t)nc, std::vector<int>());
+    const bool paint = output_cloud && points_cloud_;
+    size_t at = 0;
+    if (paint) { at = output_cloud->points.size(); output_cloud->points.resize(at + (size_t)nt); }   // one allocation for all clustered points
     for (int64_t c = 0; c < nc; c++) {
       clusters_point_idx_[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
-      if (output_cloud && points_cloud_) {
+      if (paint) {
         uint32_t hsh = (uint32_t)c * 2654435761u;
         for (int p : clusters_point_idx_[c]) {
-          pcl::PointXYZRGB q;
+          pcl::PointXYZRGB& q = output_cloud->points[at++];
           q.x = points_cloud_->points[p].x; q.y = points_cloud_->points[p].y; q.z = points_cloud_->points[p].z;
           q.r = (uint8_t)(hsh >> 8); q.g = (uint8_t)(hsh >> 16); q.b = (uint8_t)(hsh >> 24);
-          output_cloud->push_back(q);
         }
       }
     }
+    if (paint) { output_cloud->width = (std::uint32_t)output_cloud->points.size(); output_cloud->height = 1; }
   }
 
   // ---- display exports (VS.h:424-945, 1016-1104).  Voxels are visited in voxel-id order (= the leaf

@@ -111,7 +111,7 @@ struct vgs_context {
   DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
   bool use_idgrid = false;
   uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
-  DBuf fallback, uflags, singles;
+  DBuf fallback, uflags, singles, used_list;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -493,7 +493,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
   DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm,
@@ -1271,15 +1271,22 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     unsigned* d_err = h->small.as<unsigned>() + 200;
     uint32_t* d_fb_count = h->small.as<uint32_t>() + 201;
     CK(cudaMemsetAsync(d_err, 0, 8, h->stream));
+    // compact list of the used voxels (id order): one warp per USED voxel in the two kernels below
+    const int64_t n_used = h->n_used;
     {
       StageTimer tpc(h, &h->tm.pair_cache_ms, 11);
       CK(h->rows.reserve((size_t)h->n_rows * 16 + 64));
       KTimer krf(h, K_ROWS_FILL);
-      LAUNCH(k_rows_fill, (unsigned)cdiv(nu, RF_WARPS), RF_WARPS * 32, RF_WARPS * rows_fill_smem_warp(2 * lg.r2c + 1), h->key3.as<uint32_t>(), h->rec.as<float>(), nu, lg,
-             h->grid, h->bm_used.as<uint32_t>(),
+      CK(h->used_list.reserve((size_t)nu * 4 + 16));
+      CK(h->flags.reserve((size_t)nu * 4 + 16)); CK(h->scan.reserve((size_t)nu * 4 + 16));
+      LAUNCH(k_used_flags, (unsigned)cdiv(nu, 256), 256, 0, h->uflags.as<uint8_t>(), nu, h->flags.as<uint32_t>());
+      { vgs_status s_ = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), nu, nullptr); if (s_) return s_; }
+      LAUNCH(k_used_write, (unsigned)cdiv(nu, 256), 256, 0, h->uflags.as<uint8_t>(), h->scan.as<uint32_t>(), nu, h->used_list.as<uint32_t>());
+      if (n_used > 0)
+      LAUNCH(k_rows_fill, (unsigned)cdiv(n_used, RF_WARPS), RF_WARPS * 32, RF_WARPS * rows_fill_smem_warp(2 * lg.r2c + 1), h->used_list.as<uint32_t>(),
+             (uint32_t)n_used, h->key3.as<uint32_t>(), h->rec.as<float>(), lg, h->grid, h->bm_used.as<uint32_t>(),
              h->d_pc_cols.as<int4>(), (int)h->pc_cols_host.size(), h->use_idgrid ? h->idgrid.as<int32_t>() : nullptr, h->tk.as<unsigned long long>(),
-             h->tv.as<uint32_t>(), h->hmask, gp.pp,
-             h->uflags.as<uint8_t>(), h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_err);
+             h->tv.as<uint32_t>(), h->hmask, gp.pp, h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_err);
       krf.stop();
       if (h->n_long > 0) {   // rows longer than the shared-memory assembly of k_rows_fill
         KTimer krs(h, K_ROWS_SORT);
@@ -1296,10 +1303,13 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(h->fallback.reserve((size_t)nu * 4 + 16));
     KTimer kgr(h, K_GRAPH_ROWS);
     const int ncap = (int)std::min<int64_t>(LR_NCAP, (h->max_n + 3) & ~(int64_t)3);   // vertices of the largest neighbourhood
-    LAUNCH(k_local_graph_rows, (unsigned)cdiv(nu, LR_WARPS), 32 * LR_WARPS, LR_WARPS * lr_smem_bytes(h->lbits, mw, ncap), (int64_t)0, nu,
-           h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho, h->lbits, mw, ncap,
-           h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
-           h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, h->lr_target, d_dbg);
+    CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));            // unused voxels: empty connect lists
+    CK(cudaMemsetAsync(h->conn_mask.p, 0, (size_t)nu * mw * 4, h->stream));
+    if (n_used > 0)
+      LAUNCH(k_local_graph_rows, (unsigned)cdiv(n_used, LR_WARPS), 32 * LR_WARPS, LR_WARPS * lr_smem_bytes(h->lbits, mw, ncap), h->used_list.as<uint32_t>(),
+             (uint32_t)n_used, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho,
+             h->lbits, mw, ncap, h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
+             h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, h->lr_target, d_dbg);
     kgr.stop();
     uint32_t fe[2] = {0, 0};   // [0] = error bits of the fill kernels, [1] = units handed back
     CK(cudaMemcpyAsync(fe, d_err, 8, cudaMemcpyDeviceToHost, h->stream));

@@ -779,11 +779,14 @@ __global__ void __launch_bounds__(128) k_cc_hook(const uint32_t* __restrict__ ad
   if (own && !(own[u] & 1)) return;
   const uint32_t off = adj_off[u];
   const int c = (int)cnt1[u];
+  // after the pointer jumping nearly every unit points at its root: two units with the same parent are already in
+  // one tree, which one (coalesced + one random) load pair decides without walking the trees
+  const int pu = ((volatile int*)parent)[u];
   for (int e = lane; e < c; e += 32) {
     int j = idx1[off + e];
-    if (j > (int)u) uf_union(parent, (int)u, j);
+    if (j > (int)u && ((volatile int*)parent)[j] != pu) uf_union(parent, (int)u, j);
   }
-  if (lane == 0) { int a = attach[u]; if (a >= 0 && (!own || a < 0x40000000)) uf_union(parent, (int)u, a); }
+  if (lane == 0) { int a = attach[u]; if (a >= 0 && (!own || a < 0x40000000) && ((volatile int*)parent)[a] != pu) uf_union(parent, (int)u, a); }
 }
 __global__ void __launch_bounds__(256) k_cc_flatten(int* parent, int64_t n, int* __restrict__ root) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -101,8 +101,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ ke
   hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
+// (launch bound 4 CTAs per SM: without it the unrolled ranking takes 127 registers, 2 CTAs per SM, and the pass is
+//  latency-bound at 21 % active warps — ncu, profiles/r02)
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                           K* __restrict__ kout, uint32_t* __restrict__ vout, int64_t n,
                                                           int shift, const uint32_t* __restrict__ offs, int64_t nblk) {
   __shared__ uint32_t wc[RS_WARPS][256];

@@ -101,23 +101,31 @@ __global__ void __launch_bounds__(256) k_adj_count(const uint32_t* __restrict__ 
                                                  uint32_t* __restrict__ long_rows, CountStats* __restrict__ stats) {
   __shared__ unsigned long long s_sum[8];
   __shared__ unsigned s_max[8], s_used[8];
+  __shared__ float s_cax[8][96];      // per warp: centres of the stencil cells per axis (rho <= 15)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t v = (int64_t)blockIdx.x * 8 + w;
   unsigned long long my_sum = 0; unsigned my_max = 0, my_used = 0;
   if (v < nv) {
     const int kx = (int)key3[3 * v], ky = (int)key3[3 * v + 1], kz = (int)key3[3 * v + 2];
-    const float qx = centre_of(kx, lg.res_f, lg.mnx), qy = centre_of(ky, lg.res_f, lg.mny), qz = centre_of(kz, lg.res_f, lg.mnz);
+    // centre coordinates of the 2 rho + 1 cells per axis, once per voxel (the float test needs FLANN's float centres)
+    const int S = 2 * lg.rho + 1;
+    float* cax = s_cax[w];
+    for (int t = lane; t < 3 * S; t += 32) {
+      const int a = t / S, d = t - a * S;
+      cax[a * 32 + d] = a == 0 ? centre_of(kx - lg.rho + d, lg.res_f, lg.mnx) : (a == 1 ? centre_of(ky - lg.rho + d, lg.res_f, lg.mny) : centre_of(kz - lg.rho + d, lg.res_f, lg.mnz));
+    }
+    __syncwarp();
+    const float qx = cax[lg.rho], qy = cax[32 + lg.rho], qz = cax[64 + lg.rho];
     int cnt = 0;
     for (int ci = lane; ci < n_adj_cols; ci += 32) {
       const int4 o = adj_cols[ci];
       const int x = kx + o.x, y = ky + o.y;
-      uint32_t hits = bg_run(bm_all, bg_bit(g, x, y, kz - lg.rho), 2 * lg.rho + 1) & (uint32_t)o.z;
-      const float cx = centre_of(x, lg.res_f, lg.mnx), cy = centre_of(y, lg.res_f, lg.mny);
+      uint32_t hits = bg_run(bm_all, bg_bit(g, x, y, kz - lg.rho), S) & (uint32_t)o.z;
+      const float cx = cax[o.x + lg.rho], cy = cax[32 + o.y + lg.rho];
       while (hits) {
         const int j = __ffs(hits) - 1;
         hits &= hits - 1;
-        const float cz = centre_of(kz - lg.rho + j, lg.res_f, lg.mnz);
-        cnt += flann_d2(qx, qy, qz, cx, cy, cz) < lg.r2 ? 1 : 0;
+        cnt += flann_d2(qx, qy, qz, cx, cy, cax[64 + j]) < lg.r2 ? 1 : 0;
       }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -281,6 +289,18 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) k_adj_fill(const uint32_t* __r
   }
 }
 
+// compact list of the used voxels in id order (flag -> exclusive scan -> write): the row and local-graph kernels launch one
+// warp per USED voxel, so no CTA slot is spent on the voxels with too few points
+__global__ void __launch_bounds__(256) k_used_flags(const uint8_t* __restrict__ uflags, int64_t nv, uint32_t* __restrict__ flag) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv) flag[v] = (uflags[v] & F_USED) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_used_write(const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ pos, int64_t nv,
+                                                  uint32_t* __restrict__ list) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv && (uflags[v] & F_USED)) list[pos[v]] = (uint32_t)v;
+}
+
 // ---- stage 4: weight rows.  One 16-byte entry per UNORDERED pair {a, b} of used voxels that can meet in a local graph,
 //      filed in the row of the voxel a whose offset to b is lexicographically positive:
 //        .x = w(a -> b)   .y = w(b -> a)   .z = cell(max weight) << 18 | pack6(d + r2c), d = key_b - key_a   .w = cell(min weight)
@@ -305,17 +325,18 @@ __host__ __device__ inline size_t rows_fill_smem_warp(int S) {
   const size_t qcap = 32 + 32 * (size_t)S;          // a lane queues at most one z-run (<= S hits) per column step
   return (size_t)ROWS_SHORT_CAP * 16 + 2 * (size_t)ROWS_SHORT_CAP * 4 + 64 * 4 + ((qcap * 2 + 15) & ~(size_t)15) + REC_FLOATS * 4;
 }
-__global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __restrict__ key3, const float* __restrict__ rec, int64_t nv, LatticeGeom lg,
+__global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __restrict__ used_list, uint32_t n_used, const uint32_t* __restrict__ key3,
+                                                 const float* __restrict__ rec, LatticeGeom lg,
                                                  BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
                                                  const int32_t* __restrict__ idg, const unsigned long long* __restrict__ tk,
                                                  const uint32_t* __restrict__ tv, uint64_t hmask,
-                                                 PairParams pp, const uint8_t* __restrict__ uflags, const uint32_t* __restrict__ row_off,
+                                                 PairParams pp, const uint32_t* __restrict__ row_off,
                                                  uint4* __restrict__ rows, unsigned* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t v = (int64_t)blockIdx.x * RF_WARPS + w;
-  if (v >= nv) return;
-  if (!(uflags[v] & F_USED)) return;
+  const int64_t li = (int64_t)blockIdx.x * RF_WARPS + w;
+  if (li >= (int64_t)n_used) return;
+  const int64_t v = used_list[li];
   const int r2 = lg.r2c, S = 2 * r2 + 1;
   unsigned char* mine = smraw + (size_t)w * rows_fill_smem_warp(S);
   uint4* ent = reinterpret_cast<uint4*>(mine);                                  // ROWS_SHORT_CAP entries
@@ -548,7 +569,7 @@ __host__ __device__ inline size_t lr_smem_bytes(int lbits, int mwords, int ncap)
 #define VGS_LR_MINB 24
 #endif
 constexpr int LR_WARPS = VGS_LR_WARPS;      // voxels per CTA (independent warps, no block barrier)
-__global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows(int64_t first, int64_t last, const uint32_t* __restrict__ adj_off,
+__global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows(const uint32_t* __restrict__ used_list, uint32_t n_used, const uint32_t* __restrict__ adj_off,
                                                             const int32_t* __restrict__ adj_idx, const uint16_t* __restrict__ adj_code,
                                                             const uint8_t* __restrict__ uflags, float k, int rho, int lbits, int mwords, int ncap,
                                                             const uint32_t* __restrict__ row_off, const uint4* __restrict__ rows,
@@ -558,8 +579,9 @@ __global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows
                                                             unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smraw_all[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t u = first + (int64_t)blockIdx.x * LR_WARPS + wid;
-  if (u >= last) return;
+  const int64_t li = (int64_t)blockIdx.x * LR_WARPS + wid;
+  if (li >= (int64_t)n_used) return;
+  const int64_t u = used_list[li];          // unused voxels keep the empty connect lists the host memset gave them (VS.h:403-409)
   unsigned char* smraw = smraw_all + (size_t)wid * lr_smem_bytes(lbits, mwords, ncap);
   float* C_w = reinterpret_cast<float*>(smraw);                         // LR_CS
   float* s_thr = C_w + LR_CS;                                           // ncap: Int(C) - k/|C| of segment C
@@ -585,11 +607,6 @@ __global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows
   const int S1 = 2 * rho + 1;
 
   for (int i = lane; i < mwords; i += 32) s_mask[i] = 0;
-  if (!(uflags[u] & F_USED)) {          // unused voxels have empty connect lists (VS.h:403-409)
-    for (int i = lane; i < mwords; i += 32) conn_mask[(size_t)u * mwords + i] = 0;
-    if (lane == 0) conn_cnt[u] = 0;
-    return;
-  }
   for (int i = lane; i < nloc / 4; i += 32) reinterpret_cast<uint32_t*>(s_loc)[i] = 0xffffffffu;
   if (lane == 0) s_ndef = 0;
   __syncwarp();
