@@ -117,6 +117,7 @@ struct vgs_context {
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
   int use_pair_cache = 1;           // 0 = evaluate weights inside every local graph (general kernel; VGS_B200_NO_PAIR_CACHE)
   int cc_jumps = 6;                 // pointer-jumping rounds over the initial component forest
+  int lg_order = 0;                 // local-graph launch order: 0 = voxel id, b = by neighbourhood size in 2^b classes, big first (VGS_B200_LG_ORDER)
   int lr_target = LR_TARGET;        // staged entries the local-graph rounds aim at (VGS_B200_LR_TARGET)
   int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
@@ -453,6 +454,7 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg) {
   if (const char* e_nc = getenv("VGS_B200_NO_PAIR_CACHE")) h->use_pair_cache = (e_nc[0] == '1') ? 0 : 1;
   if (const char* e_ff = getenv("VGS_B200_FORCE_FALLBACK")) { int v = atoi(e_ff); if (v >= 1) h->force_fallback = v; }
   if (const char* e_ig = getenv("VGS_B200_IDGRID_MB")) { long long v = atoll(e_ig); if (v >= 0) h->idgrid_budget = (uint64_t)v << 20; }
+  if (const char* e_lo = getenv("VGS_B200_LG_ORDER")) { int v = atoi(e_lo); if (v >= 0 && v <= 8) h->lg_order = v; }
   if (const char* e_lt = getenv("VGS_B200_LR_TARGET")) { int v = atoi(e_lt); if (v >= 8 && v <= 200) h->lr_target = v; }
   if (const char* e_cj = getenv("VGS_B200_CC_JUMPS")) { int v = atoi(e_cj); if (v >= 0 && v <= 32) h->cc_jumps = v; }
   // opt in to large dynamic shared memory (227 KB per CTA on sm_100, static part included)
@@ -1303,10 +1305,24 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
     CK(h->fallback.reserve((size_t)nu * 4 + 16));
     KTimer kgr(h, K_GRAPH_ROWS);
     const int ncap = (int)std::min<int64_t>(LR_NCAP, (h->max_n + 3) & ~(int64_t)3);   // vertices of the largest neighbourhood
+    // launch order: big neighbourhoods first (VGS_B200_LG_ORDER=0: id order)
+    const uint32_t* d_order = h->used_list.as<uint32_t>();
+    if (h->lg_order > 0 && n_used > 0) {
+      CK(h->ckeysA.reserve((size_t)nu * 8 + 16)); CK(h->ckeysB.reserve((size_t)nu * 8 + 16));
+      CK(h->cvalsA.reserve((size_t)nu * 4 + 16)); CK(h->cvalsB.reserve((size_t)nu * 4 + 16));
+      const int shift = h->lg_order >= 8 ? 0 : 8 - h->lg_order;      // lg_order = number of key bits (classes of 2^(8-bits) sizes)
+      LAUNCH(k_order_keys, (unsigned)cdiv(n_used, 256), 256, 0, h->used_list.as<uint32_t>(), (uint32_t)n_used, h->adj_off.as<uint32_t>(), shift,
+             h->ckeysA.as<uint32_t>(), h->cvalsA.as<uint32_t>());
+      uint32_t* ok; uint32_t* ov;
+      vgs_status s_ = radix_sort<uint32_t>(h, n_used, 8 - shift, &ok, &ov, h->ckeysA.as<uint32_t>(), h->ckeysB.as<uint32_t>(), h->cvalsA.as<uint32_t>(),
+                                           h->cvalsB.as<uint32_t>());
+      if (s_) return s_;
+      d_order = ov;
+    }
     CK(cudaMemsetAsync(h->conn0_cnt.p, 0, (size_t)nu * 4, h->stream));            // unused voxels: empty connect lists
     CK(cudaMemsetAsync(h->conn_mask.p, 0, (size_t)nu * mw * 4, h->stream));
     if (n_used > 0)
-      LAUNCH(k_local_graph_rows, (unsigned)cdiv(n_used, LR_WARPS), 32 * LR_WARPS, LR_WARPS * lr_smem_bytes(h->lbits, mw, ncap), h->used_list.as<uint32_t>(),
+      LAUNCH(k_local_graph_rows, (unsigned)cdiv(n_used, LR_WARPS), 32 * LR_WARPS, LR_WARPS * lr_smem_bytes(h->lbits, mw, ncap), d_order,
              (uint32_t)n_used, h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->adj_code.as<uint16_t>(), h->uflags.as<uint8_t>(), cut_thred, lg.rho,
              h->lbits, mw, ncap, h->row_off.as<uint32_t>(), h->rows.as<uint4>(), d_wempty, h->conn0_cnt.as<uint32_t>(), h->conn_mask.as<uint32_t>(),
              h->fallback.as<uint32_t>(), d_fb_count, h->force_fallback, h->lr_target, d_dbg);
@@ -1440,17 +1456,21 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     uint32_t scnt[2] = {0, 0};
     CK(cudaMemcpyAsync(scnt, d_scnt, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
+    // rounds are launched three at a time with one flag each and read back together (a round costs microseconds, a host
+    // round trip more): the fixed point is reached when a round changes nothing
     int rounds = 0;
-    while (scnt[0] > 0) {
-      CK(cudaMemsetAsync(d_changed, 0, 4, h->stream));
-      LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
-             h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
-             h->attach.as<int32_t>(), d_changed);
-      uint32_t changed = 0;
-      CK(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, h->stream));
+    bool more = scnt[0] > 0;
+    while (more) {
+      constexpr int BATCH = 3;
+      CK(cudaMemsetAsync(d_changed, 0, 4 * BATCH, h->stream));
+      for (int b = 0; b < BATCH; b++)
+        LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
+               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
+               h->attach.as<int32_t>(), d_changed + b);
+      uint32_t changed[BATCH] = {0, 0, 0};
+      CK(cudaMemcpyAsync(changed, d_changed, 4 * BATCH, cudaMemcpyDeviceToHost, h->stream));
       CK(stream_wait(h->stream));
-      rounds++;
-      if (!changed) break;
+      for (int b = 0; b < BATCH && more; b++) { rounds++; if (!changed[b]) more = false; }
       if (rounds > 100000) return h->fail(VGS_ERR_LIMIT, "vgs_segment: closest-check did not converge");
     }
     unsigned long long singles = scnt[1];

@@ -301,13 +301,31 @@ __global__ void __launch_bounds__(256) k_used_write(const uint8_t* __restrict__ 
   if (v < nv && (uflags[v] & F_USED)) list[pos[v]] = (uint32_t)v;
 }
 
+// sort key of a used voxel for the local-graph launch order: big neighbourhoods first (longest job first keeps the tail of
+// the launch short); equal sizes stay in id order (stable pass), so neighbours still share their rows in L2
+__global__ void __launch_bounds__(256) k_order_keys(const uint32_t* __restrict__ used_list, uint32_t n_used, const uint32_t* __restrict__ adj_off,
+                                                  int shift, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_used) return;
+  const uint32_t u = used_list[i];
+  const uint32_t n = min(adj_off[u + 1] - adj_off[u], 255u);
+  keys[i] = (255u - n) >> shift;
+  vals[i] = u;
+}
+
 // ---- stage 4: weight rows.  One 16-byte entry per UNORDERED pair {a, b} of used voxels that can meet in a local graph,
 //      filed in the row of the voxel a whose offset to b is lexicographically positive:
 //        .x = w(a -> b)   .y = w(b -> a)   .z = cell(max weight) << 18 | pack6(d + r2c), d = key_b - key_a   .w = cell(min weight)
 //      cell(w) = floor((1 - w) * 4096) orders a row coarsely (k_rows_sort); the consumer sorts exactly inside the cells
 //      it takes.  A row is written by one warp only: no atomics, no scattered stores. ----
 constexpr int ROW_CELLS = 4096;
-constexpr int ROWS_SHORT_CAP = 256;   // rows up to this length are assembled and ordered in shared memory by k_rows_fill; longer ones by k_rows_sort
+#ifndef VGS_ROWS_CAP
+#define VGS_ROWS_CAP 192     // measured (10 M-point site): 256 -> 3.05 ms, 192 -> 2.85 ms, 128 -> 2.72 ms + 0.2 ms of long rows
+#endif
+#ifndef VGS_RF_MINB
+#define VGS_RF_MINB 8
+#endif
+constexpr int ROWS_SHORT_CAP = VGS_ROWS_CAP;   // rows up to this length are assembled and ordered in shared memory by k_rows_fill; longer ones by k_rows_sort
 __host__ __device__ __forceinline__ uint32_t row_cell(float w) {
   // monotone non-increasing in w; NaN and w <= 0 fall into the last cell
   if (!(w > 0.f)) return ROW_CELLS - 1;
@@ -325,7 +343,7 @@ __host__ __device__ inline size_t rows_fill_smem_warp(int S) {
   const size_t qcap = 32 + 32 * (size_t)S;          // a lane queues at most one z-run (<= S hits) per column step
   return (size_t)ROWS_SHORT_CAP * 16 + 2 * (size_t)ROWS_SHORT_CAP * 4 + 64 * 4 + ((qcap * 2 + 15) & ~(size_t)15) + REC_FLOATS * 4;
 }
-__global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __restrict__ used_list, uint32_t n_used, const uint32_t* __restrict__ key3,
+__global__ void __launch_bounds__(RF_WARPS * 32, VGS_RF_MINB) k_rows_fill(const uint32_t* __restrict__ used_list, uint32_t n_used, const uint32_t* __restrict__ key3,
                                                  const float* __restrict__ rec, LatticeGeom lg,
                                                  BitGrid g, const uint32_t* __restrict__ bm_used, const int4* __restrict__ pc_cols, int n_pc_cols,
                                                  const int32_t* __restrict__ idg, const unsigned long long* __restrict__ tk,
@@ -378,29 +396,37 @@ __global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __r
     }
     done += cnt;
   };
-  for (int base = 0; base < n_pc_cols; base += 32) {
-    const int ci = base + lane;
-    uint32_t hits = 0;
-    int cbase = 0;
-    if (ci < n_pc_cols) {
-      const int4 o = pc_cols[ci];
-      hits = bg_run(bm_used, bg_bit(g, kx + o.x, ky + o.y, kz - r2), S) & (uint32_t)o.z;
-      cbase = ((o.x + r2) * S + (o.y + r2)) * S;
+  // one call site of the pair evaluation (it is ~1 100 instructions: a second copy does not fit the instruction cache)
+  for (int base = 0;; base += 32) {
+    const bool flush = base >= n_pc_cols;
+    if (!flush) {
+      const int ci = base + lane;
+      uint32_t hits = 0;
+      int cbase = 0;
+      if (ci < n_pc_cols) {
+        const int4 o = pc_cols[ci];
+        hits = bg_run(bm_used, bg_bit(g, kx + o.x, ky + o.y, kz - r2), S) & (uint32_t)o.z;
+        cbase = ((o.x + r2) * S + (o.y + r2)) * S;
+      }
+      const int cnt = __popc(hits);
+      const int incl = (int)warp_incl_scan((unsigned)cnt, lane);
+      int pos = npend + incl - cnt;
+      while (hits) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        pend[pos++] = (unsigned short)(cbase + j);
+      }
+      npend += __shfl_sync(0xffffffffu, incl, 31);
     }
-    const int cnt = __popc(hits);
-    const int incl = (int)warp_incl_scan((unsigned)cnt, lane);
-    int pos = npend + incl - cnt;
-    while (hits) {
-      const int j = __ffs(hits) - 1;
-      hits &= hits - 1;
-      pend[pos++] = (unsigned short)(cbase + j);
+    __syncwarp();
+    while (npend >= 32 || (flush && npend > 0)) {
+      const int take = min(32, npend);
+      process(npend - take, take);
+      npend -= take;
     }
-    npend += __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
-    while (npend >= 32) { process(npend - 32, 32); npend -= 32; }
-    __syncwarp();
+    if (flush) break;
   }
-  process(0, npend);
   if (!in_smem) return;
   if (done != len) { if (lane == 0) atomicOr(err, 8u); return; }     // count and fill disagree: cannot happen
   __syncwarp();
@@ -444,6 +470,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) k_rows_fill(const uint32_t* __r
     }
   }
   for (int i = lane; i < len; i += 32) rows[my_row + i] = ent[kA[i] & 255u];
+  static_assert(ROWS_SHORT_CAP <= 256, "the sort words carry an 8-bit position");
 }
 
 // ---- rows ordered by weight cell: LSD radix sort (2 passes x 6 bits) of one row per warp in shared memory ----
