@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
             const int keep = __shfl_sync(0xffffffffu, a_wins ? sa : sb, Lm);
             const int drop = __shfl_sync(0xffffffffu, a_wins ? sb : sa, Lm);
             const float wl = __shfl_sync(0xffffffffu, w, Lm);
+            __syncwarp();     // every lane has read its segments / thresholds (the ballot above orders them; this states it)
             for (int v = lane; v < n; v += 32) if (s_seg[v] == drop) s_seg[v] = (unsigned short)keep;
             if (lane == 0) { s_int[keep] = wl; s_size[keep] = (unsigned short)(s_size[keep] + s_size[drop]); s_size[drop] = 0; }
             nseg--;
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(THREADS) k_local_graph2(const uint32_t* __rest
             if (nseg <= 1) { stop = true; break; }
           }
         }
+        __syncwarp();
         if (lane == 0) {
           s_nseg = nseg;
           if (nseg <= 1 || below) s_done = 1;
