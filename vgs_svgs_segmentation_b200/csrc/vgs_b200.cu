@@ -230,18 +230,21 @@ vgs_status build_units(vgs_handle h, const K* keys, int64_t n_valid, int64_t* n_
                        DBuf* ukey = nullptr, DBuf* pos_unit = nullptr) {
   if (!ustart) { ustart = &h->ustart; ukey = &h->ukey; pos_unit = &h->pos_unit; }
   if (n_valid <= 0) { *n_units = 0; return VGS_OK; }
-  CK(h->flags.reserve((size_t)n_valid * 4));
-  CK(h->scan.reserve((size_t)n_valid * 4));
   CK(pos_unit->reserve((size_t)n_valid * 4));
-  LAUNCH(k_head_flags<K>, (unsigned)cdiv(n_valid, 256), 256, 0, keys, n_valid, h->flags.as<uint32_t>());
+  const int64_t nt = std::max<int64_t>(1, cdiv(n_valid, SC_TILE));
+  CK(h->tiles.reserve((size_t)(nt + 1) * 4 + 16));
+  CK(h->small.reserve(4096));
+  unsigned long long* d_total = h->small.as<unsigned long long>() + 8;
+  LAUNCH(k_heads_reduce<K>, (unsigned)nt, SC_THREADS, 0, keys, n_valid, h->tiles.as<uint32_t>());
+  LAUNCH(k_scan_tiles, 1, 1024, 0, h->tiles.as<uint32_t>(), nt, d_total);
   unsigned long long total = 0;
-  vgs_status s = scan_u32(h, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid, &total);
-  if (s) return s;
+  CK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(stream_wait(h->stream));
   *n_units = (int64_t)total;
   CK(ustart->reserve((size_t)(total + 1) * 4));
   CK(ukey->reserve((size_t)(total + 1) * 8));
-  LAUNCH(k_head_write<K>, (unsigned)cdiv(n_valid, 256), 256, 0, keys, h->flags.as<uint32_t>(), h->scan.as<uint32_t>(), n_valid,
-         ustart->as<uint32_t>(), ukey->as<uint64_t>(), pos_unit->as<uint32_t>());
+  LAUNCH(k_heads_down<K>, (unsigned)nt, SC_THREADS, 0, keys, n_valid, h->tiles.as<uint32_t>(), ustart->as<uint32_t>(), ukey->as<uint64_t>(),
+         pos_unit->as<uint32_t>());
   uint32_t endv = (uint32_t)n_valid;
   CK(cudaMemcpyAsync(ustart->as<uint32_t>() + total, &endv, 4, cudaMemcpyHostToDevice, h->stream));
   return VGS_OK;
@@ -290,8 +293,8 @@ struct OctState {
   }
 };
 
-vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* found) {
-  unsigned long long* d_found = h->small.as<unsigned long long>();
+vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* found, float* xyz3) {
+  unsigned long long* d_found = h->small.as<unsigned long long>();      // [0] index, [1..2] the point's coordinates (3 floats)
   Box b;
   for (int a = 0; a < 3; a++) { b.mn[a] = st.mn[a]; b.mx[a] = st.mx[a]; }
   int64_t window = 1 << 18;
@@ -303,10 +306,11 @@ vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* 
     CK(cudaMemcpyAsync(d_found, &init, 8, cudaMemcpyHostToDevice, h->stream));
     int64_t blocks = std::min<int64_t>(cdiv(e - s, 256), 148 * 8);
     LAUNCH(k_find_outside, (unsigned)blocks, 256, 0, h->d_xyz, h->stride, s, e, b, st.defined ? 1 : 0, d_found, nullptr);
-    unsigned long long r = 0;
-    CK(cudaMemcpyAsync(&r, d_found, 8, cudaMemcpyDeviceToHost, h->stream));
+    LAUNCH(k_fetch_found, 1, 1, 0, h->d_xyz, h->stride, d_found, reinterpret_cast<float*>(d_found + 1));
+    struct { unsigned long long idx; float p[4]; } r;
+    CK(cudaMemcpyAsync(&r, d_found, 24, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
-    if (r != ~0ull) { *found = (int64_t)r; return VGS_OK; }
+    if (r.idx != ~0ull) { *found = (int64_t)r.idx; xyz3[0] = r.p[0]; xyz3[1] = r.p[1]; xyz3[2] = r.p[2]; return VGS_OK; }
     s = e;
     window *= 8;
   }
@@ -638,12 +642,10 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
     int64_t cursor = 0;
     while (true) {
       int64_t idx;
-      vgs_status s = find_next(h, cursor, ob.st, &idx);
+      float p[3];
+      vgs_status s = find_next(h, cursor, ob.st, &idx, p);
       if (s) return s;
       if (idx >= n) break;
-      float p[3];
-      CK(cudaMemcpyAsync(p, h->d_xyz + idx * h->stride, 12, cudaMemcpyDeviceToHost, h->stream));
-      CK(stream_wait(h->stream));
       if (const char* why = ob.add(idx, p)) return h->fail(VGS_ERR_LIMIT, std::string("vgs_voxelize: ") + why);
       cursor = idx + 1;
     }
@@ -911,7 +913,7 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   CK(cudaMemsetAsync(d_used, 0, 8, h->stream));
   CK(h->uflags.reserve((size_t)nu + 16));
   KTimer kf(h, K_FEATURES);
-  LAUNCH(k_features, (unsigned)cdiv(nu, 128), 128, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
+  LAUNCH(k_features, (unsigned)cdiv(nu, FEAT_THREADS), FEAT_THREADS, 0, h->d_xyz, h->stride, h->d_perm, h->ustart.as<uint32_t>(), nu, points_min,
          h->mode == VGS_MODE_SVGS ? 1 : 0, h->rec.as<float>(), h->uflags.as<uint8_t>(), d_used);
   kf.stop();
   if (h->mode == VGS_MODE_SVGS) {   // VGS: the count arrives with the adjacency totals (one host round trip less)
@@ -1640,7 +1642,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   cudaSetDevice(h->device);
   resolve_timers(h);
   static const char* names[vgs_context::NK] = {
-      "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_head_flags + scan + k_head_write + k_voxel_keys",
+      "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_heads_reduce + k_scan_tiles + k_heads_down + k_voxel_keys",
       "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
       "adjacency fill: k_adj_fill", "weight rows: k_rows_fill (evaluate, order by weight cell, write once)", "weight rows: k_rows_sort (rows longer than 256 entries)", "local graphs: k_local_graph_rows",
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",

@@ -460,11 +460,9 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
         mine[lr].gidx = std::numeric_limits<long long>::max();
         if (t.origin_done) return VGS_OK;
         int64_t idx;
-        vgs_status s_ = find_next(h, t.cursor, ob.st, &idx);
+        vgs_status s_ = find_next(h, t.cursor, ob.st, &idx, mine[lr].p);
         if (s_) return s_;
         if (idx >= t.n) { t.origin_done = true; return VGS_OK; }   // the box only grows: this slice is inside for good
-        CK(cudaMemcpyAsync(mine[lr].p, t.d_xyz + idx * t.stride, 12, cudaMemcpyDeviceToHost, st));
-        CK(stream_wait(st));
         mine[lr].gidx = t.gfirst + idx;
         t.found = idx;
         return VGS_OK;

@@ -59,6 +59,14 @@ __global__ void __launch_bounds__(256) k_find_outside(const float* __restrict__ 
   }
 }
 
+// the coordinates of the point k_find_outside found, next to its index (one host read per growth epoch instead of two)
+__global__ void k_fetch_found(const float* __restrict__ xyz, int stride, const unsigned long long* __restrict__ found, float* __restrict__ out3) {
+  const unsigned long long i = *found;
+  if (i == ~0ull) return;
+  const float* p = xyz + i * stride;
+  out3[0] = p[0]; out3[1] = p[1]; out3[2] = p[2];
+}
+
 // ---- stage 1a: octree key per point -> sortable 64-bit code, value = point index.
 //      key.a = (unsigned)((p.a - min_a)/res) in double (genOctreeKeyforPoint).  12 B read, 12 B written. ----
 //      K = uint32_t when the key (3 * depth bits + the sentinel bit) fits 32 bits: the sort then moves 8 instead of 12 bytes
@@ -116,46 +124,98 @@ __global__ void __launch_bounds__(256) k_seed_cell_keys(const float* __restrict_
   keys[i] = morton_encode(cx & 0x1fffffu, cy & 0x1fffffu, cz & 0x1fffffu);
 }
 
-// ---- stage 1b: segment heads of the sorted keys ----
+// ---- stage 1b: segment heads of the sorted keys.  A head is a position whose key differs from its predecessor's; the unit
+//      id of a position is the number of heads up to it, minus one.  The scan runs straight over the keys (reduce per
+//      tile -> k_scan_tiles -> down sweep): no flag array is materialised; 8 B / point read, 4 B / point written. ----
 template <class K>
-__global__ void __launch_bounds__(256) k_head_flags(const K* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+__device__ __forceinline__ uint32_t head_flag(const K* __restrict__ keys, int64_t i) { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+template <class K>
+__global__ void __launch_bounds__(SC_THREADS) k_heads_reduce(const K* __restrict__ keys, int64_t n, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t sm[33];
+  const int64_t base = (int64_t)blockIdx.x * SC_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) {
+    const int64_t i = base + (int64_t)k * SC_THREADS + threadIdx.x;
+    if (i < n) s += head_flag(keys, i);
+  }
+  uint32_t tot;
+  block_excl_scan(s, &tot, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
-// scan[i] = exclusive scan of flags.  Writes unit start offsets, the unit's sort key and the
-// sorted-position -> unit id map.
+// writes unit start offsets, the unit's sort key and the sorted-position -> unit id map
 template <class K>
-__global__ void __launch_bounds__(256) k_head_write(const K* __restrict__ keys, const uint32_t* __restrict__ flags,
-                                                  const uint32_t* __restrict__ scan, int64_t n, uint32_t* __restrict__ ustart,
-                                                  uint64_t* __restrict__ ukey, uint32_t* __restrict__ pos_unit) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t f = flags[i];
-  uint32_t u = scan[i] + f - 1u;
-  pos_unit[i] = u;
-  if (f) { ustart[u] = (uint32_t)i; ukey[u] = (uint64_t)keys[i]; }
+__global__ void __launch_bounds__(SC_THREADS) k_heads_down(const K* __restrict__ keys, int64_t n, const uint32_t* __restrict__ tile_sums,
+                                                         uint32_t* __restrict__ ustart, uint64_t* __restrict__ ukey, uint32_t* __restrict__ pos_unit) {
+  __shared__ uint32_t sm[33];
+  const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_IPT;  // blocked arrangement
+  K kk[SC_IPT + 1];
+  kk[0] = base > 0 && base - 1 < n ? keys[base - 1] : (K)0;
+  uint32_t f[SC_IPT];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) {
+    kk[k + 1] = (base + k < n) ? keys[base + k] : (K)0;
+    f[k] = (base + k < n) ? ((base + k == 0 || kk[k + 1] != kk[k]) ? 1u : 0u) : 0u;
+    s += f[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan(s, &tot, sm) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_IPT; k++) {
+    if (base + k < n) {
+      const uint32_t u = ex + f[k] - 1u;
+      pos_unit[base + k] = u;
+      if (f[k]) { ustart[u] = (uint32_t)(base + k); ukey[u] = (uint64_t)kk[k + 1]; }
+    }
+    ex += f[k];
+  }
 }
 
 // ---- stage 2: per-unit record (centroid, scatter, eigen33, normal, 8 eigen features).
-//      One thread per unit, points visited in ascending index order so the fp32 sums are the
-//      reference's sums bit for bit. ----
-__global__ void __launch_bounds__(128) k_features(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
+//      One thread per unit, points visited in ascending index order so the fp32 sums are the reference's sums bit for bit.
+//      The points of the 32 units of a warp are consecutive sorted positions: the warp gathers them into shared memory
+//      with all lanes (one coalesced read of the permutation, 32 independent point gathers in flight) and every thread
+//      then walks its own points there — the order of the ADDS is what parity fixes, not who loads the data.  Warps
+//      whose points do not fit the staging tile fall back to per-thread gathers. ----
+constexpr int FEAT_THREADS = 128, FEAT_STAGE = 768;     // staged points per warp (36 KB per CTA)
+__global__ void __launch_bounds__(FEAT_THREADS) k_features(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
                                                 const uint32_t* __restrict__ ustart, int64_t nunits, int points_min, int svgs,
                                                 float* __restrict__ rec, uint8_t* __restrict__ uflags,
                                                 unsigned long long* __restrict__ n_used) {
-  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_pts[FEAT_THREADS / 32][FEAT_STAGE * 3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t u0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;   // first unit of the warp
+  if (u0 >= nunits) return;
+  const int64_t u = u0 + lane;
+  const int64_t ul = min(u0 + 32, nunits);
+  const uint32_t p0 = ustart[u0], p1 = ustart[ul];
+  const bool staged = (p1 - p0) <= (uint32_t)FEAT_STAGE;
+  if (staged) {
+    float* sp = s_pts[w];
+    for (uint32_t p = p0 + lane; p < p1; p += 32) {
+      const float* q = xyz + (int64_t)perm[p] * stride;
+      const uint32_t o = (p - p0) * 3;
+      sp[o] = __ldg(q); sp[o + 1] = __ldg(q + 1); sp[o + 2] = __ldg(q + 2);
+    }
+  }
+  __syncwarp();
   if (u >= nunits) return;
   uint32_t s = ustart[u], e = ustart[u + 1];
   int cnt = (int)(e - s);
   bool used = svgs ? true : (cnt > points_min);
   float r[REC_FLOATS];
-  unit_record(
-      [&](int j, float& x, float& y, float& z) {
-        const float* p = xyz + (int64_t)perm[s + j] * stride;
-        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
-      },
-      cnt, used, svgs, r);
+  if (staged) {
+    const float* sp = s_pts[w] + (size_t)(s - p0) * 3;
+    unit_record([&](int j, float& x, float& y, float& z) { x = sp[3 * j]; y = sp[3 * j + 1]; z = sp[3 * j + 2]; }, cnt, used, svgs, r);
+  } else {
+    unit_record(
+        [&](int j, float& x, float& y, float& z) {
+          const float* p = xyz + (int64_t)perm[s + j] * stride;
+          x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+        },
+        cnt, used, svgs, r);
+  }
   float4* out = reinterpret_cast<float4*>(rec + u * REC_FLOATS);
   out[0] = make_float4(r[0], r[1], r[2], r[3]);
   out[1] = make_float4(r[4], r[5], r[6], r[7]);
