@@ -1295,7 +1295,7 @@ static vgs_status segment_graph(vgs_handle h, const vgs_sigmas* sg, float cut_th
       if (h->n_long > 0) {   // rows longer than the shared-memory assembly of k_rows_fill
         KTimer krs(h, K_ROWS_SORT);
         const int cap_long = (int)((h->max_row_len + 63) & ~(int64_t)63);
-        LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 16, h->row_off.as<uint32_t>(), nu, h->long_rows.as<uint32_t>(),
+        LAUNCH(k_rows_sort, (unsigned)h->n_long, 32, (size_t)2 * cap_long * 16, h->row_off.as<uint32_t>(), h->long_rows.as<uint32_t>(),
                (uint32_t)h->n_long, cap_long, h->rows.as<uint4>());
         krs.stop();
       }

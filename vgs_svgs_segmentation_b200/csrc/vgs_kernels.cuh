@@ -173,49 +173,27 @@ __global__ void __launch_bounds__(SC_THREADS) k_heads_down(const K* __restrict__
 }
 
 // ---- stage 2: per-unit record (centroid, scatter, eigen33, normal, 8 eigen features).
-//      One thread per unit, points visited in ascending index order so the fp32 sums are the reference's sums bit for bit.
-//      The points of the 32 units of a warp are consecutive sorted positions: the warp gathers them into shared memory
-//      with all lanes (one coalesced read of the permutation, 32 independent point gathers in flight) and every thread
-//      then walks its own points there — the order of the ADDS is what parity fixes, not who loads the data.  Warps
-//      whose points do not fit the staging tile fall back to per-thread gathers. ----
-constexpr int FEAT_THREADS = 128, FEAT_STAGE = 768;     // staged points per warp (36 KB per CTA)
+//      One thread per unit, points visited in ascending index order so the fp32 sums are the
+//      reference's sums bit for bit.  (Measured and rejected in round 2: gathering the points of a warp's 32 units into
+//      shared memory with all lanes first and summing from there — 0.46 ms against 0.24 ms: the per-thread gathers already
+//      overlap across the 2 waves of resident threads, and the staged walk pays bank conflicts.) ----
+constexpr int FEAT_THREADS = 128;
 __global__ void __launch_bounds__(FEAT_THREADS) k_features(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
                                                 const uint32_t* __restrict__ ustart, int64_t nunits, int points_min, int svgs,
                                                 float* __restrict__ rec, uint8_t* __restrict__ uflags,
                                                 unsigned long long* __restrict__ n_used) {
-  __shared__ float s_pts[FEAT_THREADS / 32][FEAT_STAGE * 3];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t u0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;   // first unit of the warp
-  if (u0 >= nunits) return;
-  const int64_t u = u0 + lane;
-  const int64_t ul = min(u0 + 32, nunits);
-  const uint32_t p0 = ustart[u0], p1 = ustart[ul];
-  const bool staged = (p1 - p0) <= (uint32_t)FEAT_STAGE;
-  if (staged) {
-    float* sp = s_pts[w];
-    for (uint32_t p = p0 + lane; p < p1; p += 32) {
-      const float* q = xyz + (int64_t)perm[p] * stride;
-      const uint32_t o = (p - p0) * 3;
-      sp[o] = __ldg(q); sp[o + 1] = __ldg(q + 1); sp[o + 2] = __ldg(q + 2);
-    }
-  }
-  __syncwarp();
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nunits) return;
   uint32_t s = ustart[u], e = ustart[u + 1];
   int cnt = (int)(e - s);
   bool used = svgs ? true : (cnt > points_min);
   float r[REC_FLOATS];
-  if (staged) {
-    const float* sp = s_pts[w] + (size_t)(s - p0) * 3;
-    unit_record([&](int j, float& x, float& y, float& z) { x = sp[3 * j]; y = sp[3 * j + 1]; z = sp[3 * j + 2]; }, cnt, used, svgs, r);
-  } else {
-    unit_record(
-        [&](int j, float& x, float& y, float& z) {
-          const float* p = xyz + (int64_t)perm[s + j] * stride;
-          x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
-        },
-        cnt, used, svgs, r);
-  }
+  unit_record(
+      [&](int j, float& x, float& y, float& z) {
+        const float* p = xyz + (int64_t)perm[s + j] * stride;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+      },
+      cnt, used, svgs, r);
   float4* out = reinterpret_cast<float4*>(rec + u * REC_FLOATS);
   out[0] = make_float4(r[0], r[1], r[2], r[3]);
   out[1] = make_float4(r[4], r[5], r[6], r[7]);

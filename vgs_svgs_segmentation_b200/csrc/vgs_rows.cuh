@@ -473,41 +473,60 @@ __global__ void __launch_bounds__(RF_WARPS * 32, VGS_RF_MINB) k_rows_fill(const 
   static_assert(ROWS_SHORT_CAP <= 256, "the sort words carry an 8-bit position");
 }
 
-// ---- rows ordered by weight cell: LSD radix sort (2 passes x 6 bits) of one row per warp in shared memory ----
-constexpr int RS2_WARPS = 4;
-__global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __restrict__ row_off, int64_t nv, const uint32_t* __restrict__ list,
-                                                            uint32_t nlist, int cap, uint4* __restrict__ rows) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint4* A = reinterpret_cast<uint4*>(smraw) + (size_t)w * 2 * cap;
+// ---- rows longer than the shared-memory assembly of k_rows_fill: one row per CTA (one warp), ordered by weight cell with
+//      the same 2 x 6-bit LSD radix on whole 16-byte entries.  A row is one contiguous, 16-byte aligned span of up to
+//      ~16 KB: it arrives in shared memory with ONE bulk async copy (cp.async.bulk, completion on an mbarrier) and leaves
+//      with one bulk store — the copy engine moves it while the warp only waits, instead of len/32 rounds of per-lane
+//      16-byte loads and stores. ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32) k_rows_sort(const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ list, uint32_t nlist, int cap,
+                                                uint4* __restrict__ rows) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int lane = threadIdx.x;
+  uint4* A = reinterpret_cast<uint4*>(smraw);
   uint4* B = A + cap;
-  __shared__ unsigned s_cnt[RS2_WARPS][64];
-  int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
-  if (list) { if (v >= (int64_t)nlist) return; v = list[v]; }
-  else if (v >= nv) return;
+  __shared__ unsigned s_cnt[64];
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (blockIdx.x >= nlist) return;
+  const int64_t v = list[blockIdx.x];
   const uint32_t off = row_off[v];
   const int len = (int)(row_off[v + 1] - off);
-  if (len <= 1 || len > cap) return;          // longer rows are sorted by the launch over the long-row list
-  for (int i = lane; i < len; i += 32) A[i] = rows[off + i];
+  if (len <= 1 || len > cap) return;
+  const uint32_t bytes = (uint32_t)len * 16u;
+  // --- global -> shared: one bulk copy, the warp waits on the mbarrier's transaction count ---
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the init is visible to the async proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(A)),
+                 "l"(rows + off), "r"(bytes), "r"(smem_addr(&s_bar))
+                 : "memory");
+  }
+  __syncwarp();
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(&s_bar)) : "memory");
+  }
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     const int shift = 18 + 6 * pass;
-    s_cnt[w][lane] = 0; s_cnt[w][lane + 32] = 0;
+    s_cnt[lane] = 0; s_cnt[lane + 32] = 0;
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
       const int i = i0 + lane;
       const unsigned d = i < len ? ((A[i].z >> shift) & 63u) : 0xffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
+      if (i < len && (peers & lt) == 0) s_cnt[d] += __popc(peers);
       __syncwarp();
     }
     {   // exclusive prefix sums over the 64 counters: lane owns bins 2*lane, 2*lane + 1
-      const unsigned c0 = s_cnt[w][2 * lane], c1 = s_cnt[w][2 * lane + 1];
+      const unsigned c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
       const unsigned inc = warp_incl_scan(c0 + c1, lane);
       __syncwarp();
-      s_cnt[w][2 * lane] = inc - c0 - c1;
-      s_cnt[w][2 * lane + 1] = inc - c1;
+      s_cnt[2 * lane] = inc - c0 - c1;
+      s_cnt[2 * lane + 1] = inc - c1;
     }
     __syncwarp();
     for (int i0 = 0; i0 < len; i0 += 32) {
@@ -517,15 +536,22 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) k_rows_sort(const uint32_t* __
       if (i < len) { e = A[i]; d = (e.z >> shift) & 63u; }
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       unsigned pos = 0;
-      if (i < len) pos = s_cnt[w][d] + __popc(peers & lt);
+      if (i < len) pos = s_cnt[d] + __popc(peers & lt);
       __syncwarp();
-      if (i < len && (peers & lt) == 0) s_cnt[w][d] += __popc(peers);
+      if (i < len && (peers & lt) == 0) s_cnt[d] += __popc(peers);
       if (i < len) B[pos] = e;
       __syncwarp();
     }
     uint4* t = A; A = B; B = t;
   }
-  for (int i = lane; i < len; i += 32) rows[off + i] = A[i];
+  // --- shared -> global: the warp's writes to A are made visible to the async proxy, then one bulk store ---
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rows + off), "r"(smem_addr(A)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the shared buffer is read before the CTA retires
+  }
 }
 
 // ---- stage 5a: cutGraphSegmentation (VS.h:1913-2029) of one voxel per warp (= per CTA) from the weight rows.
