@@ -777,7 +777,13 @@ __global__ void __launch_bounds__(32 * LR_WARPS, VGS_LR_MINB) k_local_graph_rows
               // entry (row a, col b) = weight(idx[a] -> idx[b]); packed (col << 8) | row orders like col*n+row (VS.h:1922)
               const float w_ji = __uint_as_float(en.x), w_ij = __uint_as_float(en.y);
               const unsigned short f_ji = (unsigned short)((i << 8) | j), f_ij = (unsigned short)((j << 8) | i);
-              if ((int)en.w < c1) {       // both directions belong to this round
+              if (en.x == en.y) {
+                // both directions carry the same weight (bit for bit): the second one in the order (larger flat index)
+                // can never act — if the first merges, the second joins one segment; if the first is refused because a
+                // threshold is >= w, no entry of the same weight in between can merge (hence lower) that segment
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < LR_CS) { C_w[slot] = w_ji; C_f[slot] = min(f_ji, f_ij); }
+              } else if ((int)en.w < c1) {       // both directions belong to this round
                 const int slot = atomicAdd(&s_cnt, 2);
                 if (slot + 1 < LR_CS) { C_w[slot] = w_ji; C_f[slot] = f_ji; C_w[slot + 1] = w_ij; C_f[slot + 1] = f_ij; }
               } else {                    // the lighter direction waits for its cell
