@@ -139,7 +139,7 @@ struct vgs_context {
   float* tm_slot[16] = {};
   unsigned tm_pending = 0;
   // per-kernel-group timers (vgs_kernel_timings): one event pair per group and run
-  static constexpr int NK = 17;
+  static constexpr int NK = 20;
   cudaEvent_t kev[2 * NK] = {};
   float k_ms[NK] = {};
   int k_launches[NK] = {};
@@ -371,7 +371,7 @@ struct StageTimer {
 
 // kernel-group timer: brackets the launches of one group (names in vgs_kernel_timings)
 enum KId { K_ORIGIN = 0, K_QUANTISE, K_SORT, K_HEADS, K_FEATURES, K_HASH, K_GRID, K_ADJ_COUNT, K_ADJ_FILL, K_ROWS_FILL, K_ROWS_SORT,
-           K_GRAPH_ROWS, K_GRAPH_GENERAL, K_MUTUAL, K_CLOSEST, K_COMPONENTS, K_LABELS };
+           K_GRAPH_ROWS, K_GRAPH_GENERAL, K_MUTUAL, K_CLOSEST, K_COMPONENTS, K_LABELS, K_VCCS, K_SVGS_UNITS, K_SVGS_ADJ };
 struct KTimer {
   vgs_handle h; int id; int64_t l0;
   KTimer(vgs_handle h_, int id_) : h(h_), id(id_), l0(h_->launches) { cudaEventRecord(h->kev[2 * id], h->stream); }
@@ -742,6 +742,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   auto& c = h->vc;
   const int64_t n = h->n;
   const int desc = h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0;
+  KTimer kvccs(h, K_VCCS);
   // --- voxel table of its own (the shared sort buffers are reused by the unit builders) ---
   CK(c.keysA.reserve((size_t)n * 8)); CK(c.keysB.reserve((size_t)n * 8));
   CK(c.valsA.reserve((size_t)n * 4)); CK(c.valsB.reserve((size_t)n * 4));
@@ -865,6 +866,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   CK(cudaMemsetAsync(d_ml, 0, 4, h->stream));
   LAUNCH(k_vccs_max_label, (unsigned)cdiv(H, 256), 256, 0, H, c.alive.as<uint8_t>(), d_ml);
   LAUNCH(k_vccs_point_labels, (unsigned)cdiv(n, 256), 256, 0, n, c.ptvox.as<int32_t>(), (const int32_t*)own_a, h->labels_own.as<int32_t>());
+  kvccs.stop();
   int32_t ml = 0;
   CK(cudaMemcpyAsync(&ml, d_ml, 4, cudaMemcpyDeviceToHost, h->stream));
   CK(stream_wait(h->stream));
@@ -900,8 +902,10 @@ vgs_status vgs_compute_features(vgs_handle h, int points_min) {
   CK(cudaSetDevice(h->device));
   StageTimer t(h, &h->tm.features_ms, 3);
   if (h->mode == VGS_MODE_SVGS && !(h->units_external && h->have_units)) {
+    KTimer ku(h, K_SVGS_UNITS);
     vgs_status s = build_svgs_units(h);
     if (s) return s;
+    ku.stop();
   }
   if (!h->have_units) return h->fail(VGS_ERR_STATE, "vgs_compute_features: call vgs_voxelize first (test:54-62)");
   h->points_min = points_min;
@@ -1062,6 +1066,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     h->stencil_host.clear();
     const int64_t nu = h->nu;
     const float cell = graph_size * 1.01f;
+    KTimer ksa(h, K_SVGS_ADJ);
     CK(h->gridmin.reserve(64));
     const uint32_t init[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
     CK(cudaMemcpyAsync(h->gridmin.p, init, 12, cudaMemcpyHostToDevice, h->stream));
@@ -1107,6 +1112,7 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     LAUNCH(k_adjacency_svgs, (unsigned)cdiv(nu, wpb), wpb * 32, smem, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
            h->cstart.as<uint32_t>(), vs, h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, r2, 1,
            h->adj_cnt.as<uint32_t>(), h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), cap, d_over);
+    ksa.stop();
     CK(stream_wait(h->stream));
     h->have_adj = true;
     t.stop();
@@ -1646,14 +1652,16 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
       "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
       "adjacency fill: k_adj_fill", "weight rows: k_rows_fill (evaluate, order by weight cell, write once)", "weight rows: k_rows_sort (rows longer than 256 entries)", "local graphs: k_local_graph_rows",
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",
-      "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels"};
+      "components: k_cc_init + k_cc_jump + k_cc_hook + k_cc_flatten", "labels: k_cluster_stats + k_cluster_count + k_point_labels",
+      "supervoxels: VCCS generator (voxel table, normals, seeds, expansion + refinement rounds)", "supervoxel units: k_label_keys + sort + heads",
+      "supervoxel adjacency: centroid grid + k_adjacency_svgs"};
   const int64_t N = h->n, V = h->nu, E = h->n_adj, R = h->n_rows, MW = h->mwords;
   const int64_t KB = h->sort_key_bytes;     // bytes per sort key
   const int passes = (3 * h->depth + 1 + 7) / 8;
   // algorithmic bytes = compulsory HBM traffic with inputs / outputs materialised once
   const int64_t bytes[vgs_context::NK] = {
       12 * N, 12 * N + (KB + 4) * N, (int64_t)passes * 2 * (KB + 4) * N, KB * N + 4 * N + 28 * V, 16 * N + 64 * V, 32 * V, 13 * V + 2 * h->grid_bytes,
-      20 * V, 16 * V + 6 * E, 64 * V + 16 * R, 32 * h->n_long * h->max_row_len, 6 * E + 16 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V};
+      20 * V, 16 * V + 6 * E, 64 * V + 16 * R, 32 * h->n_long * h->max_row_len, 6 * E + 16 * R + 4 * MW * V, 6 * E + 64 * V, 10 * E + 4 * MW * V, 0, 8 * E + 8 * V, 8 * N + 4 * V, 16 * N, 40 * N, 64 * V + 4 * E};
   int c = 0;
   for (int i = 0; i < vgs_context::NK && out && c < *n; i++) {
     if (h->k_launches[i] == 0 && h->k_ms[i] == 0.f) continue;
