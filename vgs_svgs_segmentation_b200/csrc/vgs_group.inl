@@ -67,6 +67,11 @@ __global__ void k_comb_max_i32(int32_t* __restrict__ dst, const int32_t* __restr
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = max(dst[i], src[i]);
 }
+// out = 1 if any of the n flags is set (the round's "anything changed" word, all-reduced with the attached flags)
+__global__ void k_fold_flags(const uint32_t* __restrict__ flags, int n, int32_t* __restrict__ out) {
+  const bool any = threadIdx.x < (unsigned)n && flags[threadIdx.x] != 0;
+  if (__ballot_sync(0xffffffffu, any) && threadIdx.x == 0) *out = 1;
+}
 // exported clusters of one rank: local components no other rank knows about, and (on one rank only) merged components
 __global__ void __launch_bounds__(256) k_group_cluster_count(const int* __restrict__ root, const uint8_t* __restrict__ is_cross,
                                                            const uint32_t* __restrict__ csize, int64_t nu, int min_size_excl,
@@ -603,7 +608,7 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
     s = each_rank(g, [&](int lr, vgs_handle h, TileCtx& t) -> vgs_status {
       CK(t.low_loc.reserve((size_t)LOW_IDS * sizeof(LowEntry))); CK(t.low_all.reserve((size_t)R * LOW_IDS * sizeof(LowEntry)));
       CK(t.low_glob.reserve((size_t)LOW_IDS * sizeof(LowEntry)));
-      CK(t.low_att.reserve(LOW_IDS * 4)); CK(t.low_att_out.reserve(LOW_IDS * 4));
+      CK(t.low_att.reserve((LOW_IDS + 1) * 4)); CK(t.low_att_out.reserve((LOW_IDS + 1) * 4));
       CK(cudaMemsetAsync(t.low_loc.p, 0xff, (size_t)LOW_IDS * sizeof(LowEntry), st));     // absent entries sort last
       CK(cudaMemsetAsync(t.low_att.p, 0, LOW_IDS * 4, st));
       if (h->nu > 0) {
@@ -666,41 +671,31 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
     if (s) return s;
     std::vector<size_t> bnd_bytes(R, 0);
     bool have_bnd_counts = false;
+    size_t bnd_total = 0;
+    // One global round = three local rounds of the owned singles (launched back to back, one flag each) + the exchange of
+    // the state of the singles next to a cut + the attached flags of the low-id voxels.  The "anything changed" flags of
+    // the round ride on the same all-reduce as the attached flags (word LOW_IDS), so a round costs ONE host read.
     while (true) {
-      std::vector<unsigned> changed(L, 0);
-      // local fixed point of the owned singles
-      s = each_rank(g, [&](int lr, vgs_handle h, TileCtx& t) -> vgs_status {
-        if (t.n_singles == 0) return VGS_OK;
-        uint32_t* d_changed = t.tsmall.as<uint32_t>() + 4;
-        for (int it = 0; it < 100000; it++) {
-          CK(cudaMemsetAsync(d_changed, 0, 4, st));
-          LAUNCH(k_closest_round_tile, (unsigned)cdiv((int64_t)t.n_singles * 32, 128), 128, 0, h->singles.as<uint32_t>(), t.n_singles,
-                 h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), h->nu, pp, t.own.as<uint8_t>(),
-                 t.low_glob.as<LowEntry>(), t.low_att.as<int32_t>(), n_low, t.gidlo.as<uint16_t>(), h->attach.as<int32_t>(), d_changed);
-          uint32_t c = 0;
-          CK(cudaMemcpyAsync(&c, d_changed, 4, cudaMemcpyDeviceToHost, st));
-          CK(stream_wait(st));
-          if (!c) break;
-          changed[lr] = 1;
-        }
-        return VGS_OK;
-      });
-      if (s) return s;
-      global_rounds++;
-      if (R == 1) break;
-      // state of the owned singles that other ranks hold as halo voxels + attached flags of the low-id voxels
       std::vector<void*> sp(L), rp(L), ap(L);
       s = each_rank(g, [&](int lr, vgs_handle h, TileCtx& t) -> vgs_status {
+        uint32_t* d_changed = t.tsmall.as<uint32_t>() + 4;      // [0..2] local rounds, [3] import
         uint32_t* d_nb = t.tsmall.as<uint32_t>() + 12;
+        CK(cudaMemsetAsync(d_changed, 0, 16, st));
         CK(cudaMemsetAsync(d_nb, 0, 4, st));
-        CK(cudaMemsetAsync(t.low_att_out.p, 0, LOW_IDS * 4, st));
-        if (t.n_singles > 0)
-          LAUNCH(k_boundary_export, (unsigned)cdiv(t.n_singles, 256), 256, 0, h->singles.as<uint32_t>(), t.n_singles, t.own.as<uint8_t>(),
-                 h->plainm.as<unsigned long long>(), h->attach.as<int32_t>(), t.bnd_out.as<unsigned long long>(), d_nb);
-        if (h->nu > 0 && n_low > 0)
+        CK(cudaMemsetAsync(t.low_att_out.p, 0, (LOW_IDS + 1) * 4, st));
+        if (t.n_singles > 0) {
+          for (int it = 0; it < 3; it++)
+            LAUNCH(k_closest_round_tile, (unsigned)cdiv((int64_t)t.n_singles * 32, 128), 128, 0, h->singles.as<uint32_t>(), t.n_singles,
+                   h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), h->nu, pp, t.own.as<uint8_t>(),
+                   t.low_glob.as<LowEntry>(), t.low_att.as<int32_t>(), n_low, t.gidlo.as<uint16_t>(), h->attach.as<int32_t>(), d_changed + it);
+          if (R > 1)
+            LAUNCH(k_boundary_export, (unsigned)cdiv(t.n_singles, 256), 256, 0, h->singles.as<uint32_t>(), t.n_singles, t.own.as<uint8_t>(),
+                   h->plainm.as<unsigned long long>(), h->attach.as<int32_t>(), t.bnd_out.as<unsigned long long>(), d_nb);
+        }
+        if (R > 1 && h->nu > 0 && n_low > 0)
           LAUNCH(k_low_attached, (unsigned)cdiv(h->nu, 256), 256, 0, t.low_glob.as<LowEntry>(), n_low, t.gidlo.as<uint16_t>(), t.own.as<uint8_t>(),
                  h->attach.as<int32_t>(), h->nu, t.low_att_out.as<int32_t>());
-        if (!have_bnd_counts) {
+        if (R > 1 && !have_bnd_counts) {
           CK(cudaMemcpyAsync(&t.n_bnd, d_nb, 4, cudaMemcpyDeviceToHost, st));
           CK(stream_wait(st));
         }
@@ -708,41 +703,40 @@ vgs_status vgs_group_run(vgs_group g, const vgs_params* p, const float* const* x
         return VGS_OK;
       });
       if (s) return s;
-      if (!have_bnd_counts) {   // the set of exported singles is the same in every round: sizes are exchanged once
-        std::vector<unsigned long long> mine(L), allb(R);
-        std::vector<const void*> cp(L);
-        for (int lr = 0; lr < L; lr++) { mine[lr] = (unsigned long long)g->tc[lr].n_bnd * 8ull; cp[lr] = &mine[lr]; }
-        if ((s = xg_host(g, cp.data(), allb.data(), 8))) return s;
-        size_t tot = 0;
-        for (int r = 0; r < R; r++) { bnd_bytes[r] = (size_t)allb[r]; tot += bnd_bytes[r]; }
-        for (int lr = 0; lr < L; lr++) GCK(g->tc[lr].bnd_all.reserve(tot + 16));
-        have_bnd_counts = true;
+      global_rounds++;
+      if (R > 1) {
+        if (!have_bnd_counts) {   // the set of exported singles is the same in every round: sizes are exchanged once
+          std::vector<unsigned long long> mine(L), allb(R);
+          std::vector<const void*> cp(L);
+          for (int lr = 0; lr < L; lr++) { mine[lr] = (unsigned long long)g->tc[lr].n_bnd * 8ull; cp[lr] = &mine[lr]; }
+          if ((s = xg_host(g, cp.data(), allb.data(), 8))) return s;
+          for (int r = 0; r < R; r++) { bnd_bytes[r] = (size_t)allb[r]; bnd_total += bnd_bytes[r]; }
+          for (int lr = 0; lr < L; lr++) GCK(g->tc[lr].bnd_all.reserve(bnd_total + 16));
+          have_bnd_counts = true;
+        }
+        for (int lr = 0; lr < L; lr++) rp[lr] = g->tc[lr].bnd_all.p;
+        if ((s = xg_dev(g, sp.data(), rp.data(), bnd_bytes.data()))) return s;
       }
-      for (int lr = 0; lr < L; lr++) rp[lr] = g->tc[lr].bnd_all.p;
-      if ((s = xg_dev(g, sp.data(), rp.data(), bnd_bytes.data()))) return s;
-      if ((s = xr_dev(g, ap.data(), LOW_IDS, 1))) return s;
-      size_t tot = 0;
-      for (int r = 0; r < R; r++) tot += bnd_bytes[r];
       s = each_rank(g, [&](int lr, vgs_handle h, TileCtx& t) -> vgs_status {
         uint32_t* d_changed = t.tsmall.as<uint32_t>() + 4;
-        CK(cudaMemsetAsync(d_changed, 0, 4, st));
-        if (tot > 0 && h->nu > 0)
-          LAUNCH(k_boundary_import, (unsigned)cdiv((int64_t)(tot / 8), 256), 256, 0, t.bnd_all.as<unsigned long long>(), (int64_t)(tot / 8),
-                 h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, t.own.as<uint8_t>(), h->attach.as<int32_t>(), d_changed);
-        CK(cudaMemcpyAsync(t.low_att.p, t.low_att_out.p, LOW_IDS * 4, cudaMemcpyDeviceToDevice, st));
-        uint32_t c = 0;
-        CK(cudaMemcpyAsync(&c, d_changed, 4, cudaMemcpyDeviceToHost, st));
-        CK(stream_wait(st));
-        if (c) changed[lr] = 1;
+        if (R > 1 && bnd_total > 0 && h->nu > 0)
+          LAUNCH(k_boundary_import, (unsigned)cdiv((int64_t)(bnd_total / 8), 256), 256, 0, t.bnd_all.as<unsigned long long>(), (int64_t)(bnd_total / 8),
+                 h->tk.as<unsigned long long>(), h->tv.as<uint32_t>(), h->hmask, t.own.as<uint8_t>(), h->attach.as<int32_t>(), d_changed + 3);
+        LAUNCH(k_fold_flags, 1, 32, 0, d_changed, 4, t.low_att_out.as<int32_t>() + LOW_IDS);
         return VGS_OK;
       });
       if (s) return s;
-      std::vector<unsigned> allch(R, 0);
-      std::vector<const void*> cp(L);
-      for (int lr = 0; lr < L; lr++) cp[lr] = &changed[lr];
-      if ((s = xg_host(g, cp.data(), allch.data(), 4))) return s;
-      bool any = false;
-      for (int r = 0; r < R; r++) any = any || allch[r] != 0;
+      if (R > 1 && (s = xr_dev(g, ap.data(), LOW_IDS + 1, 1))) return s;
+      int32_t any = 0;
+      s = each_rank(g, [&](int lr, vgs_handle h, TileCtx& t) -> vgs_status {
+        CK(cudaMemcpyAsync(t.low_att.p, t.low_att_out.p, LOW_IDS * 4, cudaMemcpyDeviceToDevice, st));
+        if (lr == 0) {
+          CK(cudaMemcpyAsync(&any, t.low_att_out.as<int32_t>() + LOW_IDS, 4, cudaMemcpyDeviceToHost, st));
+          CK(stream_wait(st));
+        }
+        return VGS_OK;
+      });
+      if (s) return s;
       if (!any) break;
       if (global_rounds > 100000) return g->fail(VGS_ERR_LIMIT, "vgs_group_run: closest check did not converge");
     }
