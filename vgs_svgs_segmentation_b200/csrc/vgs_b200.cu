@@ -312,7 +312,7 @@ vgs_status find_next(vgs_handle h, int64_t cursor, const OctState& st, int64_t* 
     CK(stream_wait(h->stream));
     if (r.idx != ~0ull) { *found = (int64_t)r.idx; xyz3[0] = r.p[0]; xyz3[1] = r.p[1]; xyz3[2] = r.p[2]; return VGS_OK; }
     s = e;
-    window *= 8;
+    window *= 64;     // violations come early or never: a short window first, then (nearly) the rest in one launch
   }
   return VGS_OK;
 }
