@@ -116,12 +116,19 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K* __restric
   K k[RS_IPT];
   uint32_t v[RS_IPT];
   const uint32_t lt = (1u << lane) - 1u;
+  // all loads first (32 independent requests in flight per thread), then the ranking: the warp syncs of the ranking loop
+  // are compiler barriers, loads left inside it would be issued one round trip at a time
 #pragma unroll
   for (int r = 0; r < RS_IPT; r++) {
     int64_t i = cbase + r * 32 + lane;
     bool ok = i < n;
     k[r] = ok ? kin[i] : 0;
     v[r] = ok ? vin[i] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_IPT; r++) {
+    int64_t i = cbase + r * 32 + lane;
+    bool ok = i < n;
     uint32_t d = ok ? ((uint32_t)(k[r] >> shift) & 255u) : 0xffffu;
     uint32_t peers = __match_any_sync(0xffffffffu, d);
     if (ok && (peers & lt) == 0) wc[w][d] += __popc(peers);

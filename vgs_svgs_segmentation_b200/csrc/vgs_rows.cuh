@@ -53,10 +53,17 @@ __global__ void __launch_bounds__(256) k_voxel_keys(const uint64_t* __restrict__
   }
   kx = __reduce_min_sync(0xffffffffu, kx); ky = __reduce_min_sync(0xffffffffu, ky); kz = __reduce_min_sync(0xffffffffu, kz);
   Kx = __reduce_max_sync(0xffffffffu, Kx); Ky = __reduce_max_sync(0xffffffffu, Ky); Kz = __reduce_max_sync(0xffffffffu, Kz);
+  // one set of global atomics per CTA (six hot addresses: per-warp atomics serialise in L2)
+  __shared__ uint32_t s_mm[6];
+  if (threadIdx.x < 6) s_mm[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(&kminmax[0], kx); atomicMin(&kminmax[1], ky); atomicMin(&kminmax[2], kz);
-    atomicMax(&kminmax[3], Kx); atomicMax(&kminmax[4], Ky); atomicMax(&kminmax[5], Kz);
+    atomicMin(&s_mm[0], kx); atomicMin(&s_mm[1], ky); atomicMin(&s_mm[2], kz);
+    atomicMax(&s_mm[3], Kx); atomicMax(&s_mm[4], Ky); atomicMax(&s_mm[5], Kz);
   }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicMin(&kminmax[threadIdx.x], s_mm[threadIdx.x]);
+  else if (threadIdx.x < 6) atomicMax(&kminmax[threadIdx.x], s_mm[threadIdx.x]);
 }
 __global__ void __launch_bounds__(256) k_voxel_centers(const uint32_t* __restrict__ key3, int64_t nu, float res_f, float mnx, float mny,
                                                      float mnz, float* __restrict__ center) {
