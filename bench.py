@@ -196,8 +196,9 @@ def dropin_e2e(cfg, pts, pd, runs=3):
     try:
         os.makedirs(os.path.dirname(exe), exist_ok=True)
         src = os.path.join(ROOT, "tests", "cpp", "dropin_vgs.cpp")
-        if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, src,
+        deps = [src] + [os.path.join(ROOT, "include", "vgs_dropin", f) for f in os.listdir(os.path.join(ROOT, "include", "vgs_dropin"))]
+        if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", exe, src,
                             "-L" + os.path.join(ROOT, "vgs_svgs_segmentation_b200"), "-lvgs_b200",
                             "-Wl,-rpath," + os.path.join(ROOT, "vgs_svgs_segmentation_b200")], check=True, capture_output=True)
         with tempfile.TemporaryDirectory() as td:
@@ -209,13 +210,17 @@ def dropin_e2e(cfg, pts, pd, runs=3):
             if r.returncode != 0:
                 return {"error": (r.stderr or r.stdout)[-300:]}
             ms = [float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("dropin_ms")]
+            phases = [[float(x) for x in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith("dropin_phases")]
             import numpy as np
             lab = np.fromfile(os.path.join(td, "l.i32"), np.int32)
         v = sum(ms) / len(ms)
-        return {"value": pts.shape[0] / (v / 1e3), "unit": "points/s", "ms_per_run": v, "runs": len(ms), "labels": lab,
+        names = ("voxelise_incl_h2d", "centres", "features", "adjacency", "segment", "clusters_and_coloured_cloud", "getClusterIdx", "destruction")
+        phase_ms = {k: round(sum(p[i] for p in phases) / len(phases), 3) for i, k in enumerate(names)} if phases else None
+        return {"value": pts.shape[0] / (v / 1e3), "unit": "points/s", "ms_per_run": v, "runs": len(ms), "labels": lab, "phases_ms": phase_ms,
                 "what": "pcl::VoxelBasedSegmentation drop-in class, the reference's call sequence (test:51-76) incl. getVoxelCenters, "
                         "drawColorMapofPointsinClusters (an XYZRGB cloud of every clustered point) and getClusterIdx() (vector<vector<int>>); "
-                        "pageable host cloud, a fresh object per run"}
+                        "pageable host cloud, a fresh object per run, constructed and destroyed inside the timed region (the library parks its device "
+                        "working set between objects: vgs_acquire / vgs_release)"}
     except Exception as e:   # noqa: BLE001
         return {"error": str(e)[:300]}
 

@@ -90,12 +90,23 @@ vgs_status vgs_create(vgs_handle* out, const vgs_config* cfg);
 void vgs_destroy(vgs_handle h);
 const char* vgs_last_error(vgs_handle h);       /* h may be NULL: error of the last failed vgs_create */
 vgs_status vgs_device_count(int* n);            /* VGS_ERR_NO_DEVICE when none */
+/* Pooled lifecycle for callers that make one object per cloud (the drop-in classes: the reference constructs a
+ * VoxelBasedSegmentation per call of segmentationVGS, test:51).  vgs_release parks the handle — its device buffers,
+ * streams and events — in a process-wide pool instead of freeing them; vgs_acquire hands out a parked handle of the same
+ * (device, mode, leaf_order) with all per-cloud state reset, or creates one.  Handles made on a caller's stream
+ * (cfg->stream != NULL) are never pooled.  vgs_pool_trim destroys every parked handle (call it before cudaDeviceReset). */
+vgs_status vgs_acquire(vgs_handle* out, const vgs_config* cfg);
+void vgs_release(vgs_handle h);
+void vgs_pool_trim(void);
 
 /* -- input: replaces setInputCloud + getCloudPointNum (VS.h:94-102, test:52-53).  xyz = n points,
  *    stride_bytes 12 (packed) or 16 (pcl::PointXYZ).  on_device != 0: xyz is a device pointer that
  *    must stay valid until the run ends (no copy is made); else a host pointer, copied H2D on the handle's stream:
  *    asynchronously when the buffer is pinned, so it must stay valid and unchanged until the next call that
- *    synchronises (vgs_voxelize and every later stage do; vgs_run does before it returns). -- */
+ *    synchronises (vgs_voxelize and every later stage do; vgs_run does before it returns).  Large PAGEABLE host
+ *    buffers (here and in the result getters) move through the library's pinned staging ring, filled / drained by a
+ *    few host threads — several times the bandwidth of a plain pageable cudaMemcpy; such a call returns only when the
+ *    caller's buffer has been read / written completely. -- */
 vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_bytes, int on_device);
 
 /* -- stage 0+1: replaces OctreePointCloud(res) + addPointsFromInputCloud + setVoxelCenters
@@ -107,6 +118,9 @@ vgs_status vgs_get_bounding_box(vgs_handle h, double out6[6]);          /* PCL g
 vgs_status vgs_set_bounding_box(vgs_handle h, const double in6[6]);
 vgs_status vgs_voxel_count(vgs_handle h, int64_t* n_voxels);            /* getVoxelNum VS.h:104 */
 vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz /* V x 3 */); /* getVoxelCenters VS.h:191 */
+/* getOneVoxelAdjacency VS.h:268-287: ids of the units within graph_size of `unit`, nearest first, itself first; *n = list
+ * length (ids may be NULL to query it), at most cap ids are written.  Needs vgs_find_adjacency. */
+vgs_status vgs_get_unit_adjacency(vgs_handle h, int64_t unit, int32_t* ids, int cap, int* n);
 
 /* -- SVGS units: per-point supervoxel labels as pcl::SupervoxelClustering::getLabeledCloud gives
  *    them (SV.h:283-323; 0 = unlabelled, labels >= max_label are dropped, max_label <= 0 keeps all).

@@ -9,12 +9,14 @@
 // (useSeedGridSupervoxels).  Everything downstream of the labels is the reference's algorithm on the GPU.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../vgs_b200.h"
 #include <algorithm>
+#include "host_parallel.h"
 #include "mesh_export.h"
 #include "pcl_shim.h"
 
@@ -30,9 +32,9 @@ class SuperVoxelBasedSegmentation {
     cfg.mode = VGS_MODE_SVGS;
     cfg.device = device;
     cfg.leaf_order = VGS_LEAF_DESCENDING;
-    if (vgs_create(&h_, &cfg) != VGS_OK) throw std::runtime_error(std::string("vgs_create: ") + vgs_last_error(nullptr));
+    if (vgs_acquire(&h_, &cfg) != VGS_OK) throw std::runtime_error(std::string("vgs_acquire: ") + vgs_last_error(nullptr));
   }
-  ~SuperVoxelBasedSegmentation() { vgs_destroy(h_); }
+  ~SuperVoxelBasedSegmentation() { vgs_release(h_); }
   SuperVoxelBasedSegmentation(const SuperVoxelBasedSegmentation&) = delete;
   SuperVoxelBasedSegmentation& operator=(const SuperVoxelBasedSegmentation&) = delete;
 
@@ -56,7 +58,7 @@ class SuperVoxelBasedSegmentation {
   int getVoxelNum() { int64_t v = 0; ck(vgs_voxel_count(h_, &v)); voxels_num_ = (int)v; return voxels_num_; }  // SV.h:111
   int getSuperVoxelNum() { return supervoxels_num_; }                                // SV.h:118
   int getClusterNum() { return clusters_num_; }                                      // SV.h:124
-  std::vector<std::vector<int>> getClusterIdx() { return clusters_point_idx_; }      // SV.h:130
+  std::vector<std::vector<int>> getClusterIdx() { return vgs_dropin::copy_lists(clusters_point_idx_); }   // SV.h:130 (by value)
 
   void setVoxelSize(double input_resolution, int points_num_min) {                   // SV.h:143
     voxel_resolution_ = (float)input_resolution; voxel_points_min_ = points_num_min;
@@ -119,24 +121,34 @@ class SuperVoxelBasedSegmentation {
     int64_t nc = 0, nt = 0;
     ck(vgs_get_clusters_csr(h_, 0, &nc, &nt, nullptr, nullptr));
     std::vector<int64_t> off((size_t)nc + 1);
-    std::vector<int32_t> idx((size_t)(nt > 0 ? nt : 1));
-    ck(vgs_get_clusters_csr(h_, 0, &nc, &nt, off.data(), idx.data()));
-    clusters_point_idx_.assign((size_t)nc, std::vector<int>());
-    for (int64_t c = 0; c < nc; c++) clusters_point_idx_[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
+    std::unique_ptr<int32_t[]> idx(new int32_t[(size_t)(nt > 0 ? nt : 1)]);
+    ck(vgs_get_clusters_csr(h_, 0, &nc, &nt, off.data(), idx.get()));
+    vgs_dropin::csr_to_lists(off, idx.get(), clusters_point_idx_);
     clusters_num_ = (int)nc;
   }
 
   void drawColorMapofPointsinClusters(pcl::PointCloud<pcl::PointXYZRGB>::Ptr output_cloud) {   // SV.h:613
     if (!output_cloud || !points_cloud_) return;
-    for (size_t c = 0; c < clusters_point_idx_.size(); c++) {
-      uint32_t hsh = (uint32_t)c * 2654435761u;
-      for (int p : clusters_point_idx_[c]) {
-        pcl::PointXYZRGB q;
-        q.x = points_cloud_->points[p].x; q.y = points_cloud_->points[p].y; q.z = points_cloud_->points[p].z;
-        q.r = (uint8_t)(hsh >> 8); q.g = (uint8_t)(hsh >> 16); q.b = (uint8_t)(hsh >> 24);
-        output_cloud->push_back(q);
+    std::vector<size_t> first(clusters_point_idx_.size() + 1, 0);
+    for (size_t c = 0; c < clusters_point_idx_.size(); c++) first[c + 1] = first[c] + clusters_point_idx_[c].size();
+    const size_t at = output_cloud->points.size();
+    output_cloud->points.reserve(at + first.back());
+    vgs_dropin::advise_huge(output_cloud->points.data(), (at + first.back()) * sizeof(pcl::PointXYZRGB));
+    output_cloud->points.resize(at + first.back());
+    pcl::PointXYZRGB* dst = output_cloud->points.data() + at;
+    const auto& src = points_cloud_->points;
+    vgs_dropin::parallel_blocks(clusters_point_idx_.size(), 64, [&](size_t b, size_t e) {
+      for (size_t c = b; c < e; c++) {
+        const uint32_t hsh = (uint32_t)c * 2654435761u;
+        size_t k = first[c];
+        for (int p : clusters_point_idx_[c]) {
+          pcl::PointXYZRGB& q = dst[k++];
+          q.x = src[(size_t)p].x; q.y = src[(size_t)p].y; q.z = src[(size_t)p].z;
+          q.r = (uint8_t)(hsh >> 8); q.g = (uint8_t)(hsh >> 16); q.b = (uint8_t)(hsh >> 24);
+        }
       }
-    }
+    });
+    output_cloud->width = (std::uint32_t)output_cloud->points.size(); output_cloud->height = 1;
   }
   // ---- display exports (SV.h:424-611); colours are vgs_dropin::color_of(index), see mesh_export.h ----
 

@@ -4,12 +4,15 @@
 // The reference signals no errors (all stage methods return void); failures of the CUDA path
 // throw std::runtime_error with vgs_last_error() — there is no CPU fallback.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../vgs_b200.h"
+#include "host_parallel.h"
 #include "mesh_export.h"
 #include "pcl_shim.h"
 
@@ -26,9 +29,10 @@ class VoxelBasedSegmentation {
     cfg.mode = VGS_MODE_VGS;
     cfg.device = device;
     cfg.leaf_order = VGS_LEAF_DESCENDING;  // PCL 1.8.1 leaf iterator (README.md:9 of the reference)
-    if (vgs_create(&h_, &cfg) != VGS_OK) throw std::runtime_error(std::string("vgs_create: ") + vgs_last_error(nullptr));
+    // pooled: the reference makes one object per cloud (test:51); the device working set is kept between objects
+    if (vgs_acquire(&h_, &cfg) != VGS_OK) throw std::runtime_error(std::string("vgs_acquire: ") + vgs_last_error(nullptr));
   }
-  ~VoxelBasedSegmentation() { vgs_destroy(h_); }
+  ~VoxelBasedSegmentation() { vgs_release(h_); }
   VoxelBasedSegmentation(const VoxelBasedSegmentation&) = delete;
   VoxelBasedSegmentation& operator=(const VoxelBasedSegmentation&) = delete;
 
@@ -58,7 +62,7 @@ class VoxelBasedSegmentation {
     return voxels_num_;
   }
   int getClusterNum() { return clusters_num_; }                            // VS.h:111
-  std::vector<std::vector<int>> getClusterIdx() { return clusters_point_idx_; }  // VS.h:117
+  std::vector<std::vector<int>> getClusterIdx() { return vgs_dropin::copy_lists(clusters_point_idx_); }  // VS.h:117 (by value)
 
   void setVoxelSize(double input_resolution, int points_num_min, int voxels_num_min, int voxels_adj_min) {  // VS.h:124
     voxel_resolution_ = (float)input_resolution;
@@ -87,19 +91,15 @@ class VoxelBasedSegmentation {
   void setVoxelClustered(int /*voxel_idx*/, int /*clustered_ornot*/) {}
   // VS.h:269: ids of the voxels within graph_size of voxel_id, nearest first, the voxel itself first (FLANN radius order)
   std::vector<int> getOneVoxelAdjacency(int voxel_id) {
-    if (adj_off_cache_.empty()) {
-      adj_off_cache_ = vgs_dropin::fetch<int64_t>(h_, VGS_BLOB_ADJ_OFFSETS);
-      adj_idx_cache_ = vgs_dropin::fetch<int32_t>(h_, VGS_BLOB_ADJ_IDX);
-    }
-    if (voxel_id < 0 || (size_t)voxel_id + 1 >= adj_off_cache_.size()) throw std::runtime_error("getOneVoxelAdjacency: voxel id out of range");
-    return std::vector<int>(adj_idx_cache_.begin() + adj_off_cache_[voxel_id], adj_idx_cache_.begin() + adj_off_cache_[voxel_id + 1]);
+    int n = 0;
+    std::vector<int> ids(256);                       // a voxel has at most 255 neighbours (vgs_find_adjacency fails beyond)
+    ck(vgs_get_unit_adjacency(h_, voxel_id, ids.data(), (int)ids.size(), &n));
+    ids.resize((size_t)n);
+    return ids;
   }
 
   void calcualteVoxelCloudAttributes(PCXYZPtr /*input_cloud*/) { ck(vgs_compute_features(h_, voxel_points_min_)); }  // VS.h:290 [sic]
-  void findAllVoxelAdjacency(float graph_size) {                                                                      // VS.h:223
-    adj_off_cache_.clear(); adj_idx_cache_.clear();
-    ck(vgs_find_adjacency(h_, graph_size));
-  }
+  void findAllVoxelAdjacency(float graph_size) { ck(vgs_find_adjacency(h_, graph_size)); }                           // VS.h:223
   void segmentVoxelCloudWithGraphModel(float cut_thred, float sig_p, float sig_n, float sig_o, float sig_e, float sig_c,
                                        float sig_w) {  // VS.h:372
     vgs_sigmas s{sig_p, sig_n, sig_o, sig_e, sig_c, sig_w};
@@ -116,24 +116,33 @@ class VoxelBasedSegmentation {
     int64_t nc = 0, nt = 0;
     ck(vgs_get_clusters_csr(h_, cluster_voxels_min_, &nc, &nt, nullptr, nullptr));
     std::vector<int64_t> off((size_t)nc + 1);
-    std::vector<int32_t> idx((size_t)(nt > 0 ? nt : 1));
-    ck(vgs_get_clusters_csr(h_, cluster_voxels_min_, &nc, &nt, off.data(), idx.data()));
-    clusters_point_idx_.assign((size_t)nc, std::vector<int>());
-    const bool paint = output_cloud && points_cloud_;
-    size_t at = 0;
-    if (paint) { at = output_cloud->points.size(); output_cloud->points.resize(at + (size_t)nt); }   // one allocation for all clustered points
-    for (int64_t c = 0; c < nc; c++) {
-      clusters_point_idx_[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
-      if (paint) {
-        uint32_t hsh = (uint32_t)c * 2654435761u;
-        for (int p : clusters_point_idx_[c]) {
-          pcl::PointXYZRGB& q = output_cloud->points[at++];
-          q.x = points_cloud_->points[p].x; q.y = points_cloud_->points[p].y; q.z = points_cloud_->points[p].z;
-          q.r = (uint8_t)(hsh >> 8); q.g = (uint8_t)(hsh >> 16); q.b = (uint8_t)(hsh >> 24);
+    std::unique_ptr<int32_t[]> idx(new int32_t[(size_t)(nt > 0 ? nt : 1)]);     // not zero-filled: the copy writes every entry
+    ck(vgs_get_clusters_csr(h_, cluster_voxels_min_, &nc, &nt, off.data(), idx.get()));
+    vgs_dropin::csr_to_lists(off, idx.get(), clusters_point_idx_);
+    if (!(output_cloud && points_cloud_)) return;
+    // the coloured cloud: clustered point k of the CSR -> output point at + k (cluster after cluster, as the reference
+    // pushes them); the gather from the input cloud runs on a few host threads
+    const size_t at = output_cloud->points.size();
+    output_cloud->points.reserve(at + (size_t)nt);    // one allocation for all clustered points
+    vgs_dropin::advise_huge(output_cloud->points.data(), (at + (size_t)nt) * sizeof(pcl::PointXYZRGB));
+    output_cloud->points.resize(at + (size_t)nt);
+    pcl::PointXYZRGB* dst = output_cloud->points.data() + at;
+    const auto& src = points_cloud_->points;
+    vgs_dropin::parallel_blocks((size_t)nt, (size_t)1 << 16, [&](size_t b, size_t e) {
+      size_t c = (size_t)(std::upper_bound(off.begin(), off.end(), (int64_t)b) - off.begin()) - 1;
+      for (size_t k = b; k < e;) {
+        while ((size_t)off[c + 1] <= k) c++;
+        const size_t stop = std::min(e, (size_t)off[c + 1]);
+        const uint32_t hsh = (uint32_t)c * 2654435761u;
+        const uint8_t r = (uint8_t)(hsh >> 8), g = (uint8_t)(hsh >> 16), bl = (uint8_t)(hsh >> 24);
+        for (; k < stop; k++) {
+          const auto& p = src[(size_t)idx[(std::ptrdiff_t)k]];
+          pcl::PointXYZRGB& q = dst[k];
+          q.x = p.x; q.y = p.y; q.z = p.z; q.r = r; q.g = g; q.b = bl;
         }
       }
-    }
-    if (paint) { output_cloud->width = (std::uint32_t)output_cloud->points.size(); output_cloud->height = 1; }
+    });
+    output_cloud->width = (std::uint32_t)output_cloud->points.size(); output_cloud->height = 1;
   }
 
   // ---- display exports (VS.h:424-945, 1016-1104).  Voxels are visited in voxel-id order (= the leaf
@@ -257,8 +266,6 @@ class VoxelBasedSegmentation {
   int voxel_points_min_ = 0, voxel_adjacency_min_ = 0, cluster_voxels_min_ = 0;
   float voxel_resolution_ = 0;
   std::vector<std::vector<int>> clusters_point_idx_;
-  std::vector<int64_t> adj_off_cache_;
-  std::vector<int32_t> adj_idx_cache_;
 };
 
 }  // namespace pcl

@@ -59,7 +59,7 @@ _lib = None
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only; no reference sources are used)."""
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(
-            os.path.getmtime(os.path.join(_HERE, f)) for f in ("vgs_oracle.cpp", "vgs_oracle.h")):
+            os.path.getmtime(os.path.join(_HERE, f)) for f in ("vgs_oracle.cpp", "vccs_oracle.cpp", "vgs_oracle.h", "Makefile")):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
 

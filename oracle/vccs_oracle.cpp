@@ -24,8 +24,9 @@
  *
  * Two schedules:  schedule 0 = PCL's sequential order (supervoxels expand one after the other and see each
  * other's claims inside a round; float sums in voxel order);  schedule 1 = synchronous rounds (every voxel picks
- * the best claim of the round, ties to the smaller label; centroid sums in 2^-20 / 2^-30 fixed point, hence
- * order independent) — the schedule the CUDA generator implements, and with which it must agree bit for bit.
+ * the best claim of the round, ties to the smaller label; centroid sums in 2^-20 / 2^-30 fixed point and the plane-fit
+ * moments in exact 2^-20 fixed-point integer arithmetic, hence order independent) — the schedule the CUDA generator
+ * implements, and with which it must agree bit for bit.
  */
 #include <algorithm>
 #include <array>
@@ -158,6 +159,73 @@ struct Vccs {
     float z = (n.x * n.x + n.y * n.y) + n.z * n.z;
     if (z > 0.f) { float s = std::sqrt(z); n.x /= s; n.y /= s; n.z /= s; }
     return n;
+  }
+
+  // ---- schedule 1: the same plane fit with ORDER-INDEPENDENT sums (what the CUDA generator computes).  Voxel centroids
+  //      in 2^-20 fixed point (64-bit integers); every voxel u first gets the moments of its own 27-neighbourhood relative
+  //      to itself (fit_moments); the two-ring multiset of v is then the sum of its neighbours' records translated by
+  //      q_u - q_v.  Integer arithmetic is exact, so 27 + 27 gathers give what the 27 x 27 walk of fit_normal sums. ----
+  struct Mom { int64_t n, s[3], m[6]; };
+  std::vector<Mom> mom;
+  static void q3(const F3& p, int64_t q[3]) {
+    q[0] = (int64_t)std::llrint((double)p.x * 1048576.0); q[1] = (int64_t)std::llrint((double)p.y * 1048576.0);
+    q[2] = (int64_t)std::llrint((double)p.z * 1048576.0);
+  }
+  void fit_moments(bool filtered) {
+    mom.assign((size_t)V, Mom{0, {0, 0, 0}, {0, 0, 0, 0, 0, 0}});
+    for (int64_t u = 0; u < V; u++) {
+      const int32_t f = filtered ? owner[u] : -2;
+      if (filtered && f < 0) continue;
+      int64_t qu[3];
+      q3(xyz[u], qu);
+      Mom A{0, {0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+      for (int k = 0; k < 27; k++) {
+        const int32_t w = nb[(size_t)u * 27 + k];
+        if (w < 0 || (f >= 0 && owner[w] != f)) continue;
+        int64_t qw[3];
+        q3(xyz[w], qw);
+        const int64_t x = qw[0] - qu[0], y = qw[1] - qu[1], z = qw[2] - qu[2];
+        A.n++; A.s[0] += x; A.s[1] += y; A.s[2] += z;
+        A.m[0] += x * x; A.m[1] += x * y; A.m[2] += x * z; A.m[3] += y * y; A.m[4] += y * z; A.m[5] += z * z;
+      }
+      mom[u] = A;
+    }
+  }
+  F3 fit_normal_fixed(int32_t v, int32_t filter /* -2: initial (self counted once more, no filter) */) const {
+    const F3 K = xyz[v];
+    int64_t qv[3];
+    q3(K, qv);
+    int64_t n = filter == -2 ? 1 : 0, S[3] = {0, 0, 0}, M[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 27; j++) {
+      const int32_t u = nb[(size_t)v * 27 + j];
+      if (u < 0 || (filter >= 0 && owner[u] != filter)) continue;
+      int64_t qu[3];
+      q3(xyz[u], qu);
+      const int64_t tx = qu[0] - qv[0], ty = qu[1] - qv[1], tz = qu[2] - qv[2];
+      const Mom& A = mom[u];
+      const int64_t c = A.n + 1;                    // u itself + its neighbourhood
+      n += c;
+      S[0] += A.s[0] + c * tx; S[1] += A.s[1] + c * ty; S[2] += A.s[2] + c * tz;
+      M[0] += A.m[0] + 2 * A.s[0] * tx + c * tx * tx;
+      M[1] += A.m[1] + A.s[0] * ty + tx * A.s[1] + c * tx * ty;
+      M[2] += A.m[2] + A.s[0] * tz + tx * A.s[2] + c * tx * tz;
+      M[3] += A.m[3] + 2 * A.s[1] * ty + c * ty * ty;
+      M[4] += A.m[4] + A.s[1] * tz + ty * A.s[2] + c * ty * tz;
+      M[5] += A.m[5] + 2 * A.s[2] * tz + c * tz * tz;
+    }
+    const float nanv = std::numeric_limits<float>::quiet_NaN();
+    if (n < 3) return F3{nanv, nanv, nanv};
+    const double cd = (double)n, sc = 9.094947017729282379150390625e-13;   // 2^-40: fixed point^2 -> m^2
+    const double mx = (double)S[0] / cd, my = (double)S[1] / cd, mz = (double)S[2] / cd;
+    float cov[6] = {(float)(((double)M[0] / cd - mx * mx) * sc), (float)(((double)M[1] / cd - mx * my) * sc),
+                    (float)(((double)M[2] / cd - mx * mz) * sc), (float)(((double)M[3] / cd - my * my) * sc),
+                    (float)(((double)M[4] / cd - my * mz) * sc), (float)(((double)M[5] / cd - mz * mz) * sc)};
+    F3 nn = smallest_eigenvector(cov);
+    F3 vp{0.0f - K.x, 0.0f - K.y, 0.0f - K.z};
+    if (dot3(vp, nn) < 0) { nn.x *= -1; nn.y *= -1; nn.z *= -1; }
+    float z = (nn.x * nn.x + nn.y * nn.y) + nn.z * nn.z;
+    if (z > 0.f) { float sq = std::sqrt(z); nn.x /= sq; nn.y /= sq; nn.z /= sq; }
+    return nn;
   }
 
   // voxelDataDistance(centroid of helper h, voxel v)
@@ -316,7 +384,12 @@ extern "C" int vgso_vccs(const float* xyz, int64_t n, int stride, int64_t V, con
   S.owner.assign((size_t)V, -1);
   S.dist.assign((size_t)V, std::numeric_limits<float>::max());
   S.nrm.resize((size_t)V);
-  for (int64_t v = 0; v < V; v++) S.nrm[v] = S.fit_normal((int32_t)v, -2);
+  if (p->schedule == 1) {
+    S.fit_moments(false);
+    for (int64_t v = 0; v < V; v++) S.nrm[v] = S.fit_normal_fixed((int32_t)v, -2);
+  } else {
+    for (int64_t v = 0; v < V; v++) S.nrm[v] = S.fit_normal((int32_t)v, -2);
+  }
   if (vox_normal)
     for (int64_t v = 0; v < V; v++) { vox_normal[3 * v] = S.nrm[v].x; vox_normal[3 * v + 1] = S.nrm[v].y; vox_normal[3 * v + 2] = S.nrm[v].z; }
 
@@ -397,8 +470,9 @@ extern "C" int vgso_vccs(const float* xyz, int64_t n, int stride, int64_t V, con
 
   // --- refineSupervoxels ---
   for (int it = 0; it < p->refine_iterations; it++) {
+    if (p->schedule == 1) S.fit_moments(true);
     for (int64_t v = 0; v < V; v++)
-      if (S.owner[v] >= 0) S.nrm[v] = S.fit_normal((int32_t)v, S.owner[v]);
+      if (S.owner[v] >= 0) S.nrm[v] = p->schedule == 1 ? S.fit_normal_fixed((int32_t)v, S.owner[v]) : S.fit_normal((int32_t)v, S.owner[v]);
     std::vector<int32_t> seedv((size_t)H, -1);
     for (int32_t h = 0; h < H; h++)
       if (S.alive[h]) seedv[h] = S.nearest_voxel(S.hc[h]);

@@ -54,7 +54,7 @@ def read_colored_pcd(path):
 def _compile():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     lib = os.path.join(ROOT, "vgs_svgs_segmentation_b200")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
                     os.path.join(ROOT, "tools", "vgs_driver.cpp"), "-L" + lib, "-lvgs_b200", "-Wl,-rpath," + lib], check=True)
 
 

@@ -14,7 +14,7 @@ P = ["0.15", "0.5", "0.2", "0.2", "0.2", "0.2", "0.2", "2", "0.3", "10", "3", "3
 
 def _compile():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
                     os.path.join(ROOT, "tests", "cpp", "dropin_vgs.cpp"), "-L" + os.path.join(ROOT, "vgs_svgs_segmentation_b200"),
                     "-lvgs_b200", "-Wl,-rpath," + os.path.join(ROOT, "vgs_svgs_segmentation_b200")], check=True)
 

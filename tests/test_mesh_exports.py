@@ -15,7 +15,7 @@ EDGES = [(0, 1), (0, 3), (1, 2), (2, 3), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4),
 
 def _compile():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
                     os.path.join(ROOT, "tests", "cpp", "mesh_exports.cpp"), "-L" + os.path.join(ROOT, "vgs_svgs_segmentation_b200"),
                     "-lvgs_b200", "-Wl,-rpath," + os.path.join(ROOT, "vgs_svgs_segmentation_b200")], check=True)
 

@@ -13,7 +13,7 @@ EXE = os.path.join(ROOT, "tests", "_build", "pcd_roundtrip")
 @pytest.fixture(scope="module")
 def exe():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", EXE,
                     os.path.join(ROOT, "tests", "cpp", "pcd_roundtrip.cpp")], check=True)
     return EXE
 

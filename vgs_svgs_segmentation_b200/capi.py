@@ -69,7 +69,7 @@ BLOBS = dict(POINT_KEY=(1, np.uint32), POINT_UNIT=(2, np.int32), UNIT_KEY=(3, np
              ADJ_IDX=(12, np.int32), CONN0_COUNT=(13, np.int32), CONN0_IDX=(14, np.int32), CONN1_COUNT=(15, np.int32),
              CONN1_IDX=(16, np.int32), ATTACH=(17, np.int32), UNIT_ROOT=(19, np.int32))
 
-EXPORTED = ["vgs_create", "vgs_destroy", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
+EXPORTED = ["vgs_create", "vgs_destroy", "vgs_acquire", "vgs_release", "vgs_pool_trim", "vgs_get_unit_adjacency", "vgs_last_error", "vgs_device_count", "vgs_set_points", "vgs_voxelize",
             "vgs_get_bounding_box", "vgs_set_bounding_box", "vgs_voxel_count", "vgs_get_voxel_centers", "vgs_set_supervoxel_labels", "vgs_make_supervoxels_grid", "vgs_make_supervoxels_vccs", "vgs_get_supervoxel_labels", "vgs_unit_count",
             "vgs_compute_features", "vgs_find_adjacency", "vgs_segment", "vgs_cluster_count", "vgs_get_point_labels",
             "vgs_get_clusters_csr", "vgs_run", "vgs_get_counts", "vgs_stage_timings", "vgs_debug_get", "vgs_kernel_timings",
@@ -91,6 +91,12 @@ def load():
         L.vgs_last_error.argtypes = [C.c_void_p]
         L.vgs_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
         L.vgs_destroy.argtypes = [C.c_void_p]
+        L.vgs_acquire.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
+        L.vgs_release.argtypes = [C.c_void_p]
+        L.vgs_release.restype = None
+        L.vgs_pool_trim.argtypes = []
+        L.vgs_pool_trim.restype = None
+        L.vgs_get_unit_adjacency.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.vgs_device_count.argtypes = [C.POINTER(C.c_int)]
         L.vgs_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]
         L.vgs_voxelize.argtypes = [C.c_void_p, C.c_float]
@@ -237,13 +243,15 @@ def make_params(voxel_size=0.15, graph_size=0.5, sig_p=0.2, sig_n=0.2, sig_o=0.2
 class Handle:
     """One vgs_handle (one device, one stream)."""
 
-    def __init__(self, mode=VGS_MODE_VGS, device=0, stream=None, leaf_order=0):
+    def __init__(self, mode=VGS_MODE_VGS, device=0, stream=None, leaf_order=0, pooled=False):
+        """pooled=True: vgs_acquire / vgs_release (the device working set is parked between handles, as the drop-in classes do)"""
         self.L = load()
         self.h = C.c_void_p()
         if stream == 0:
             stream = 1   # torch's default stream is CUDA's legacy default stream: pass cudaStreamLegacy, not NULL (= "own stream")
         cfg = Config(mode, device, stream, leaf_order)
-        st = self.L.vgs_create(C.byref(self.h), C.byref(cfg))
+        self.pooled = bool(pooled)
+        st = (self.L.vgs_acquire if pooled else self.L.vgs_create)(C.byref(self.h), C.byref(cfg))
         if st != 0:
             raise VgsError(st, self.L.vgs_last_error(None).decode())
         self.n = 0
@@ -251,8 +259,15 @@ class Handle:
 
     def close(self):
         if self.h:
-            self.L.vgs_destroy(self.h)
+            (self.L.vgs_release if self.pooled else self.L.vgs_destroy)(self.h)
             self.h = C.c_void_p()
+
+    def unit_adjacency(self, unit: int) -> np.ndarray:
+        """getOneVoxelAdjacency (VS.h:268): ids within graph_size of the unit, nearest first, itself first"""
+        n = C.c_int(0)
+        ids = np.empty(256, np.int32)
+        self._ck(self.L.vgs_get_unit_adjacency(self.h, unit, ids.ctypes.data, 256, C.byref(n)))
+        return ids[:n.value].copy()
 
     def __del__(self):
         try:

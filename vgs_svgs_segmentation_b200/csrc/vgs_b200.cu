@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <optional>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "vgs_kernels.cuh"
 #include "vgs_rows.cuh"
 #include "vgs_vccs.cuh"
+#include "vgs_hostio.cuh"
 
 using namespace vgs;
 
@@ -95,6 +97,8 @@ struct vgs_context {
   DBuf conn0_cnt, conn0_idx, conn1_cnt, conn1_idx, attach, parent, root, csize, cminpt, labels_out, tmp;
   int sort_key_bytes = 8;       // width of the voxel sort keys of the last vgs_voxelize
   uint32_t* d_perm = nullptr;   // sorted point indices
+  uint32_t* vox_perm = nullptr;  // point indices in voxel order as vgs_voxelize left them (with ustart / ukey: the voxel table)
+  bool vox_table_valid = false;  // ... until another sort reuses the shared buffers (SVGS unit builders)
   uint64_t hmask = 0;
   // lattice searches (VGS): host tables rebuilt only when (voxel_size, graph_size, float-noise bound) change
   std::vector<int4> stencil_host;   // radius stencil, sorted by integer distance class
@@ -111,7 +115,7 @@ struct vgs_context {
   DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
   bool use_idgrid = false;
   uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
-  DBuf fallback, uflags, singles, used_list;
+  DBuf fallback, uflags, singles, used_list, origin_state;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -122,7 +126,7 @@ struct vgs_context {
   int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
-    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, owner, owner2, dist, claim;
+    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, mom, owner, owner2, dist, claim;
     DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, cnt, tk, tv, tk2, tv2;
   } vc;
   int64_t vccs_seeds = 0;
@@ -499,10 +503,10 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
-  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm,
+  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom,
                  &c.owner, &c.owner2, &c.dist, &c.claim, &c.ckA, &c.ckB, &c.cvA, &c.cvB, &c.cstart, &c.ckey, &c.cpos, &c.cell3, &c.best,
                  &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.cnt, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
@@ -512,6 +516,71 @@ void vgs_destroy(vgs_handle h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// ---- pooled lifecycle: a parked handle keeps its device buffers, streams and events (cudaMalloc / cudaFree of the ~1.6 GB
+//      working set of a 10 M-point cloud cost more than the segmentation itself) ----
+namespace {
+std::mutex g_pool_mu;
+std::vector<vgs_handle> g_pool;
+constexpr size_t POOL_MAX = 4;
+void reset_for_reuse(vgs_handle h) {
+  h->err.clear();
+  h->launches = 0;
+  h->d_xyz = nullptr; h->n = 0; h->stride = 3;
+  h->d_labels = nullptr; h->max_label = 0;
+  h->voxel_size = 0; h->depth = 0; h->n_finite = 0; h->n_voxels = 0; h->nu = 0; h->n_valid = 0;
+  h->voxelized = h->have_graph = h->units_external = h->have_units = h->have_features = h->have_adj = h->have_segments = false;
+  h->have_geometry = h->have_cluster_stats = h->have_csr = h->conn0_is_mask = false;
+  h->last_voxels_min = std::numeric_limits<int>::min();
+  h->n_used = h->n_adj = h->n_pairs = h->max_n = h->n_singles = h->n_attached = h->closest_rounds = 0;
+  h->n_clusters_all = h->n_clusters_exp = 0; h->n_fallback = 0; h->csr_total = 0;
+  h->d_perm = nullptr; h->vox_perm = nullptr; h->vox_table_valid = false;
+  h->tm = vgs_timings{};
+  h->tm_pending = 0; h->k_pending = 0;
+  for (int i = 0; i < vgs_context::NK; i++) { h->k_ms[i] = 0.f; h->k_launches[i] = 0; }
+}
+}  // namespace
+
+vgs_status vgs_acquire(vgs_handle* out, const vgs_config* cfg) {
+  if (!out || !cfg) { g_create_error = "vgs_acquire: null argument"; return VGS_ERR_INVALID; }
+  if (!cfg->stream) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); i++) {
+      vgs_handle h = g_pool[i];
+      if (h->device == cfg->device && h->mode == cfg->mode && h->leaf_order == cfg->leaf_order) {
+        g_pool.erase(g_pool.begin() + (long)i);
+        *out = h;
+        return VGS_OK;
+      }
+    }
+  }
+  return vgs_create(out, cfg);
+}
+
+void vgs_release(vgs_handle h) {
+  if (!h) return;
+  static const bool no_pool = [] { const char* e = getenv("VGS_B200_NO_POOL"); return e && e[0] == '1'; }();   // A/B knob
+  if (h->own_stream && !no_pool) {
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) == cudaSuccess) {
+      reset_for_reuse(h);
+      std::lock_guard<std::mutex> lock(g_pool_mu);
+      if (g_pool.size() < POOL_MAX) { g_pool.push_back(h); return; }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  vgs_destroy(h);
+}
+
+void vgs_pool_trim(void) {
+  std::vector<vgs_handle> all;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    all.swap(g_pool);
+  }
+  for (vgs_handle h : all) vgs_destroy(h);
 }
 
 const char* vgs_last_error(vgs_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -532,7 +601,7 @@ vgs_status vgs_set_points(vgs_handle h, const float* xyz, int64_t n, int stride_
   else {
     StageTimer t(h, &h->tm.h2d_ms, 0);
     CK(h->xyz_own.reserve((size_t)n * stride_bytes));
-    CK(cudaMemcpyAsync(h->xyz_own.p, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(vgs_hostio::to_device(h->xyz_own.p, xyz, (size_t)n * stride_bytes, h->device, h->stream));
     h->d_xyz = h->xyz_own.as<float>();
     t.stop();
   }
@@ -547,7 +616,7 @@ vgs_status vgs_set_supervoxel_labels(vgs_handle h, const int32_t* labels, int32_
   if (on_device) h->d_labels = labels;
   else {
     CK(h->labels_own.reserve((size_t)h->n * 4));
-    CK(cudaMemcpyAsync(h->labels_own.p, labels, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(vgs_hostio::to_device(h->labels_own.p, labels, (size_t)h->n * 4, h->device, h->stream));
     h->d_labels = h->labels_own.as<int32_t>();
   }
   h->max_label = max_label;
@@ -610,6 +679,7 @@ static vgs_status voxelize_sorted(vgs_handle h, int gidx_w) {
     if (lastkey >> (3 * h->depth)) { n_fin = laststart; nunits--; }
     h->n_finite = n_fin;
     h->n_voxels = nunits;
+    h->vox_perm = vs; h->vox_table_valid = true;
     if (h->mode == VGS_MODE_VGS) {
       h->d_perm = vs;
       h->nu = nunits; h->n_valid = n_fin;
@@ -629,6 +699,7 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   const int64_t n = h->n;
   h->voxel_size = voxel_size;
   h->voxelized = false;
+  h->vox_table_valid = false;
   h->have_units = h->have_features = h->have_adj = h->have_segments = false;   // the sort buffers are shared
   h->units_external = false;
   CK(h->small.reserve(4096));
@@ -636,18 +707,52 @@ vgs_status vgs_voxelize(vgs_handle h, float voxel_size) {
   // ---- stage 0: PCL dynamic bounding box (origin) ----
   OriginBuilder ob;
   ob.begin((double)voxel_size);
+  static const bool host_origin = [] { const char* e = getenv("VGS_B200_HOST_ORIGIN"); return e && e[0] == '1'; }();   // A/B knob: one host round trip per epoch
   {
     StageTimer t(h, &h->tm.origin_ms, 1);
     KTimer kt(h, K_ORIGIN);
-    int64_t cursor = 0;
-    while (true) {
-      int64_t idx;
-      float p[3];
-      vgs_status s = find_next(h, cursor, ob.st, &idx, p);
-      if (s) return s;
-      if (idx >= n) break;
-      if (const char* why = ob.add(idx, p)) return h->fail(VGS_ERR_LIMIT, std::string("vgs_voxelize: ") + why);
-      cursor = idx + 1;
+    if (host_origin) {
+      int64_t cursor = 0;
+      while (true) {
+        int64_t idx;
+        float p[3];
+        vgs_status s = find_next(h, cursor, ob.st, &idx, p);
+        if (s) return s;
+        if (idx >= n) break;
+        if (const char* why = ob.add(idx, p)) return h->fail(VGS_ERR_LIMIT, std::string("vgs_voxelize: ") + why);
+        cursor = idx + 1;
+      }
+    } else {
+      // the growth loop runs on the device (k_origin_scan / k_origin_adopt rounds, state in device memory): the host
+      // enqueues a batch of rounds and reads the state once; a typical cloud is done after 6-9 rounds
+      CK(h->origin_state.reserve(sizeof(OriginState) + 64));
+      OriginState* d_st = h->origin_state.as<OriginState>();
+      LAUNCH(k_origin_init, 1, 1, 0, d_st, (double)voxel_size, (long long)n);
+      OriginState hs;
+      for (int batch = 0;; batch++) {
+        const int rounds = batch == 0 ? 10 : 16;
+        for (int r = 0; r < rounds; r++) {
+          LAUNCH(k_origin_scan, 148 * 8, 256, 0, h->d_xyz, h->stride, d_st);
+          LAUNCH(k_origin_adopt, 1, 1, 0, h->d_xyz, h->stride, d_st);
+        }
+        CK(cudaMemcpyAsync(&hs, d_st, sizeof(OriginState), cudaMemcpyDeviceToHost, h->stream));
+        CK(stream_wait(h->stream));
+        if (hs.done) break;
+        if (batch > 64) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: the bounding-box growth loop did not finish");
+      }
+      if (hs.error == 1) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: octree depth > 21 bits per axis (extent / voxel_size too large)");
+      if (hs.error == 2) return h->fail(VGS_ERR_LIMIT, "vgs_voxelize: too many bounding-box growth epochs");
+      // the device state in the host builder's terms (shifts of the epoch keys, installation into the handle)
+      ob.st.defined = hs.defined != 0;
+      ob.st.depth = hs.depth;
+      for (int a = 0; a < 3; a++) { ob.st.mn[a] = hs.mn[a]; ob.st.mx[a] = hs.mx[a]; }
+      for (int k = 0; k < hs.n_events; k++) ob.st.events.push_back(OctState::Ev{hs.ev_lowered[k], hs.ev_depth_old[k]});
+      ob.ep.n = hs.n_epochs;
+      for (int e = 0; e < hs.n_epochs; e++) {
+        ob.ep.viol[e] = hs.viol[e];
+        for (int a = 0; a < 3; a++) ob.ep.mn[e][a] = hs.ep_mn[e][a];
+        ob.events_before.push_back((size_t)hs.events_before[e]);
+      }
     }
     if (!ob.st.defined) return h->fail(VGS_ERR_INVALID, "vgs_voxelize: no finite point in the cloud");
     ob.finish();
@@ -674,6 +779,7 @@ vgs_status vgs_voxel_count(vgs_handle h, int64_t* nv) {
 
 static vgs_status build_svgs_units(vgs_handle h) {
   if (!h->d_labels) return h->fail(VGS_ERR_STATE, "SVGS: call vgs_set_supervoxel_labels first");
+  h->vox_table_valid = false;     // the shared sort buffers and the unit table are rebuilt over the labels
   const int64_t n = h->n;
   int32_t ml = h->max_label;
   if (ml <= 0) ml = std::numeric_limits<int32_t>::max();
@@ -681,7 +787,9 @@ static vgs_status build_svgs_units(vgs_handle h) {
   CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
   LAUNCH(k_label_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_labels, h->d_xyz, h->stride, n, ml, h->keysA.as<uint64_t>(), h->valsA.as<uint32_t>());
   uint64_t* ks; uint32_t* vs;
-  vgs_status s = radix_sort<uint64_t>(h, n, 33, &ks, &vs);
+  int label_bits = 1;
+  while (label_bits < 32 && ((uint32_t)ml >> label_bits)) label_bits++;      // keys are <= ml: only its bits are sorted
+  vgs_status s = radix_sort<uint64_t>(h, n, label_bits, &ks, &vs);
   if (s) return s;
   int64_t nunits = 0;
   s = build_units<uint64_t>(h, ks, n, &nunits);
@@ -691,7 +799,7 @@ static vgs_status build_svgs_units(vgs_handle h) {
   CK(cudaMemcpyAsync(&laststart, h->ustart.as<uint32_t>() + (nunits - 1), 4, cudaMemcpyDeviceToHost, h->stream));
   CK(stream_wait(h->stream));
   int64_t nval = n;
-  if (lastkey >> 32) { nval = laststart; nunits--; }
+  if (lastkey == (uint64_t)(uint32_t)ml) { nval = laststart; nunits--; }   // the segment of the dropped labels
   h->d_perm = vs;
   h->nu = nunits; h->n_valid = nval;
   h->have_units = true;
@@ -705,6 +813,7 @@ vgs_status vgs_make_supervoxels_grid(vgs_handle h, float seed_size) {
   if (!(seed_size > 0)) return h->fail(VGS_ERR_INVALID, "vgs_make_supervoxels_grid: seed_size must be > 0");
   CK(cudaSetDevice(h->device));
   const int64_t n = h->n;
+  h->vox_table_valid = false;
   CK(h->keysA.reserve((size_t)n * 8)); CK(h->keysB.reserve((size_t)n * 8));
   CK(h->valsA.reserve((size_t)n * 4)); CK(h->valsB.reserve((size_t)n * 4));
   LAUNCH(k_seed_cell_keys, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->box.mn[0], h->box.mn[1], h->box.mn[2],
@@ -743,30 +852,40 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   const int64_t n = h->n;
   const int desc = h->leaf_order == VGS_LEAF_DESCENDING ? 1 : 0;
   KTimer kvccs(h, K_VCCS);
-  // --- voxel table of its own (the shared sort buffers are reused by the unit builders) ---
-  CK(c.keysA.reserve((size_t)n * 8)); CK(c.keysB.reserve((size_t)n * 8));
-  CK(c.valsA.reserve((size_t)n * 4)); CK(c.valsB.reserve((size_t)n * 4));
-  LAUNCH(k_quantise<uint64_t>, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
-         c.keysA.as<uint64_t>(), c.valsA.as<uint32_t>(), (uint32_t*)nullptr);
-  uint64_t* ks; uint32_t* vs;
-  vgs_status s = radix_sort<uint64_t>(h, n, 3 * h->depth + 1, &ks, &vs, c.keysA.as<uint64_t>(), c.keysB.as<uint64_t>(), c.valsA.as<uint32_t>(),
-                            c.valsB.as<uint32_t>());
-  if (s) return s;
+  // --- voxel table: the one vgs_voxelize left behind (sorted point indices, voxel starts and keys) while it is intact;
+  //     the shared sort buffers are reused by the unit builders, so a later call sorts the points again ---
   int64_t V = 0;
-  s = build_units<uint64_t>(h, ks, n, &V, &c.start, &c.key, &c.pos);
-  if (s) return s;
-  {
-    uint64_t lastkey = 0;
-    CK(cudaMemcpyAsync(&lastkey, c.key.as<uint64_t>() + (V - 1), 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(stream_wait(h->stream));
-    if (lastkey >> (3 * h->depth)) V--;   // the segment of the non-finite points
+  const uint32_t* vs = nullptr;
+  const uint32_t* vstart = nullptr;
+  const uint64_t* vkeys = nullptr;
+  vgs_status s;
+  if (h->vox_table_valid) {
+    V = h->n_voxels; vs = h->vox_perm; vstart = h->ustart.as<uint32_t>(); vkeys = h->ukey.as<uint64_t>();
+  } else {
+    CK(c.keysA.reserve((size_t)n * 8)); CK(c.keysB.reserve((size_t)n * 8));
+    CK(c.valsA.reserve((size_t)n * 4)); CK(c.valsB.reserve((size_t)n * 4));
+    LAUNCH(k_quantise<uint64_t>, (unsigned)cdiv(n, 256), 256, 0, h->d_xyz, h->stride, n, h->ep, (double)h->voxel_size, h->depth, desc,
+           c.keysA.as<uint64_t>(), c.valsA.as<uint32_t>(), (uint32_t*)nullptr);
+    uint64_t* ks; uint32_t* vs_;
+    s = radix_sort<uint64_t>(h, n, 3 * h->depth + 1, &ks, &vs_, c.keysA.as<uint64_t>(), c.keysB.as<uint64_t>(), c.valsA.as<uint32_t>(),
+                             c.valsB.as<uint32_t>());
+    if (s) return s;
+    s = build_units<uint64_t>(h, ks, n, &V, &c.start, &c.key, &c.pos);
+    if (s) return s;
+    {
+      uint64_t lastkey = 0;
+      CK(cudaMemcpyAsync(&lastkey, c.key.as<uint64_t>() + (V - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(stream_wait(h->stream));
+      if (lastkey >> (3 * h->depth)) V--;   // the segment of the non-finite points
+    }
+    if (V != h->n_voxels) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: voxel table differs from vgs_voxelize's");
+    vs = vs_; vstart = c.start.as<uint32_t>(); vkeys = c.key.as<uint64_t>();
   }
-  if (V != h->n_voxels) return h->fail(VGS_ERR_STATE, "vgs_make_supervoxels_vccs: voxel table differs from vgs_voxelize's");
   CK(c.xyz.reserve((size_t)V * 12 + 16)); CK(c.key3.reserve((size_t)V * 12 + 16)); CK(c.plain.reserve((size_t)V * 8 + 16));
   CK(c.ptvox.reserve((size_t)n * 4)); CK(c.nb.reserve((size_t)V * 27 * 4)); CK(c.nrm.reserve((size_t)V * 12 + 16));
   CK(c.owner.reserve((size_t)V * 4)); CK(c.owner2.reserve((size_t)V * 4)); CK(c.dist.reserve((size_t)V * 4)); CK(c.claim.reserve((size_t)V * 4));
   CK(cudaMemsetAsync(c.ptvox.p, 0xff, (size_t)n * 4, h->stream));
-  LAUNCH(k_vccs_voxels, (unsigned)cdiv(V, 256), 256, 0, h->d_xyz, h->stride, vs, c.start.as<uint32_t>(), c.key.as<uint64_t>(), V, h->depth, desc,
+  LAUNCH(k_vccs_voxels, (unsigned)cdiv(V, 256), 256, 0, h->d_xyz, h->stride, vs, vstart, vkeys, V, h->depth, desc,
          c.xyz.as<float>(), c.key3.as<uint32_t>(), c.plain.as<uint64_t>(), c.ptvox.as<int32_t>());
   uint64_t capacity = 64;
   while (capacity < (uint64_t)V * 2) capacity <<= 1;
@@ -776,7 +895,10 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   LAUNCH(k_hash_insert, (unsigned)cdiv(V, 256), 256, 0, c.plain.as<uint64_t>(), V, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask);
   LAUNCH(k_vccs_neighbours, (unsigned)cdiv(V * 27, 256), 256, 0, c.key3.as<uint32_t>(), V, h->depth, c.tk.as<unsigned long long>(),
          c.tv.as<uint32_t>(), vmask, c.nb.as<int32_t>());
-  LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.nrm.as<float>());
+  CK(c.mom.reserve((size_t)V * sizeof(VMom) + 16));
+  LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>());
+  LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>(),
+         c.nrm.as<float>());
 
   // --- seeds ---
   const double seed_d = (double)seed_resolution;
@@ -785,7 +907,14 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   LAUNCH(k_vccs_cell_keys, (unsigned)cdiv(V, 256), 256, 0, c.xyz.as<float>(), V, h->box.mn[0], h->box.mn[1], h->box.mn[2], seed_d,
          c.ckA.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cell3.as<int32_t>());
   uint64_t* cks; uint32_t* cvs;
-  s = radix_sort<uint64_t>(h, V, 63, &cks, &cvs, c.ckA.as<uint64_t>(), c.ckB.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cvB.as<uint32_t>());
+  // seed cells are counted from the octree origin: a coordinate is below side / seed + 1, the morton key needs 3 x its bits
+  int cell_bits = 1;
+  {
+    const double side = std::ldexp((double)h->voxel_size, h->depth);
+    const double cells = std::floor(side / seed_d) + 2.0;
+    while (cell_bits < 21 && std::ldexp(1.0, cell_bits) < cells) cell_bits++;
+  }
+  s = radix_sort<uint64_t>(h, V, 3 * cell_bits, &cks, &cvs, c.ckA.as<uint64_t>(), c.ckB.as<uint64_t>(), c.cvA.as<uint32_t>(), c.cvB.as<uint32_t>());
   if (s) return s;
   int64_t NC = 0;
   s = build_units<uint64_t>(h, cks, V, &NC, &c.cstart, &c.ckey, &c.cpos);
@@ -835,14 +964,12 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   int32_t* own_b = c.owner2.as<int32_t>();
   auto expand = [&]() -> vgs_status {
     for (int it = 1; it < depth; it++) {
-      LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, c.nb.as<int32_t>(), own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
-             c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
-             spatial_importance, normal_importance);
-      std::swap(own_a, own_b);
       CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 48, h->stream));
       CK(cudaMemsetAsync(c.cnt.p, 0, (size_t)H * 8, h->stream));
-      LAUNCH(k_vccs_accumulate, (unsigned)cdiv(V, 256), 256, 0, V, own_a, c.xyz.as<float>(), c.nrm.as<float>(), c.acc.as<unsigned long long>(),
-             c.cnt.as<unsigned long long>());
+      LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, c.nb.as<int32_t>(), own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
+             c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
+             spatial_importance, normal_importance, c.acc.as<unsigned long long>(), c.cnt.as<unsigned long long>());
+      std::swap(own_a, own_b);
       LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, c.acc.as<unsigned long long>(), c.cnt.as<unsigned long long>(), c.hc.as<float>(),
              c.hn.as<float>(), c.alive.as<uint8_t>());
     }
@@ -852,7 +979,9 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   if (s) return s;
   // --- refineSupervoxels(k): normals inside each supervoxel, reseed at the voxel nearest to the centroid, expand ---
   for (int it = 0; it < refine_iterations; it++) {
-    LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.nrm.as<float>());
+    LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.mom.as<VMom>());
+    LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.mom.as<VMom>(),
+           c.nrm.as<float>());
     LAUNCH(k_vccs_reseed, (unsigned)cdiv(H * 32, 128), 128, 0, H, c.hc.as<float>(), c.alive.as<uint8_t>(), h->box.mn[0], h->box.mn[1], h->box.mn[2],
            (double)voxel_res, h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, c.xyz.as<float>(), c.seedv.as<int32_t>());
     LAUNCH(k_vccs_reset, (unsigned)cdiv(V, 256), 256, 0, V, own_a, c.dist.as<float>(), c.claim.as<int32_t>());
@@ -958,6 +1087,23 @@ vgs_status vgs_get_voxel_centers(vgs_handle h, float* xyz) {
   { vgs_status s = ensure_geometry(h); if (s) return s; }
   CK(cudaMemcpyAsync(xyz, h->center.p, (size_t)h->nu * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(stream_wait(h->stream));
+  return VGS_OK;
+}
+
+vgs_status vgs_get_unit_adjacency(vgs_handle h, int64_t unit, int32_t* ids, int cap, int* n) {
+  if (!h || !n) return VGS_ERR_INVALID;
+  if (!h->have_adj) return h->fail(VGS_ERR_STATE, "vgs_get_unit_adjacency: call vgs_find_adjacency first");
+  if (unit < 0 || unit >= h->nu) return h->fail(VGS_ERR_INVALID, "vgs_get_unit_adjacency: unit id out of range");
+  CK(cudaSetDevice(h->device));
+  uint32_t off[2] = {0, 0};
+  CK(cudaMemcpyAsync(off, h->adj_off.as<uint32_t>() + unit, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(stream_wait(h->stream));
+  const int len = (int)(off[1] - off[0]);
+  *n = len;
+  if (ids && cap > 0 && len > 0) {
+    CK(cudaMemcpyAsync(ids, h->adj_idx.as<int32_t>() + off[0], (size_t)std::min(len, cap) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(stream_wait(h->stream));
+  }
   return VGS_OK;
 }
 
@@ -1076,7 +1222,14 @@ vgs_status vgs_find_adjacency(vgs_handle h, float graph_size) {
     LAUNCH(k_cell_keys, (unsigned)cdiv(nu, 256), 256, 0, h->rec.as<float>(), nu, h->gridmin.as<uint32_t>(), cell,
            h->ckeysA.as<uint64_t>(), h->cvalsA.as<uint32_t>());
     uint64_t* ks; uint32_t* vs;
-    vgs_status s = radix_sort<uint64_t>(h, nu, 63, &ks, &vs, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(), h->cvalsA.as<uint32_t>(),
+    // cells are counted from the smallest centroid, which lies inside the octree box: coordinates are below side / cell + 2
+    int cell_bits = 1;
+    {
+      const double side = std::ldexp((double)h->voxel_size, h->depth);
+      const double cells = std::floor(side / (double)cell) + 3.0;
+      while (cell_bits < 21 && std::ldexp(1.0, cell_bits) < cells) cell_bits++;
+    }
+    vgs_status s = radix_sort<uint64_t>(h, nu, 3 * cell_bits, &ks, &vs, h->ckeysA.as<uint64_t>(), h->ckeysB.as<uint64_t>(), h->cvalsA.as<uint32_t>(),
                               h->cvalsB.as<uint32_t>());
     if (s) return s;
     int64_t ncells = 0;
@@ -1551,9 +1704,8 @@ vgs_status vgs_get_point_labels(vgs_handle h, int voxels_min, int32_t* labels, i
   t.stop();
   if (!on_device) {
     StageTimer t2(h, &h->tm.d2h_ms, 10);
-    CK(cudaMemcpyAsync(labels, d_out, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(vgs_hostio::to_host(labels, d_out, (size_t)h->n * 4, h->device, h->stream));   // synchronous: the caller's buffer is valid on return
     t2.stop();
-    CK(stream_wait(h->stream));   // the caller's host buffer is valid on return
   }
   return VGS_OK;
 }
@@ -1600,7 +1752,7 @@ vgs_status vgs_get_clusters_csr(vgs_handle h, int voxels_min, int64_t* n_cluster
   if (offsets && point_idx) {
     static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
     CK(cudaMemcpyAsync(offsets, h->csr_off.p, ((size_t)h->n_clusters_exp + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (h->csr_total > 0) CK(cudaMemcpyAsync(point_idx, h->csr_idx.p, (size_t)h->csr_total * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (h->csr_total > 0) CK(vgs_hostio::to_host(point_idx, h->csr_idx.p, (size_t)h->csr_total * 4, h->device, h->stream));
     CK(stream_wait(h->stream));
   }
   return VGS_OK;
@@ -1679,8 +1831,7 @@ vgs_status vgs_debug_get(vgs_handle h, vgs_blob_kind kind, void* dst, size_t* by
   auto copy_out = [&](const void* src, size_t nbytes) -> vgs_status {
     if (!dst) { *bytes = nbytes; return VGS_OK; }
     if (*bytes < nbytes) return h->fail(VGS_ERR_INVALID, "vgs_debug_get: buffer too small");
-    CK(stream_wait(h->stream));
-    CK(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost));
+    CK(vgs_hostio::to_host(dst, src, nbytes, h->device, h->stream));
     *bytes = nbytes;
     return VGS_OK;
   };

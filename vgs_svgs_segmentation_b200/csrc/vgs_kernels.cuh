@@ -67,6 +67,116 @@ __global__ void k_fetch_found(const float* __restrict__ xyz, int stride, const u
   out3[0] = p[0]; out3[1] = p[1]; out3[2] = p[2];
 }
 
+// ---- stage 0 on the device: the growth loop of PCL's dynamic bounding box without a host round trip per epoch.
+//      The state (box, depth, epoch table, growth events, scan cursor) lives in device memory; one ROUND is
+//      k_origin_scan (first finite point outside the box in the window [cursor, cursor + window)) followed by
+//      k_origin_adopt (one thread: adoptBoundingBoxToPoint / getKeyBitSize of octree_pointcloud.hpp on that point, or the
+//      window moves on).  The host enqueues a batch of rounds back to back and reads the state once; rounds after the
+//      end are empty launches.  Every operation of the adopt step is an IEEE double operation in the order of the host
+//      version (OctState::adopt), so both give the same box bit for bit (-fmad=false). ----
+constexpr int MAX_GROW_EVENTS = 40;
+struct OriginState {
+  double mn[3], mx[3], res;
+  unsigned depth;
+  int defined, done, error;          // error: 1 = depth > 21, 2 = too many epochs
+  long long cursor, window, n;
+  unsigned long long found;          // smallest violating index of the current window (~0 = none)
+  int n_epochs, n_events;
+  long long viol[MAX_EPOCHS];
+  double ep_mn[MAX_EPOCHS][3];
+  int events_before[MAX_EPOCHS];
+  unsigned ev_lowered[MAX_GROW_EVENTS], ev_depth_old[MAX_GROW_EVENTS];
+};
+constexpr long long ORIGIN_WINDOW0 = 1ll << 18;   // violations come early or never: a short window first, then x64 per miss
+__global__ void k_origin_init(OriginState* __restrict__ st, double res, long long n) {
+  st->res = res; st->depth = 0; st->defined = 0; st->done = n <= 0 ? 1 : 0; st->error = 0;
+  st->cursor = 0; st->window = ORIGIN_WINDOW0; st->n = n; st->found = ~0ull; st->n_epochs = 0; st->n_events = 0;
+  for (int a = 0; a < 3; a++) { st->mn[a] = 0; st->mx[a] = 0; }
+}
+__global__ void __launch_bounds__(256) k_origin_scan(const float* __restrict__ xyz, int stride, OriginState* __restrict__ st) {
+  if (st->done) return;
+  const long long start = st->cursor;
+  const long long end = min(st->n, start + st->window);
+  const int have_box = st->defined;
+  const double m0 = st->mn[0], m1 = st->mn[1], m2 = st->mn[2], M0 = st->mx[0], M1 = st->mx[1], M2 = st->mx[2];
+  unsigned long long best = ~0ull;
+  for (long long i = start + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long long)gridDim.x * blockDim.x) {
+    const float* p = xyz + i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    if (!finite3(x, y, z)) continue;
+    const bool out = !have_box || (double)x < m0 || (double)y < m1 || (double)z < m2 || (double)x >= M0 || (double)y >= M1 || (double)z >= M2;
+    if (out) { best = (unsigned long long)i; break; }   // indices ascend per thread
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+    best = t < best ? t : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&st->found, best);
+}
+__global__ void k_origin_adopt(const float* __restrict__ xyz, int stride, OriginState* __restrict__ st) {
+  if (st->done) return;
+  const unsigned long long f = st->found;
+  if (f == ~0ull) {       // nothing outside the box in this window
+    st->cursor += st->window;
+    st->window *= 64;
+    if (st->cursor >= st->n) st->done = 1;
+    return;
+  }
+  const float* q = xyz + (long long)f * stride;
+  const float p[3] = {q[0], q[1], q[2]};
+  const float eps = 1.1920928955078125e-07f;   // std::numeric_limits<float>::epsilon()
+  double mn[3] = {st->mn[0], st->mn[1], st->mn[2]}, mx[3] = {st->mx[0], st->mx[1], st->mx[2]};
+  const double res = st->res;
+  unsigned depth = st->depth;
+  bool defined = st->defined != 0;
+  int nev = st->n_events;
+  while (true) {
+    bool up[3], any = false;
+    for (int a = 0; a < 3; a++) {
+      const bool lo = p[a] < mn[a];
+      up[a] = p[a] >= mx[a];
+      any = any || lo || up[a];
+    }
+    if (!any && defined) break;
+    if (defined) {
+      double side = (double)(1 << depth) * res;
+      unsigned lowered = 0;
+      for (int a = 0; a < 3; a++) if (!up[a]) { mn[a] -= side; lowered |= 1u << a; }
+      if (nev < MAX_GROW_EVENTS) { st->ev_lowered[nev] = lowered; st->ev_depth_old[nev] = depth; }
+      nev++;
+      depth++;
+      side = (double)(1 << depth) * res - eps;
+      for (int a = 0; a < 3; a++) mx[a] = mn[a] + side;
+      if (depth > 30) break;
+    } else {
+      for (int a = 0; a < 3; a++) { mn[a] = p[a] - res / 2; mx[a] = p[a] + res / 2; }
+      unsigned mk = 2;
+      for (int a = 0; a < 3; a++) mk = max(mk, (unsigned)((mx[a] - mn[a]) / res));
+      depth = (unsigned)ceil(log((double)mk) / log(2.0) - eps);
+      const double side = (double)(1 << depth) * res - eps;
+      for (int a = 0; a < 3; a++) {
+        const double over = (side - (mx[a] - mn[a])) / 2.0;
+        mn[a] -= over; mx[a] += over;
+      }
+      defined = true;
+    }
+  }
+  for (int a = 0; a < 3; a++) { st->mn[a] = mn[a]; st->mx[a] = mx[a]; }
+  st->depth = depth; st->defined = 1; st->n_events = nev;
+  const int e = st->n_epochs;
+  if (depth > 21 || nev > MAX_GROW_EVENTS) { st->error = 1; st->done = 1; return; }
+  if (e >= MAX_EPOCHS) { st->error = 2; st->done = 1; return; }
+  st->viol[e] = (long long)f;
+  for (int a = 0; a < 3; a++) st->ep_mn[e][a] = mn[a];
+  st->events_before[e] = nev;
+  st->n_epochs = e + 1;
+  st->cursor = (long long)f + 1;
+  st->window = ORIGIN_WINDOW0;
+  st->found = ~0ull;
+  if (st->cursor >= st->n) st->done = 1;
+}
+
 // ---- stage 1a: octree key per point -> sortable 64-bit code, value = point index.
 //      key.a = (unsigned)((p.a - min_a)/res) in double (genOctreeKeyforPoint).  12 B read, 12 B written. ----
 //      K = uint32_t when the key (3 * depth bits + the sentinel bit) fits 32 bits: the sort then moves 8 instead of 12 bytes
@@ -98,7 +208,8 @@ __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ xyz,
   if (key3_out) { key3_out[3 * i] = kx; key3_out[3 * i + 1] = ky; key3_out[3 * i + 2] = kz; }
 }
 
-// SVGS units: key = supervoxel label (SV.h:288-323), dropped labels sort last
+// SVGS units: key = supervoxel label (SV.h:288-323); dropped labels get the key max_label, which sorts after every kept
+// label (kept labels are < max_label), so the sort only has to look at the bits of max_label
 __global__ void __launch_bounds__(256) k_label_keys(const int32_t* __restrict__ labels, const float* __restrict__ xyz, int stride, int64_t n,
                                                   int32_t max_label, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +217,7 @@ __global__ void __launch_bounds__(256) k_label_keys(const int32_t* __restrict__ 
   int32_t l = labels[i];
   vals[i] = (uint32_t)i;
   bool ok = l > 0 && l < max_label;
-  keys[i] = ok ? (uint64_t)(uint32_t)l : (1ull << 32);
+  keys[i] = ok ? (uint64_t)(uint32_t)l : (uint64_t)(uint32_t)max_label;
 }
 
 // Built-in stand-in for the supervoxel generator (the reference calls PCL's VCCS, SV.h:265-284, which

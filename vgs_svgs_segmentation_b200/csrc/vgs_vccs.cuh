@@ -55,41 +55,81 @@ __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restr
 __device__ __forceinline__ float vccs_dot3(float ax, float ay, float az, float bx, float by, float bz) { return (ax * bx + ay * by) + az * bz; }
 
 // ---- normals: plane fit (pcl::computePointNormal) over the multiset { [v] } + for u in N(v): u, N(u);
-//      filter -2: initial fit (self pushed first, everybody counts); owner != null: only voxels of v's supervoxel
-//      (SupervoxelHelper::refineNormals).  Sums are shifted by the voxel's own centroid.  One thread per voxel. ----
+//      filter -2: initial fit (self counted once more, everybody counts); owner != null: only voxels of v's supervoxel
+//      (SupervoxelHelper::refineNormals).
+//      The sums are ORDER INDEPENDENT: voxel centroids in 2^-20 fixed point, moments in 64-bit integers (exact).  That makes
+//      the two-ring walk factorise: k_vccs_moments gives every voxel u the moments of its own 27-neighbourhood relative to
+//      itself (27 gathers), k_vccs_normals sums the records of the 27 neighbours translated by q_u - q_v (27 gathers of
+//      80 bytes) — instead of the 27 x 27 = 729 gathers per voxel of the literal walk (0.73 ms -> 0.1 ms per fit at 1.5 M
+//      voxels).  oracle/vccs_oracle.cpp (fit_moments / fit_normal_fixed) is the same arithmetic. ----
+struct __align__(16) VMom { long long n, s[3], m[6]; };
+__device__ __forceinline__ void vccs_q3(const float* __restrict__ vxyz, int64_t w, long long q[3]) {
+  q[0] = __double2ll_rn((double)vxyz[3 * w] * 1048576.0);
+  q[1] = __double2ll_rn((double)vxyz[3 * w + 1] * 1048576.0);
+  q[2] = __double2ll_rn((double)vxyz[3 * w + 2] * 1048576.0);
+}
+__global__ void __launch_bounds__(128) k_vccs_moments(int64_t V, const float* __restrict__ vxyz, const int32_t* __restrict__ nb,
+                                                    const int32_t* __restrict__ owner, VMom* __restrict__ mom) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= V) return;
+  int f = -2;
+  if (owner) { f = owner[u]; if (f < 0) return; }        // the record of an unowned voxel is never read
+  long long qu[3];
+  vccs_q3(vxyz, u, qu);
+  VMom A;
+  A.n = 0; A.s[0] = A.s[1] = A.s[2] = 0;
+  for (int i = 0; i < 6; i++) A.m[i] = 0;
+  for (int k = 0; k < 27; k++) {
+    const int w = nb[u * 27 + k];
+    if (w < 0 || (f >= 0 && owner[w] != f)) continue;
+    long long qw[3];
+    vccs_q3(vxyz, w, qw);
+    const long long x = qw[0] - qu[0], y = qw[1] - qu[1], z = qw[2] - qu[2];
+    A.n++; A.s[0] += x; A.s[1] += y; A.s[2] += z;
+    A.m[0] += x * x; A.m[1] += x * y; A.m[2] += x * z; A.m[3] += y * y; A.m[4] += y * z; A.m[5] += z * z;
+  }
+  longlong2* out = reinterpret_cast<longlong2*>(mom + u);
+  out[0] = make_longlong2(A.n, A.s[0]); out[1] = make_longlong2(A.s[1], A.s[2]); out[2] = make_longlong2(A.m[0], A.m[1]);
+  out[3] = make_longlong2(A.m[2], A.m[3]); out[4] = make_longlong2(A.m[4], A.m[5]);
+}
 __global__ void __launch_bounds__(128) k_vccs_normals(int64_t V, const float* __restrict__ vxyz, const int32_t* __restrict__ nb,
-                                                    const int32_t* __restrict__ owner, float* __restrict__ nrm) {
+                                                    const int32_t* __restrict__ owner, const VMom* __restrict__ mom,
+                                                    float* __restrict__ nrm) {
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   int filter = -2;
   if (owner) { filter = owner[v]; if (filter < 0) return; }
   const float Kx = vxyz[3 * v], Ky = vxyz[3 * v + 1], Kz = vxyz[3 * v + 2];
-  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
-  int cnt = 0;
-  auto push = [&](int w) {
-    const float x = vxyz[3 * (int64_t)w] - Kx, y = vxyz[3 * (int64_t)w + 1] - Ky, z = vxyz[3 * (int64_t)w + 2] - Kz;
-    a0 += x * x; a1 += x * y; a2 += x * z; a3 += y * y; a4 += y * z; a5 += z * z;
-    a6 += x; a7 += y; a8 += z;
-    cnt++;
-  };
-  if (filter == -2) push((int)v);
+  long long qv[3];
+  vccs_q3(vxyz, v, qv);
+  long long n = filter == -2 ? 1 : 0, S0 = 0, S1 = 0, S2 = 0, M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0;
   for (int j = 0; j < 27; j++) {
     const int u = nb[v * 27 + j];
     if (u < 0 || (filter >= 0 && owner[u] != filter)) continue;
-    push(u);
-    for (int k = 0; k < 27; k++) {
-      const int w = nb[(int64_t)u * 27 + k];
-      if (w < 0 || (filter >= 0 && owner[w] != filter)) continue;
-      push(w);
-    }
+    long long qu[3];
+    vccs_q3(vxyz, u, qu);
+    const long long tx = qu[0] - qv[0], ty = qu[1] - qv[1], tz = qu[2] - qv[2];
+    const longlong2* in = reinterpret_cast<const longlong2*>(mom + u);
+    const longlong2 r0 = __ldg(in), r1 = __ldg(in + 1), r2 = __ldg(in + 2), r3 = __ldg(in + 3), r4 = __ldg(in + 4);
+    const long long c = r0.x + 1;                 // u itself + its neighbourhood
+    const long long sx = r0.y, sy = r1.x, sz = r1.y;
+    n += c;
+    S0 += sx + c * tx; S1 += sy + c * ty; S2 += sz + c * tz;
+    M0 += r2.x + 2 * sx * tx + c * tx * tx;
+    M1 += r2.y + sx * ty + tx * sy + c * tx * ty;
+    M2 += r3.x + sx * tz + tx * sz + c * tx * tz;
+    M3 += r3.y + 2 * sy * ty + c * ty * ty;
+    M4 += r4.x + sy * tz + ty * sz + c * ty * tz;
+    M5 += r4.y + 2 * sz * tz + c * tz * tz;
   }
   float nx, ny, nz;
-  if (cnt < 3) {
+  if (n < 3) {
     nx = ny = nz = __int_as_float(0x7fc00000);
   } else {
-    const float c = (float)cnt;
-    a0 /= c; a1 /= c; a2 /= c; a3 /= c; a4 /= c; a5 /= c; a6 /= c; a7 /= c; a8 /= c;
-    const Sym3 cov{a0 - a6 * a6, a1 - a6 * a7, a2 - a6 * a8, a3 - a7 * a7, a4 - a7 * a8, a5 - a8 * a8};
+    const double cd = (double)n, sc = 9.094947017729282379150390625e-13;   // 2^-40: fixed point^2 -> m^2
+    const double mx = (double)S0 / cd, my = (double)S1 / cd, mz = (double)S2 / cd;
+    const Sym3 cov{(float)(((double)M0 / cd - mx * mx) * sc), (float)(((double)M1 / cd - mx * my) * sc), (float)(((double)M2 / cd - mx * mz) * sc),
+                   (float)(((double)M3 / cd - my * my) * sc), (float)(((double)M4 / cd - my * mz) * sc), (float)(((double)M5 / cd - mz * mz) * sc)};
     // pcl::eigen33(mat, eigenvalue, eigenvector): eigenvector of the smallest eigenvalue
     float scale = fmaxf(fmaxf(fmaxf(fabsf(cov.a00), fabsf(cov.a01)), fmaxf(fabsf(cov.a02), fabsf(cov.a11))),
                         fmaxf(fabsf(cov.a12), fabsf(cov.a22)));
@@ -97,14 +137,14 @@ __global__ void __launch_bounds__(128) k_vccs_normals(int64_t V, const float* __
     const Sym3 a{cov.a00 / scale, cov.a01 / scale, cov.a02 / scale, cov.a11 / scale, cov.a12 / scale, cov.a22 / scale};
     float ev[3];
     roots3(a, ev);
-    F3 v1, v2, v3, n; float l1, l2, l3;
+    F3 v1, v2, v3, nn; float l1, l2, l3;
     row_crosses(a, ev[0], v1, v2, v3, l1, l2, l3);
-    pick_cross(v1, v2, v3, l1, l2, l3, n);
+    pick_cross(v1, v2, v3, l1, l2, l3, nn);
     // flipNormalTowardsViewpoint(point, 0, 0, 0, normal); normal[3] = 0; normalize
-    if (vccs_dot3(0.0f - Kx, 0.0f - Ky, 0.0f - Kz, n.x, n.y, n.z) < 0) { n.x *= -1; n.y *= -1; n.z *= -1; }
-    const float z = (n.x * n.x + n.y * n.y) + n.z * n.z;
-    if (z > 0.f) { const float s = sqrtf(z); n.x /= s; n.y /= s; n.z /= s; }
-    nx = n.x; ny = n.y; nz = n.z;
+    if (vccs_dot3(0.0f - Kx, 0.0f - Ky, 0.0f - Kz, nn.x, nn.y, nn.z) < 0) { nn.x *= -1; nn.y *= -1; nn.z *= -1; }
+    const float z = (nn.x * nn.x + nn.y * nn.y) + nn.z * nn.z;
+    if (z > 0.f) { const float sq = sqrtf(z); nn.x /= sq; nn.y /= sq; nn.z /= sq; }
+    nx = nn.x; ny = nn.y; nz = nn.z;
   }
   nrm[3 * v] = nx; nrm[3 * v + 1] = ny; nrm[3 * v + 2] = nz;
 }
@@ -198,55 +238,67 @@ __global__ void __launch_bounds__(256) k_vccs_helpers(const unsigned long long* 
 
 // ---- expandSupervoxels, one synchronous round: a voxel goes to the supervoxel (among the owners of its 26
 //      neighbours) whose centroid is nearest in voxelDataDistance, if that beats its best distance so far;
-//      ties to the smaller label (the sequential reference lets the first, i.e. smaller, label win) ----
+//      ties to the smaller label (the sequential reference lets the first, i.e. smaller, label win).
+//      The same kernel files the voxel under its (new) owner for SupervoxelHelper::updateCentroid: order-independent
+//      sums, 2^-20 fixed point for xyz, 2^-30 for normals; neighbouring voxels (Morton order) mostly share their
+//      supervoxel, so the lanes of a warp that chose the same owner add up first (REDUX on 20-bit halves — exact) and
+//      ONE lane issues the seven atomics. ----
+__device__ __forceinline__ long long vccs_group_sum(unsigned peers, long long q) {
+  const int lo = (int)(q & 0xfffff);       // q = hi * 2^20 + lo exactly (arithmetic shift); 32 of each fit an int
+  const int hi = (int)(q >> 20);
+  return (long long)__reduce_add_sync(peers, hi) * 1048576ll + (long long)__reduce_add_sync(peers, lo);
+}
 __global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const int32_t* __restrict__ nb, const int32_t* __restrict__ owner_old,
                                                    int32_t* __restrict__ owner_new, float* __restrict__ dist, const float* __restrict__ vxyz,
                                                    const float* __restrict__ nrm, const float* __restrict__ hc, const float* __restrict__ hn,
-                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn) {
-  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  const int own = owner_old[v];
-  float bd = dist[v];
-  int bh = own;
-  const float px = vxyz[3 * v], py = vxyz[3 * v + 1], pz = vxyz[3 * v + 2];
-  const float qx = nrm[3 * v], qy = nrm[3 * v + 1], qz = nrm[3 * v + 2];
-  int last = -1;
-  for (int j = 0; j < 27; j++) {
-    const int u = nb[v * 27 + j];
-    if (u < 0) continue;
-    const int h = owner_old[u];
-    if (h < 0 || h == own || h == last || !alive[h]) continue;   // h == last: same candidate again, same distance
-    last = h;
-    const float dx = hc[3 * (int64_t)h] - px, dy = hc[3 * (int64_t)h + 1] - py, dz = hc[3 * (int64_t)h + 2] - pz;
-    const float spatial = sqrtf(dx * dx + (dy * dy + dz * dz)) / seed_res;
-    const float color = 0.0f;
-    const float cosn = 1.0f - fabsf(vccs_dot3(hn[3 * (int64_t)h], hn[3 * (int64_t)h + 1], hn[3 * (int64_t)h + 2], qx, qy, qz));
-    const float d = cosn * wn + color * wc + spatial * ws;
-    if (d < bd || (d == bd && bh != own && h < bh)) { bd = d; bh = h; }
+                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn,
+                                                   unsigned long long* __restrict__ acc, unsigned long long* __restrict__ cnt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool ok = v < V;
+  int bh = -1;
+  float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+  if (ok) {
+    const int own = owner_old[v];
+    float bd = dist[v];
+    bh = own;
+    px = vxyz[3 * v]; py = vxyz[3 * v + 1]; pz = vxyz[3 * v + 2];
+    qx = nrm[3 * v]; qy = nrm[3 * v + 1]; qz = nrm[3 * v + 2];
+    int last = -1;
+    for (int j = 0; j < 27; j++) {
+      const int u = nb[v * 27 + j];
+      if (u < 0) continue;
+      const int h = owner_old[u];
+      if (h < 0 || h == own || h == last || !alive[h]) continue;   // h == last: same candidate again, same distance
+      last = h;
+      const float dx = hc[3 * (int64_t)h] - px, dy = hc[3 * (int64_t)h + 1] - py, dz = hc[3 * (int64_t)h + 2] - pz;
+      const float spatial = sqrtf(dx * dx + (dy * dy + dz * dz)) / seed_res;
+      const float color = 0.0f;
+      const float cosn = 1.0f - fabsf(vccs_dot3(hn[3 * (int64_t)h], hn[3 * (int64_t)h + 1], hn[3 * (int64_t)h + 2], qx, qy, qz));
+      const float d = cosn * wn + color * wc + spatial * ws;
+      if (d < bd || (d == bd && bh != own && h < bh)) { bd = d; bh = h; }
+    }
+    owner_new[v] = bh;
+    dist[v] = bd;
   }
-  owner_new[v] = bh;
-  dist[v] = bd;
-}
-
-// ---- SupervoxelHelper::updateCentroid with order-independent sums: 2^-20 fixed point for xyz, 2^-30 for normals ----
-__global__ void __launch_bounds__(256) k_vccs_accumulate(int64_t V, const int32_t* __restrict__ owner, const float* __restrict__ vxyz,
-                                                       const float* __restrict__ nrm, unsigned long long* __restrict__ acc,
-                                                       unsigned long long* __restrict__ cnt) {
-  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  const int h = owner[v];
-  if (h < 0) return;
-  unsigned long long* a = acc + (int64_t)h * 6;
-  atomicAdd(a + 0, (unsigned long long)__double2ll_rn((double)vxyz[3 * v] * 1048576.0));
-  atomicAdd(a + 1, (unsigned long long)__double2ll_rn((double)vxyz[3 * v + 1] * 1048576.0));
-  atomicAdd(a + 2, (unsigned long long)__double2ll_rn((double)vxyz[3 * v + 2] * 1048576.0));
-  const float nx = nrm[3 * v];
-  if (nx == nx) {   // NaN normals (isolated voxels) contribute nothing
-    atomicAdd(a + 3, (unsigned long long)__double2ll_rn((double)nx * 1073741824.0));
-    atomicAdd(a + 4, (unsigned long long)__double2ll_rn((double)nrm[3 * v + 1] * 1073741824.0));
-    atomicAdd(a + 5, (unsigned long long)__double2ll_rn((double)nrm[3 * v + 2] * 1073741824.0));
+  // SupervoxelHelper::updateCentroid sums of this round (acc / cnt are zeroed before the launch)
+  const bool owned = ok && bh >= 0;
+  const unsigned peers = __match_any_sync(0xffffffffu, owned ? bh : -1 - lane);    // unowned lanes: groups of one, skipped
+  const bool hasn = qx == qx;                                                      // NaN normals (isolated voxels) contribute nothing
+  const long long sx = vccs_group_sum(peers, owned ? __double2ll_rn((double)px * 1048576.0) : 0ll);
+  const long long sy = vccs_group_sum(peers, owned ? __double2ll_rn((double)py * 1048576.0) : 0ll);
+  const long long sz = vccs_group_sum(peers, owned ? __double2ll_rn((double)pz * 1048576.0) : 0ll);
+  const long long nx = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qx * 1073741824.0) : 0ll);
+  const long long ny = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qy * 1073741824.0) : 0ll);
+  const long long nz = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qz * 1073741824.0) : 0ll);
+  if (owned && lane == __ffs(peers) - 1) {
+    unsigned long long* a = acc + (int64_t)bh * 6;
+    atomicAdd(a + 0, (unsigned long long)sx); atomicAdd(a + 1, (unsigned long long)sy); atomicAdd(a + 2, (unsigned long long)sz);
+    if (nx) atomicAdd(a + 3, (unsigned long long)nx);
+    if (ny) atomicAdd(a + 4, (unsigned long long)ny);
+    if (nz) atomicAdd(a + 5, (unsigned long long)nz);
+    atomicAdd(cnt + bh, (unsigned long long)__popc(peers));
   }
-  atomicAdd(cnt + h, 1ull);
 }
 
 __global__ void __launch_bounds__(256) k_vccs_centroids(int64_t H, const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ cnt,
