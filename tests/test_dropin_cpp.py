@@ -48,3 +48,14 @@ def test_dropin_matches_oracle(built_lib, tmp_path):
     np.testing.assert_array_equal(lab, ref.point_label)
     assert f"voxels {ref.stats['n_units']} " in r.stdout
     assert f"clusters_all {ref.stats['n_clusters_all']} exported {ref.stats['n_clusters_exported']} " in r.stdout
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_host_parallel_helpers(threads):
+    """include/vgs_dropin/host_parallel.h: threaded list building / copying equals the serial definition (host only)"""
+    exe = os.path.join(ROOT, "tests", "_build", "host_parallel_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "host_parallel_check.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, VGS_DROPIN_THREADS=threads))
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

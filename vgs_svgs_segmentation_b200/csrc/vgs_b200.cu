@@ -127,7 +127,7 @@ struct vgs_context {
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
     DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, mom, owner, owner2, dist, claim;
-    DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, cnt, tk, tv, tk2, tv2;
+    DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, tk, tv, tk2, tv2;
   } vc;
   int64_t vccs_seeds = 0;
 
@@ -508,7 +508,7 @@ void vgs_destroy(vgs_handle h) {
   auto& c = h->vc;
   DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom,
                  &c.owner, &c.owner2, &c.dist, &c.claim, &c.ckA, &c.ckB, &c.cvA, &c.cvB, &c.cstart, &c.ckey, &c.cpos, &c.cell3, &c.best,
-                 &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.cnt, &c.tk, &c.tv, &c.tk2, &c.tv2};
+                 &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->kev) if (ev) cudaEventDestroy(ev);
@@ -934,7 +934,8 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   const float voxel_res = h->voxel_size;
   const float search_radius = 0.5f * seed_resolution;
   const float min_points = 0.05f * (search_radius) * (search_radius) * 3.1415926536f / (voxel_res * voxel_res);
-  const int reach = (int)std::ceil((double)search_radius / (double)voxel_res) + 1;
+  // two centroids closer than r lie in cells at most floor(r / res) + 1 apart per axis
+  const int reach = (int)std::floor((double)search_radius / (double)voxel_res * (1.0 + 1e-5)) + 1;
   if (reach > 40) return h->fail(VGS_ERR_LIMIT, "vgs_make_supervoxels_vccs: seed_resolution / voxel_resolution too large");
   LAUNCH(k_vccs_seed_filter, (unsigned)cdiv(NC * 32, 128), 128, 0, c.best.as<unsigned long long>(), c.claim.as<int32_t>(), NC, c.key3.as<uint32_t>(),
          c.xyz.as<float>(), h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, search_radius * search_radius, min_points, reach,
@@ -953,7 +954,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
     return h->fail(VGS_ERR_INVALID, "vgs_make_supervoxels_vccs: no seed survived (cloud too sparse for this seed_resolution)");
   }
   CK(c.hc.reserve((size_t)H * 12 + 16)); CK(c.hn.reserve((size_t)H * 12 + 16)); CK(c.alive.reserve((size_t)H + 16));
-  CK(c.acc.reserve((size_t)H * 48)); CK(c.cnt.reserve((size_t)H * 8)); CK(c.seedv.reserve((size_t)H * 4));
+  CK(c.acc.reserve((size_t)H * 56 + 16)); CK(c.seedv.reserve((size_t)H * 4));
   CK(cudaMemsetAsync(c.alive.p, 0, (size_t)H, h->stream));
   LAUNCH(k_vccs_helpers, (unsigned)cdiv(NC, 256), 256, 0, c.best.as<unsigned long long>(), c.flag.as<uint32_t>(), c.rank.as<uint32_t>(), NC,
          c.xyz.as<float>(), c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), c.owner.as<int32_t>());
@@ -964,13 +965,14 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   int32_t* own_b = c.owner2.as<int32_t>();
   auto expand = [&]() -> vgs_status {
     for (int it = 1; it < depth; it++) {
-      CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 48, h->stream));
-      CK(cudaMemsetAsync(c.cnt.p, 0, (size_t)H * 8, h->stream));
       LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, c.nb.as<int32_t>(), own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
              c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
-             spatial_importance, normal_importance, c.acc.as<unsigned long long>(), c.cnt.as<unsigned long long>());
+             spatial_importance, normal_importance);
       std::swap(own_a, own_b);
-      LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, c.acc.as<unsigned long long>(), c.cnt.as<unsigned long long>(), c.hc.as<float>(),
+      CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 56, h->stream));      // acc (6 x u64 per helper) and cnt live in one buffer
+      LAUNCH(k_vccs_accumulate, (unsigned)cdiv(cdiv(V, VCCS_ACC_RUN), 256), 256, 0, V, own_a, c.xyz.as<float>(), c.nrm.as<float>(), c.acc.as<unsigned long long>(),
+             c.acc.as<unsigned long long>() + (size_t)H * 6);
+      LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, c.acc.as<unsigned long long>(), c.acc.as<unsigned long long>() + (size_t)H * 6, c.hc.as<float>(),
              c.hn.as<float>(), c.alive.as<uint8_t>());
     }
     return VGS_OK;

@@ -10,6 +10,10 @@
 namespace vgs {
 
 constexpr float VCCS_FMAX = 3.402823466e+38f;
+// key of the generator's own voxel hash table: the three lattice coordinates side by side (21 bits each) — the lookups of
+// the neighbour table, the seed filter and the reseeding probe hundreds of cells per warp, and a Morton interleave per
+// probe was most of their instructions
+__device__ __forceinline__ uint64_t vccs_key(uint32_t x, uint32_t y, uint32_t z) { return ((uint64_t)x << 42) | ((uint64_t)y << 21) | (uint64_t)z; }
 
 // ---- computeVoxelData: voxel = float mean of its points (ascending point index), lattice key, point -> voxel ----
 __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
@@ -24,7 +28,7 @@ __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ x
   uint32_t kx, ky, kz;
   morton_decode(m, kx, ky, kz);
   key3[3 * v] = kx; key3[3 * v + 1] = ky; key3[3 * v + 2] = kz;
-  plain[v] = m;
+  plain[v] = vccs_key(kx, ky, kz);
   float sx = 0.f, sy = 0.f, sz = 0.f;
   const uint32_t b = vstart[v], e = vstart[v + 1];
   for (uint32_t j = b; j < e; j++) {
@@ -37,7 +41,9 @@ __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ x
   vxyz[3 * v] = sx / c; vxyz[3 * v + 1] = sy / c; vxyz[3 * v + 2] = sz / c;
 }
 
-// ---- OctreePointCloudAdjacency::computeNeighbors: the 27 lattice cells around a voxel, self included ----
+// ---- OctreePointCloudAdjacency::computeNeighbors: the 27 lattice cells around a voxel, self included.
+//      Table layout nb[v * 27 + j] (measured against the slot-major layout nb[j * V + v]: expand 95 vs 112 us, plane-fit
+//      moments 131 vs 184 us — a thread walks its own 108 bytes through L1, 27 far-apart streams per warp cost more) ----
 __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restrict__ key3, int64_t V, int depth,
                                                        const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
                                                        uint64_t mask, int32_t* __restrict__ nb) {
@@ -48,7 +54,7 @@ __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restr
   const int64_t lim = 1ll << depth;
   const int64_t x = (int64_t)key3[3 * v] + (j / 9 - 1), y = (int64_t)key3[3 * v + 1] + ((j / 3) % 3 - 1), z = (int64_t)key3[3 * v + 2] + (j % 3 - 1);
   int id = -1;
-  if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim) id = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+  if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim) id = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
   nb[i] = id;
 }
 
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(128) k_vccs_seed_filter(const unsigned long lo
       const int64_t x = (int64_t)key3[3 * s] + (t / (side * side) - reach), y = (int64_t)key3[3 * s + 1] + ((t / side) % side - reach),
                     z = (int64_t)key3[3 * s + 2] + (t % side - reach);
       if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim) continue;
-      const int w = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+      const int w = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
       if (w < 0) continue;
       const float dx = vxyz[3 * (int64_t)w] - sx, dy = vxyz[3 * (int64_t)w + 1] - sy, dz = vxyz[3 * (int64_t)w + 2] - sz;
       if (dx * dx + (dy * dy + dz * dz) < r2) num++;
@@ -238,67 +244,78 @@ __global__ void __launch_bounds__(256) k_vccs_helpers(const unsigned long long* 
 
 // ---- expandSupervoxels, one synchronous round: a voxel goes to the supervoxel (among the owners of its 26
 //      neighbours) whose centroid is nearest in voxelDataDistance, if that beats its best distance so far;
-//      ties to the smaller label (the sequential reference lets the first, i.e. smaller, label win).
-//      The same kernel files the voxel under its (new) owner for SupervoxelHelper::updateCentroid: order-independent
-//      sums, 2^-20 fixed point for xyz, 2^-30 for normals; neighbouring voxels (Morton order) mostly share their
-//      supervoxel, so the lanes of a warp that chose the same owner add up first (REDUX on 20-bit halves — exact) and
-//      ONE lane issues the seven atomics. ----
-__device__ __forceinline__ long long vccs_group_sum(unsigned peers, long long q) {
-  const int lo = (int)(q & 0xfffff);       // q = hi * 2^20 + lo exactly (arithmetic shift); 32 of each fit an int
-  const int hi = (int)(q >> 20);
-  return (long long)__reduce_add_sync(peers, hi) * 1048576ll + (long long)__reduce_add_sync(peers, lo);
-}
+//      ties to the smaller label (the sequential reference lets the first, i.e. smaller, label win) ----
 __global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const int32_t* __restrict__ nb, const int32_t* __restrict__ owner_old,
                                                    int32_t* __restrict__ owner_new, float* __restrict__ dist, const float* __restrict__ vxyz,
                                                    const float* __restrict__ nrm, const float* __restrict__ hc, const float* __restrict__ hn,
-                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn,
-                                                   unsigned long long* __restrict__ acc, unsigned long long* __restrict__ cnt) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool ok = v < V;
-  int bh = -1;
-  float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
-  if (ok) {
-    const int own = owner_old[v];
-    float bd = dist[v];
-    bh = own;
-    px = vxyz[3 * v]; py = vxyz[3 * v + 1]; pz = vxyz[3 * v + 2];
-    qx = nrm[3 * v]; qy = nrm[3 * v + 1]; qz = nrm[3 * v + 2];
-    int last = -1;
-    for (int j = 0; j < 27; j++) {
-      const int u = nb[v * 27 + j];
-      if (u < 0) continue;
-      const int h = owner_old[u];
-      if (h < 0 || h == own || h == last || !alive[h]) continue;   // h == last: same candidate again, same distance
-      last = h;
-      const float dx = hc[3 * (int64_t)h] - px, dy = hc[3 * (int64_t)h + 1] - py, dz = hc[3 * (int64_t)h + 2] - pz;
-      const float spatial = sqrtf(dx * dx + (dy * dy + dz * dz)) / seed_res;
-      const float color = 0.0f;
-      const float cosn = 1.0f - fabsf(vccs_dot3(hn[3 * (int64_t)h], hn[3 * (int64_t)h + 1], hn[3 * (int64_t)h + 2], qx, qy, qz));
-      const float d = cosn * wn + color * wc + spatial * ws;
-      if (d < bd || (d == bd && bh != own && h < bh)) { bd = d; bh = h; }
-    }
-    owner_new[v] = bh;
-    dist[v] = bd;
+                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int own = owner_old[v];
+  float bd = dist[v];
+  int bh = own;
+  const float px = vxyz[3 * v], py = vxyz[3 * v + 1], pz = vxyz[3 * v + 2];
+  const float qx = nrm[3 * v], qy = nrm[3 * v + 1], qz = nrm[3 * v + 2];
+  // (measured and rejected: fetching the 27 neighbour ids and then their 27 owners into registers first — 104 vs 95 us)
+  int last = -1;
+  for (int j = 0; j < 27; j++) {
+    const int u = nb[v * 27 + j];
+    if (u < 0) continue;
+    const int h = owner_old[u];
+    if (h < 0 || h == own || h == last || !alive[h]) continue;   // h == last: same candidate again, same distance
+    last = h;
+    const float dx = hc[3 * (int64_t)h] - px, dy = hc[3 * (int64_t)h + 1] - py, dz = hc[3 * (int64_t)h + 2] - pz;
+    const float spatial = sqrtf(dx * dx + (dy * dy + dz * dz)) / seed_res;
+    const float color = 0.0f;
+    const float cosn = 1.0f - fabsf(vccs_dot3(hn[3 * (int64_t)h], hn[3 * (int64_t)h + 1], hn[3 * (int64_t)h + 2], qx, qy, qz));
+    const float d = cosn * wn + color * wc + spatial * ws;
+    if (d < bd || (d == bd && bh != own && h < bh)) { bd = d; bh = h; }
   }
-  // SupervoxelHelper::updateCentroid sums of this round (acc / cnt are zeroed before the launch)
-  const bool owned = ok && bh >= 0;
-  const unsigned peers = __match_any_sync(0xffffffffu, owned ? bh : -1 - lane);    // unowned lanes: groups of one, skipped
-  const bool hasn = qx == qx;                                                      // NaN normals (isolated voxels) contribute nothing
-  const long long sx = vccs_group_sum(peers, owned ? __double2ll_rn((double)px * 1048576.0) : 0ll);
-  const long long sy = vccs_group_sum(peers, owned ? __double2ll_rn((double)py * 1048576.0) : 0ll);
-  const long long sz = vccs_group_sum(peers, owned ? __double2ll_rn((double)pz * 1048576.0) : 0ll);
-  const long long nx = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qx * 1073741824.0) : 0ll);
-  const long long ny = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qy * 1073741824.0) : 0ll);
-  const long long nz = vccs_group_sum(peers, owned && hasn ? __double2ll_rn((double)qz * 1073741824.0) : 0ll);
-  if (owned && lane == __ffs(peers) - 1) {
-    unsigned long long* a = acc + (int64_t)bh * 6;
+  owner_new[v] = bh;
+  dist[v] = bd;
+}
+
+// ---- SupervoxelHelper::updateCentroid with order-independent sums: 2^-20 fixed point for xyz, 2^-30 for normals.
+//      Consecutive voxels (Morton order) mostly share their supervoxel: a thread walks VCCS_ACC_RUN consecutive voxels and
+//      issues its seven atomics only when the owner changes.  (Measured and rejected: warp-level aggregation with
+//      match_any / REDUX over run masks — 138 us per round against 56 us for one set of atomics per voxel.) ----
+constexpr int VCCS_ACC_RUN = 8;
+__global__ void __launch_bounds__(256) k_vccs_accumulate(int64_t V, const int32_t* __restrict__ owner, const float* __restrict__ vxyz,
+                                                       const float* __restrict__ nrm, unsigned long long* __restrict__ acc,
+                                                       unsigned long long* __restrict__ cnt) {
+  const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VCCS_ACC_RUN;
+  if (v0 >= V) return;
+  int cur = -1;
+  long long sx = 0, sy = 0, sz = 0, nx = 0, ny = 0, nz = 0;
+  unsigned long long c = 0;
+  auto flush = [&]() {
+    if (cur < 0 || c == 0) return;
+    unsigned long long* a = acc + (int64_t)cur * 6;
     atomicAdd(a + 0, (unsigned long long)sx); atomicAdd(a + 1, (unsigned long long)sy); atomicAdd(a + 2, (unsigned long long)sz);
     if (nx) atomicAdd(a + 3, (unsigned long long)nx);
     if (ny) atomicAdd(a + 4, (unsigned long long)ny);
     if (nz) atomicAdd(a + 5, (unsigned long long)nz);
-    atomicAdd(cnt + bh, (unsigned long long)__popc(peers));
+    atomicAdd(cnt + cur, c);
+  };
+#pragma unroll
+  for (int k = 0; k < VCCS_ACC_RUN; k++) {
+    const int64_t v = v0 + k;
+    if (v >= V) break;
+    const int h = owner[v];
+    if (h != cur) { flush(); cur = h; sx = sy = sz = nx = ny = nz = 0; c = 0; }
+    if (h < 0) continue;
+    sx += __double2ll_rn((double)vxyz[3 * v] * 1048576.0);
+    sy += __double2ll_rn((double)vxyz[3 * v + 1] * 1048576.0);
+    sz += __double2ll_rn((double)vxyz[3 * v + 2] * 1048576.0);
+    const float fx = nrm[3 * v];
+    if (fx == fx) {   // NaN normals (isolated voxels) contribute nothing
+      nx += __double2ll_rn((double)fx * 1073741824.0);
+      ny += __double2ll_rn((double)nrm[3 * v + 1] * 1073741824.0);
+      nz += __double2ll_rn((double)nrm[3 * v + 2] * 1073741824.0);
+    }
+    c++;
   }
+  flush();
 }
 
 __global__ void __launch_bounds__(256) k_vccs_centroids(int64_t H, const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ cnt,
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(128) k_vccs_reseed(int64_t H, const float* __r
       for (int t = lane; t < side * side * side; t += 32) {
         const long long x = kx + (t / (side * side) - R), y = ky + ((t / side) % side - R), z = kz + (t % side - R);
         if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim) continue;
-        const int v = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+        const int v = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
         if (v < 0) continue;
         const float dx = vxyz[3 * (int64_t)v] - cx, dy = vxyz[3 * (int64_t)v + 1] - cy, dz = vxyz[3 * (int64_t)v + 2] - cz;
         const float d2 = dx * dx + (dy * dy + dz * dz);
