@@ -115,7 +115,7 @@ struct vgs_context {
   DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
   bool use_idgrid = false;
   uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
-  DBuf fallback, uflags, singles, used_list, origin_state;
+  DBuf fallback, uflags, singles, singles_dep, used_list, origin_state;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -503,7 +503,7 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state, &h->singles_dep};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
   DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom,
@@ -1619,17 +1619,27 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     uint32_t scnt[2] = {0, 0};
     CK(cudaMemcpyAsync(scnt, d_scnt, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
-    // rounds are launched three at a time with one flag each and read back together (a round costs microseconds, a host
-    // round trip more): the fixed point is reached when a round changes nothing
+    // The first round visits every eligible single and files the ones whose result can still move (a candidate that is a
+    // smaller-id single) in a sublist; the following rounds visit only that sublist (its length is read on the device).
+    // Rounds are launched three at a time with one flag each and read back together (a round costs microseconds, a host
+    // round trip more): the fixed point is reached when a round changes nothing.
     int rounds = 0;
     bool more = scnt[0] > 0;
+    uint32_t* d_dep_cnt = h->small.as<uint32_t>() + 136;
+    if (more) { CK(h->singles_dep.reserve((size_t)scnt[0] * 4 + 16)); CK(cudaMemsetAsync(d_dep_cnt, 0, 4, h->stream)); }
     while (more) {
       constexpr int BATCH = 3;
       CK(cudaMemsetAsync(d_changed, 0, 4 * BATCH, h->stream));
-      for (int b = 0; b < BATCH; b++)
-        LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
-               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
-               h->attach.as<int32_t>(), d_changed + b);
+      for (int b = 0; b < BATCH; b++) {
+        if (rounds == 0 && b == 0)
+          LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
+                 h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
+                 h->attach.as<int32_t>(), d_changed + b, (const uint32_t*)nullptr, h->singles_dep.as<uint32_t>(), d_dep_cnt);
+        else
+          LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles_dep.as<uint32_t>(), scnt[0],
+                 h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
+                 h->attach.as<int32_t>(), d_changed + b, (const uint32_t*)d_dep_cnt);
+      }
       uint32_t changed[BATCH] = {0, 0, 0};
       CK(cudaMemcpyAsync(changed, d_changed, 4 * BATCH, cudaMemcpyDeviceToHost, h->stream));
       CK(stream_wait(h->stream));

@@ -833,14 +833,18 @@ __global__ void __launch_bounds__(256) k_collect_singles(const uint32_t* __restr
   list[atomicAdd(&counts[0], 1u)] = (uint32_t)i;
 }
 // one warp per single unit: lanes evaluate the candidates; the winner is the LAST candidate with the
-// largest weight (`>=` in VS.h:2281), candidates in the order slot 0 (= the COUNT), then the neighbours
+// largest weight (`>=` in VS.h:2281), candidates in the order slot 0 (= the COUNT), then the neighbours.
+// A single can only change between rounds when one of its candidates is itself a single with a smaller id (the only
+// dynamic eligibility rule): the first round files those singles in dep_list, the later rounds (nlist_dev = its length,
+// read on the device: no host round trip in between) visit only them.
 __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __restrict__ list, uint32_t nlist, const uint32_t* __restrict__ adj_off,
                                                           const int32_t* __restrict__ adj_idx, const uint32_t* __restrict__ cnt1,
                                                           const float* __restrict__ rec, int64_t nu, PairParams pp, int32_t* attach,
-                                                          uint32_t* __restrict__ changed) {
+                                                          uint32_t* __restrict__ changed, const uint32_t* __restrict__ nlist_dev = nullptr,
+                                                          uint32_t* __restrict__ dep_list = nullptr, uint32_t* __restrict__ dep_count = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (li >= nlist) return;
+  if (li >= nlist || (nlist_dev && li >= *nlist_dev)) return;
   const int64_t i = list[li];
   const uint32_t off = adj_off[i];
   const int n = (int)(adj_off[i + 1] - off);
@@ -848,10 +852,12 @@ __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __re
   for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
   float best = 0.f;
   int bj = -1, bi = -1;
+  bool dynamic = false;
   for (int j = lane; j <= n; j += 32) {
     const int64_t c = (j == 0) ? (int64_t)n : (int64_t)adj_idx[off + j - 1];
     if (c < 0 || c >= nu) continue;
     const uint32_t cc = cnt1[c];
+    if (cc == 1u && c < i) dynamic = true;
     if (!(cc > 1u || (cc == 1u && c < i && ((volatile int32_t*)attach)[c] >= 0))) continue;
     for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
     float w_ab, w_ba;
@@ -864,7 +870,11 @@ __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __re
     const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (oj >= 0 && (bj < 0 || ow > best || (ow == best && oj > bj))) { best = ow; bj = oj; bi = oi; }
   }
-  if (lane == 0 && bi != attach[i]) { attach[i] = bi; *changed = 1u; }
+  const bool any_dynamic = __any_sync(0xffffffffu, dynamic);
+  if (lane == 0) {
+    if (bi != attach[i]) { attach[i] = bi; *changed = 1u; }
+    if (dep_list && any_dynamic) dep_list[atomicAdd(dep_count, 1u)] = (uint32_t)i;
+  }
 }
 
 // ---- stage 5d: connected components by lock-free union-find, root = smallest unit id ----
