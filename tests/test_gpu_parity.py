@@ -11,6 +11,11 @@ from vgs_svgs_segmentation_b200 import scenes
 
 from util import VGS_PARAMS, csr_sets, gpu_stages, oracle_conn_sets
 
+
+def capi_handle(**kw):
+    from vgs_svgs_segmentation_b200 import capi
+    return capi.Handle(**kw)
+
 pytestmark = pytest.mark.gpu
 
 FEATURE_RTOL = 1e-5   # north_star: "per-voxel features agree within 1e-5 relative in fp32"
@@ -402,3 +407,34 @@ def test_svgs_tiny(built_lib):
     g = gpu_stages(xyz, mode=1, labels=labels, max_label=ml)
     r = oracle.run(xyz, labels=labels, max_label=ml, mode=1, math=1)
     _compare_svgs(xyz, labels, g, r)
+
+
+def test_origin_growth_loop_late_violations(built_lib):
+    """the device-side growth loop of PCL's bounding box (k_origin_scan / k_origin_adopt): violations far apart in the
+    insertion order make the scan windows miss and grow (x64), and the ten rounds of the first batch are not enough —
+    box, depth and every key must still equal the oracle's sequential insertion"""
+    rng = np.random.default_rng(11)
+    n = 1_400_000
+    xyz = (rng.random((n, 3)) * np.array([1.0, 1.0, 0.3])).astype(np.float32)             # a dense patch ...
+    far = {5: (2.5, 0.2, 0.1), 300_000: (-3.0, 0.5, 0.2), 600_001: (0.5, 9.0, 0.1), 700_000: (0.2, -20.0, 0.3),
+           980_000: (45.0, 1.0, 0.2), 1_250_000: (0.5, 0.5, 70.0), 1_399_999: (-150.0, 2.0, 1.0)}  # ... and late outliers
+    for i, p in far.items():
+        xyz[i] = p
+    xyz[17] = (np.nan, 0.0, 0.0)
+    g = gpu_stages(xyz)
+    r = oracle.run(xyz, math=1)
+    assert r.stats["growth_events"] >= 10
+    _compare_vgs(xyz, g, r)
+
+
+def test_origin_depth_limit_is_reported(built_lib):
+    """an extent beyond 2^21 voxels per axis fails loudly (VGS_ERR_LIMIT), from the device loop as from the host one"""
+    xyz = np.array([[0, 0, 0], [1, 1, 1], [4.0e5, 0, 0]], np.float32)
+    h = capi_handle()
+    try:
+        h.set_points(xyz)
+        with pytest.raises(Exception) as e:
+            h.voxelize(0.15)
+        assert "depth" in str(e.value)
+    finally:
+        h.close()
