@@ -115,7 +115,7 @@ struct vgs_context {
   DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
   bool use_idgrid = false;
   uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
-  DBuf fallback, uflags, singles, singles_dep, used_list, origin_state;
+  DBuf fallback, uflags, singles, singles_dep, singles_best, used_list, origin_state;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -126,7 +126,7 @@ struct vgs_context {
   int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
-    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, mom, owner, owner2, dist, claim;
+    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, mom, bits, owner, owner2, dist, claim;
     DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, tk, tv, tk2, tv2;
   } vc;
   int64_t vccs_seeds = 0;
@@ -503,10 +503,10 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state, &h->singles_dep};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state, &h->singles_dep, &h->singles_best};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
-  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom,
+  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom, &c.bits,
                  &c.owner, &c.owner2, &c.dist, &c.claim, &c.ckA, &c.ckB, &c.cvA, &c.cvB, &c.cstart, &c.ckey, &c.cpos, &c.cell3, &c.best,
                  &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
@@ -893,8 +893,27 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   CK(c.tk.reserve(capacity * 8)); CK(c.tv.reserve(capacity * 4));
   CK(cudaMemsetAsync(c.tk.p, 0xff, capacity * 8, h->stream));
   LAUNCH(k_hash_insert, (unsigned)cdiv(V, 256), 256, 0, c.plain.as<uint64_t>(), V, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask);
+  // occupancy bits of the voxel lattice over the occupied key range (+ the largest search reach): the cube searches below
+  // test a bit before they probe the hash table
+  VccsBits ob{};
+  {
+    const int margin = 34;        // reseeding looks up to 32 cells away
+    ob.g.x0 = (int)h->kminmax[0] - margin; ob.g.y0 = (int)h->kminmax[1] - margin; ob.g.z0 = (int)h->kminmax[2] - margin;
+    const uint64_t nx = (uint64_t)(h->kminmax[3] - h->kminmax[0] + 1) + 2 * margin;
+    ob.g.ny = (uint32_t)(h->kminmax[4] - h->kminmax[1] + 1) + 2 * margin;
+    ob.g.nz = (uint32_t)(h->kminmax[5] - h->kminmax[2] + 1) + 2 * margin;
+    ob.nx = (uint32_t)nx;
+    const uint64_t nbits = nx * ob.g.ny * ob.g.nz;
+    if (nbits <= ((uint64_t)1 << 33)) {
+      const size_t bytes = (size_t)(nbits / 8) + 64;
+      CK(c.bits.reserve(bytes));
+      CK(cudaMemsetAsync(c.bits.p, 0, bytes, h->stream));
+      LAUNCH(k_vccs_bits_set, (unsigned)cdiv(V, 256), 256, 0, c.key3.as<uint32_t>(), V, ob.g, c.bits.as<uint32_t>());
+      ob.bits = c.bits.as<uint32_t>();
+    }
+  }
   LAUNCH(k_vccs_neighbours, (unsigned)cdiv(V * 27, 256), 256, 0, c.key3.as<uint32_t>(), V, h->depth, c.tk.as<unsigned long long>(),
-         c.tv.as<uint32_t>(), vmask, c.nb.as<int32_t>());
+         c.tv.as<uint32_t>(), vmask, ob, c.nb.as<int32_t>());
   CK(c.mom.reserve((size_t)V * sizeof(VMom) + 16));
   LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>());
   LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>(),
@@ -938,7 +957,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   const int reach = (int)std::floor((double)search_radius / (double)voxel_res * (1.0 + 1e-5)) + 1;
   if (reach > 40) return h->fail(VGS_ERR_LIMIT, "vgs_make_supervoxels_vccs: seed_resolution / voxel_resolution too large");
   LAUNCH(k_vccs_seed_filter, (unsigned)cdiv(NC * 32, 128), 128, 0, c.best.as<unsigned long long>(), c.claim.as<int32_t>(), NC, c.key3.as<uint32_t>(),
-         c.xyz.as<float>(), h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, search_radius * search_radius, min_points, reach,
+         c.xyz.as<float>(), h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, ob, search_radius * search_radius, min_points, reach,
          c.flag.as<uint32_t>());
   unsigned long long Htot = 0;
   s = scan_u32(h, c.flag.as<uint32_t>(), c.rank.as<uint32_t>(), NC, &Htot);
@@ -985,7 +1004,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
     LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.mom.as<VMom>(),
            c.nrm.as<float>());
     LAUNCH(k_vccs_reseed, (unsigned)cdiv(H * 32, 128), 128, 0, H, c.hc.as<float>(), c.alive.as<uint8_t>(), h->box.mn[0], h->box.mn[1], h->box.mn[2],
-           (double)voxel_res, h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, c.xyz.as<float>(), c.seedv.as<int32_t>());
+           (double)voxel_res, h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, ob, c.xyz.as<float>(), c.seedv.as<int32_t>());
     LAUNCH(k_vccs_reset, (unsigned)cdiv(V, 256), 256, 0, V, own_a, c.dist.as<float>(), c.claim.as<int32_t>());
     LAUNCH(k_vccs_reseed_claim, (unsigned)cdiv(H, 256), 256, 0, H, c.seedv.as<int32_t>(), c.alive.as<uint8_t>(), c.claim.as<int32_t>());
     LAUNCH(k_vccs_reseed_apply, (unsigned)cdiv(H, 256), 256, 0, H, c.seedv.as<int32_t>(), c.alive.as<uint8_t>(), c.claim.as<int32_t>(), own_a);
@@ -1626,20 +1645,19 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     int rounds = 0;
     bool more = scnt[0] > 0;
     uint32_t* d_dep_cnt = h->small.as<uint32_t>() + 136;
-    if (more) { CK(h->singles_dep.reserve((size_t)scnt[0] * 4 + 16)); CK(cudaMemsetAsync(d_dep_cnt, 0, 4, h->stream)); }
+    if (more) {
+      CK(h->singles_dep.reserve((size_t)scnt[0] * 4 + 16));
+      CK(h->singles_best.reserve((size_t)scnt[0] * sizeof(ClosestBest) + 16));
+      CK(cudaMemsetAsync(d_dep_cnt, 0, 4, h->stream));
+    }
     while (more) {
       constexpr int BATCH = 3;
       CK(cudaMemsetAsync(d_changed, 0, 4 * BATCH, h->stream));
-      for (int b = 0; b < BATCH; b++) {
-        if (rounds == 0 && b == 0)
-          LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
-                 h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
-                 h->attach.as<int32_t>(), d_changed + b, (const uint32_t*)nullptr, h->singles_dep.as<uint32_t>(), d_dep_cnt);
-        else
-          LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles_dep.as<uint32_t>(), scnt[0],
-                 h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
-                 h->attach.as<int32_t>(), d_changed + b, (const uint32_t*)d_dep_cnt);
-      }
+      for (int b = 0; b < BATCH; b++)
+        LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
+               h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
+               h->attach.as<int32_t>(), d_changed + b, (rounds == 0 && b == 0) ? 1 : 0, h->singles_best.as<ClosestBest>(),
+               h->singles_dep.as<uint32_t>(), d_dep_cnt);
       uint32_t changed[BATCH] = {0, 0, 0};
       CK(cudaMemcpyAsync(changed, d_changed, 4 * BATCH, cudaMemcpyDeviceToHost, h->stream));
       CK(stream_wait(h->stream));
@@ -1812,7 +1830,7 @@ vgs_status vgs_kernel_timings(vgs_handle h, vgs_kernel_timing* out, int* n) {
   cudaSetDevice(h->device);
   resolve_timers(h);
   static const char* names[vgs_context::NK] = {
-      "origin: k_find_outside rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_heads_reduce + k_scan_tiles + k_heads_down + k_voxel_keys",
+      "origin: k_origin_scan + k_origin_adopt rounds", "keys: k_quantise", "sort: k_rs_hist + scan + k_rs_scatter per digit", "heads: k_heads_reduce + k_scan_tiles + k_heads_down + k_voxel_keys",
       "features: k_features", "hash: k_plain_morton + k_hash_insert", "grids: memset + k_bitgrid_set", "adjacency count: k_adj_count + 2 scans",
       "adjacency fill: k_adj_fill", "weight rows: k_rows_fill (evaluate, order by weight cell, write once)", "weight rows: k_rows_sort (rows longer than 256 entries)", "local graphs: k_local_graph_rows",
       "local graphs: k_local_graph2 (general / fallback)", "mutual filter: k_mutual(_mask)", "closest check: k_collect_singles + k_closest_round_warp rounds",

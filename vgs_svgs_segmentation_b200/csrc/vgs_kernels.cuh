@@ -350,7 +350,10 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float* __restrict__ rec
   keys[u] = morton_encode((uint32_t)cx & 0x1fffffu, (uint32_t)cy & 0x1fffffu, (uint32_t)cz & 0x1fffffu);
   vals[u] = (uint32_t)u;
 }
-// one warp per unit; cstart/cunits = cell table (units sorted by cell key); fill as in k_adjacency
+// one warp per unit; cstart/cunits = cell table (units sorted by cell key).  Lanes 0..26 look up the 27 cells around the
+// unit's own at once (one round of hash probes instead of 27 dependent ones), a warp scan concatenates their member
+// ranges, and the lanes walk that list 32 candidates at a time.  fill = 0: count only; fill = 1: lists ordered by
+// (dist2, id) with a rank count (FLANN's order, independent of the order the candidates were met in).
 __global__ void __launch_bounds__(128) k_adjacency_svgs(const float* __restrict__ rec, int64_t nu, const uint32_t* __restrict__ gmin,
                                                       float cell, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ cunits,
                                                       const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
@@ -366,31 +369,45 @@ __global__ void __launch_bounds__(128) k_adjacency_svgs(const float* __restrict_
   const float qx = rec[v * REC_FLOATS], qy = rec[v * REC_FLOATS + 1], qz = rec[v * REC_FLOATS + 2];
   int cx, cy, cz;
   cell_of(rec + v * REC_FLOATS, gmin, cell, cx, cy, cz);
-  int count = 0;
-  for (int d = 0; d < 27; d++) {
-    const int x = cx + d / 9 - 1, y = cy + (d / 3) % 3 - 1, z = cz + d % 3 - 1;
-    if (x < 0 || y < 0 || z < 0) continue;
-    const int c = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
-    if (c < 0) continue;
-    const uint32_t s = cstart[c], e = cstart[c + 1];
-    for (uint32_t b = s; b < e; b += 32) {
-      const uint32_t i = b + lane;
-      int id = -1;
-      float d2 = 0.f;
-      if (i < e) {
-        id = (int)cunits[i];
-        const float* t = rec + (int64_t)id * REC_FLOATS;
-        const float dx = qx - t[0], dy = qy - t[1], dz = qz - t[2];
-        d2 = 0.f; d2 += dx * dx; d2 += dy * dy; d2 += dz * dz;
-        if (!(d2 < r2)) id = -1;
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
-      if (fill && id >= 0) {
-        const int pos = count + __popc(bal & ((1u << lane) - 1u));
-        if (pos < cap) { sd2[pos] = d2; sid[pos] = id; }
-      }
-      count += __popc(bal);
+  // lane d < 27: member range of cell d
+  uint32_t s0 = 0, n0 = 0;
+  if (lane < 27) {
+    const int x = cx + lane / 9 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane % 3 - 1;
+    if (x >= 0 && y >= 0 && z >= 0) {
+      const int c = hash_lookup(tk, tv, mask, morton_encode((uint32_t)x, (uint32_t)y, (uint32_t)z));
+      if (c >= 0) { s0 = cstart[c]; n0 = cstart[c + 1] - s0; }
     }
+  }
+  __syncwarp();                                              // the probe loops end at different iterations
+  const uint32_t incl = warp_incl_scan(n0, lane);            // candidates of the cells up to and including this lane's
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  int count = 0;
+  for (uint32_t b = 0; b < total; b += 32) {
+    const uint32_t t = b + lane;
+    const uint32_t tt = min(t, total - 1u);      // every lane takes part in the shuffles below
+    // cell of candidate tt = first lane whose inclusive count exceeds tt (a 5-step search over the lanes' counts)
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const uint32_t probe = __shfl_sync(0xffffffffu, incl, min(lo + step - 1, 31));
+      if (lo + step <= 31 && probe <= tt) lo += step;
+    }
+    const uint32_t incl_lo = __shfl_sync(0xffffffffu, incl, lo), n_lo = __shfl_sync(0xffffffffu, n0, lo), s_lo = __shfl_sync(0xffffffffu, s0, lo);
+    int id = -1;
+    float d2 = 0.f;
+    if (t < total) {
+      id = (int)cunits[s_lo + (tt - (incl_lo - n_lo))];
+      const float* q = rec + (int64_t)id * REC_FLOATS;
+      const float dx = qx - q[0], dy = qy - q[1], dz = qz - q[2];
+      d2 = 0.f; d2 += dx * dx; d2 += dy * dy; d2 += dz * dz;
+      if (!(d2 < r2)) id = -1;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, id >= 0);
+    if (fill && id >= 0) {
+      const int pos = count + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) { sd2[pos] = d2; sid[pos] = id; }
+    }
+    count += __popc(bal);
   }
   if (count >= cap) { if (lane == 0) atomicAdd(overflow, 1ull); count = cap - 1; }
   if (!fill) { if (lane == 0) adj_cnt[v] = (uint32_t)count; return; }
@@ -834,47 +851,69 @@ __global__ void __launch_bounds__(256) k_collect_singles(const uint32_t* __restr
 }
 // one warp per single unit: lanes evaluate the candidates; the winner is the LAST candidate with the
 // largest weight (`>=` in VS.h:2281), candidates in the order slot 0 (= the COUNT), then the neighbours.
-// A single can only change between rounds when one of its candidates is itself a single with a smaller id (the only
-// dynamic eligibility rule): the first round files those singles in dep_list, the later rounds (nlist_dev = its length,
-// read on the device: no host round trip in between) visit only them.
-__global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __restrict__ list, uint32_t nlist, const uint32_t* __restrict__ adj_off,
+// A candidate with a list of more than one unit is always eligible (STATIC); a candidate that is itself a single is
+// eligible only once it has attached, and only for singles with a larger id (DYNAMIC) — the one rule that makes the
+// reference's loop order dependent.  The first round (first != 0) evaluates everything, keeps the best static
+// candidate of every single that has dynamic candidates (best_w / best_j / best_c, indexed like `singles`) and files
+// those singles in dep_list; the later rounds visit only dep_list (length read on the device: no host round trip in
+// between) and evaluate only the dynamic candidates against the kept static best.
+struct ClosestBest { float w; int j; int c; };
+__device__ __forceinline__ void closest_take(float w, int j, int c, float& bw, int& bj, int& bc) {
+  if (w >= bw) { bw = w; bj = j; bc = c; }      // per lane: j ascends, so `>=` keeps the last of equal weights
+}
+__device__ __forceinline__ void closest_reduce(float& bw, int& bj, int& bc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ow = __shfl_xor_sync(0xffffffffu, bw, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    if (oj >= 0 && (bj < 0 || ow > bw || (ow == bw && oj > bj))) { bw = ow; bj = oj; bc = oc; }
+  }
+}
+__global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __restrict__ singles, uint32_t nsingles, const uint32_t* __restrict__ adj_off,
                                                           const int32_t* __restrict__ adj_idx, const uint32_t* __restrict__ cnt1,
                                                           const float* __restrict__ rec, int64_t nu, PairParams pp, int32_t* attach,
-                                                          uint32_t* __restrict__ changed, const uint32_t* __restrict__ nlist_dev = nullptr,
-                                                          uint32_t* __restrict__ dep_list = nullptr, uint32_t* __restrict__ dep_count = nullptr) {
+                                                          uint32_t* __restrict__ changed, int first, ClosestBest* __restrict__ kept,
+                                                          uint32_t* __restrict__ dep_list, uint32_t* __restrict__ dep_count) {
   const int lane = threadIdx.x & 31;
-  const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (li >= nlist || (nlist_dev && li >= *nlist_dev)) return;
-  const int64_t i = list[li];
+  uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (first) { if (li >= nsingles) return; }
+  else { if (li >= *dep_count) return; li = dep_list[li]; }
+  const int64_t i = singles[li];
   const uint32_t off = adj_off[i];
   const int n = (int)(adj_off[i + 1] - off);
   float ri[REC_FLOATS], rc[REC_FLOATS];
   for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
-  float best = 0.f;
-  int bj = -1, bi = -1;
+  float sw = 0.f, dw = 0.f;       // best static / dynamic candidate of this lane
+  int sj = -1, sc = -1, dj = -1, dc = -1;
   bool dynamic = false;
   for (int j = lane; j <= n; j += 32) {
     const int64_t c = (j == 0) ? (int64_t)n : (int64_t)adj_idx[off + j - 1];
     if (c < 0 || c >= nu) continue;
     const uint32_t cc = cnt1[c];
-    if (cc == 1u && c < i) dynamic = true;
-    if (!(cc > 1u || (cc == 1u && c < i && ((volatile int32_t*)attach)[c] >= 0))) continue;
+    const bool is_static = cc > 1u, is_dynamic = cc == 1u && c < i;
+    if (is_dynamic) dynamic = true;
+    if (is_static ? !first : !(is_dynamic && ((volatile int32_t*)attach)[c] >= 0)) continue;   // later rounds: statics come from `kept`
     for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
     float w_ab, w_ba;
     pair_weights(ri, rc, pp, w_ab, w_ba);
-    if (w_ab >= best) { best = w_ab; bj = j; bi = (int)c; }
+    if (is_static) closest_take(w_ab, j, (int)c, sw, sj, sc);
+    else closest_take(w_ab, j, (int)c, dw, dj, dc);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ow = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oj >= 0 && (bj < 0 || ow > best || (ow == best && oj > bj))) { best = ow; bj = oj; bi = oi; }
+  closest_reduce(dw, dj, dc);
+  if (first) {
+    closest_reduce(sw, sj, sc);
+    if (__any_sync(0xffffffffu, dynamic) && lane == 0) {
+      kept[li] = ClosestBest{sw, sj, sc};
+      dep_list[atomicAdd(dep_count, 1u)] = li;
+    }
+  } else {
+    const ClosestBest k = kept[li];
+    sw = k.w; sj = k.j; sc = k.c;
   }
-  const bool any_dynamic = __any_sync(0xffffffffu, dynamic);
-  if (lane == 0) {
-    if (bi != attach[i]) { attach[i] = bi; *changed = 1u; }
-    if (dep_list && any_dynamic) dep_list[atomicAdd(dep_count, 1u)] = (uint32_t)i;
-  }
+  // the winner over both kinds: largest weight, the later slot among equals
+  float bw = sw; int bj = sj, bc = sc;
+  if (dj >= 0 && (bj < 0 || dw > bw || (dw == bw && dj > bj))) { bw = dw; bj = dj; bc = dc; }
+  if (lane == 0 && bc != attach[i]) { attach[i] = bc; *changed = 1u; }
 }
 
 // ---- stage 5d: connected components by lock-free union-find, root = smallest unit id ----

@@ -6,6 +6,7 @@
 // Third-party algorithm: parity with PCL itself is unpinned.
 #pragma once
 #include "vgs_prims.cuh"
+#include "vgs_rows.cuh"
 
 namespace vgs {
 
@@ -14,6 +15,24 @@ constexpr float VCCS_FMAX = 3.402823466e+38f;
 // the neighbour table, the seed filter and the reseeding probe hundreds of cells per warp, and a Morton interleave per
 // probe was most of their instructions
 __device__ __forceinline__ uint64_t vccs_key(uint32_t x, uint32_t y, uint32_t z) { return ((uint64_t)x << 42) | ((uint64_t)y << 21) | (uint64_t)z; }
+
+// Occupancy bits of the voxel lattice over the occupied key range + a margin (BitGrid of vgs_rows.cuh; bits == nullptr when
+// the range is too large for one).  On a surface 70-85 % of the cells a cube search visits are empty: one bit test (lanes
+// that walk along z share a word) answers those without the hash probe.  A cell outside the grid holds no voxel.
+struct VccsBits { BitGrid g; uint32_t nx; const uint32_t* bits; };
+__device__ __forceinline__ bool vccs_maybe_occupied(const VccsBits& b, long long x, long long y, long long z) {
+  if (!b.bits) return true;
+  const long long rx = x - b.g.x0, ry = y - b.g.y0, rz = z - b.g.z0;
+  if (rx < 0 || ry < 0 || rz < 0 || rx >= (long long)b.nx || ry >= (long long)b.g.ny || rz >= (long long)b.g.nz) return false;
+  const uint64_t bit = ((uint64_t)rx * b.g.ny + (uint64_t)ry) * b.g.nz + (uint64_t)rz;
+  return (__ldg(b.bits + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+__global__ void __launch_bounds__(256) k_vccs_bits_set(const uint32_t* __restrict__ key3, int64_t V, BitGrid g, uint32_t* __restrict__ bits) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const uint64_t b = bg_bit(g, (int)key3[3 * v], (int)key3[3 * v + 1], (int)key3[3 * v + 2]);
+  atomicOr(&bits[b >> 5], 1u << (b & 31));
+}
 
 // ---- computeVoxelData: voxel = float mean of its points (ascending point index), lattice key, point -> voxel ----
 __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ xyz, int stride, const uint32_t* __restrict__ perm,
@@ -46,7 +65,7 @@ __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ x
 //      moments 131 vs 184 us — a thread walks its own 108 bytes through L1, 27 far-apart streams per warp cost more) ----
 __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restrict__ key3, int64_t V, int depth,
                                                        const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
-                                                       uint64_t mask, int32_t* __restrict__ nb) {
+                                                       uint64_t mask, VccsBits ob, int32_t* __restrict__ nb) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V * 27) return;
   const int64_t v = i / 27;
@@ -54,7 +73,8 @@ __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restr
   const int64_t lim = 1ll << depth;
   const int64_t x = (int64_t)key3[3 * v] + (j / 9 - 1), y = (int64_t)key3[3 * v + 1] + ((j / 3) % 3 - 1), z = (int64_t)key3[3 * v + 2] + (j % 3 - 1);
   int id = -1;
-  if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim) id = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
+  if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim && vccs_maybe_occupied(ob, x, y, z))
+    id = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
   nb[i] = id;
 }
 
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(256) k_vccs_seed_claim(const unsigned long lon
 __global__ void __launch_bounds__(128) k_vccs_seed_filter(const unsigned long long* __restrict__ best, const int32_t* __restrict__ claim, int64_t NC,
                                                         const uint32_t* __restrict__ key3, const float* __restrict__ vxyz, int depth,
                                                         const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv, uint64_t mask,
-                                                        float r2, float min_points, int reach, uint32_t* __restrict__ flag) {
+                                                        VccsBits ob, float r2, float min_points, int reach, uint32_t* __restrict__ flag) {
   const int lane = threadIdx.x & 31;
   int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= NC) return;
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(128) k_vccs_seed_filter(const unsigned long lo
     for (int t = lane; t < side * side * side; t += 32) {
       const int64_t x = (int64_t)key3[3 * s] + (t / (side * side) - reach), y = (int64_t)key3[3 * s + 1] + ((t / side) % side - reach),
                     z = (int64_t)key3[3 * s + 2] + (t % side - reach);
-      if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim) continue;
+      if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim || !vccs_maybe_occupied(ob, x, y, z)) continue;
       const int w = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
       if (w < 0) continue;
       const float dx = vxyz[3 * (int64_t)w] - sx, dy = vxyz[3 * (int64_t)w + 1] - sy, dz = vxyz[3 * (int64_t)w + 2] - sz;
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(256) k_vccs_centroids(int64_t H, const unsigne
 //      outside.  One warp per supervoxel. ----
 __global__ void __launch_bounds__(128) k_vccs_reseed(int64_t H, const float* __restrict__ hc, const uint8_t* __restrict__ alive, double ox, double oy,
                                                    double oz, double res, int depth, const unsigned long long* __restrict__ tk,
-                                                   const uint32_t* __restrict__ tv, uint64_t mask, const float* __restrict__ vxyz,
+                                                   const uint32_t* __restrict__ tv, uint64_t mask, VccsBits ob, const float* __restrict__ vxyz,
                                                    int32_t* __restrict__ seedv) {
   const int lane = threadIdx.x & 31;
   int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -354,7 +374,7 @@ __global__ void __launch_bounds__(128) k_vccs_reseed(int64_t H, const float* __r
       unsigned long long bestk = ~0ull;
       for (int t = lane; t < side * side * side; t += 32) {
         const long long x = kx + (t / (side * side) - R), y = ky + ((t / side) % side - R), z = kz + (t % side - R);
-        if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim) continue;
+        if (x < 0 || y < 0 || z < 0 || x >= lim || y >= lim || z >= lim || !vccs_maybe_occupied(ob, x, y, z)) continue;
         const int v = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
         if (v < 0) continue;
         const float dx = vxyz[3 * (int64_t)v] - cx, dy = vxyz[3 * (int64_t)v + 1] - cy, dz = vxyz[3 * (int64_t)v + 2] - cz;
