@@ -115,7 +115,7 @@ struct vgs_context {
   DBuf bm_all, bm_used, idgrid, row_len, row_off, rows, long_rows, cstats, conn_mask;
   bool use_idgrid = false;
   uint64_t idgrid_budget = 8ull << 30;   // bytes (VGS_B200_IDGRID_MB; 0 = always the hash table)
-  DBuf fallback, uflags, singles, singles_dep, singles_best, used_list, origin_state;
+  DBuf fallback, uflags, singles, singles_dep, singles_best, closest_w, used_list, origin_state;
   bool conn0_is_mask = false;       // connect lists of stage 5a held as lattice-offset masks (VGS row kernel)
   int64_t n_fallback = 0;
   DBuf ckeysA, ckeysB, cvalsA, cvalsB, cstart, ckey, cpos, gridmin;   // SVGS centroid grid
@@ -126,7 +126,7 @@ struct vgs_context {
   int force_fallback = 0;           // test knob VGS_B200_FORCE_FALLBACK=m: the row kernel hands every m-th voxel to the general kernel
   // supervoxel generator (vgs_make_supervoxels_vccs): its own voxel table and working set
   struct {
-    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nrm, mom, bits, owner, owner2, dist, claim;
+    DBuf keysA, keysB, valsA, valsB, start, key, pos, xyz, key3, plain, ptvox, nb, nb_cnt, nb_off, nb_csr, nrm, mom, bits, owner, owner2, dist, claim;
     DBuf ckA, ckB, cvA, cvB, cstart, ckey, cpos, cell3, best, flag, rank, seedv, hc, hn, alive, acc, tk, tv, tk2, tv2;
   } vc;
   int64_t vccs_seeds = 0;
@@ -503,10 +503,10 @@ void vgs_destroy(vgs_handle h) {
                  &h->labels_out, &h->tmp, &h->fallback, &h->uflags, &h->singles, &h->ckeysA, &h->ckeysB, &h->cvalsA, &h->cvalsB,
                  &h->cstart, &h->ckey, &h->cpos, &h->gridmin, &h->d_adj_cols, &h->d_pc_cols, &h->tb_slot, &h->tb_code5, &h->tb_first,
                  &h->tb_last, &h->bm_all, &h->bm_used, &h->idgrid, &h->row_len, &h->row_off, &h->rows, &h->long_rows,
-                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state, &h->singles_dep, &h->singles_best};
+                 &h->cstats, &h->conn_mask, &h->csr_off, &h->csr_idx, &h->used_list, &h->origin_state, &h->singles_dep, &h->singles_best, &h->closest_w};
   for (DBuf* b : all) b->release();
   auto& c = h->vc;
-  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nrm, &c.mom, &c.bits,
+  DBuf* vcb[] = {&c.keysA, &c.keysB, &c.valsA, &c.valsB, &c.start, &c.key, &c.pos, &c.xyz, &c.key3, &c.plain, &c.ptvox, &c.nb, &c.nb_cnt, &c.nb_off, &c.nb_csr, &c.nrm, &c.mom, &c.bits,
                  &c.owner, &c.owner2, &c.dist, &c.claim, &c.ckA, &c.ckB, &c.cvA, &c.cvB, &c.cstart, &c.ckey, &c.cpos, &c.cell3, &c.best,
                  &c.flag, &c.rank, &c.seedv, &c.hc, &c.hn, &c.alive, &c.acc, &c.tk, &c.tv, &c.tk2, &c.tv2};
   for (DBuf* b : vcb) b->release();
@@ -914,9 +914,17 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   }
   LAUNCH(k_vccs_neighbours, (unsigned)cdiv(V * 27, 256), 256, 0, c.key3.as<uint32_t>(), V, h->depth, c.tk.as<unsigned long long>(),
          c.tv.as<uint32_t>(), vmask, ob, c.nb.as<int32_t>());
+  // the existing neighbours as a CSR (slot order kept): what every round below streams
+  CK(c.nb_cnt.reserve((size_t)(V + 1) * 4 + 16)); CK(c.nb_off.reserve((size_t)(V + 1) * 4 + 16)); CK(c.nb_csr.reserve((size_t)V * 27 * 4 + 16));
+  LAUNCH(k_vccs_nb_count, (unsigned)cdiv(V + 1, 256), 256, 0, c.nb.as<int32_t>(), V, c.nb_cnt.as<uint32_t>());
+  s = scan_u32(h, c.nb_cnt.as<uint32_t>(), c.nb_off.as<uint32_t>(), V + 1, nullptr);
+  if (s) return s;
+  LAUNCH(k_vccs_nb_compact, (unsigned)cdiv(V, 256), 256, 0, c.nb.as<int32_t>(), V, c.nb_off.as<uint32_t>(), c.nb_csr.as<int32_t>());
+  const uint32_t* nb_off = c.nb_off.as<uint32_t>();
+  const int32_t* nb_csr = c.nb_csr.as<int32_t>();
   CK(c.mom.reserve((size_t)V * sizeof(VMom) + 16));
-  LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>());
-  LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)nullptr, c.mom.as<VMom>(),
+  LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), nb_off, nb_csr, (const int32_t*)nullptr, c.mom.as<VMom>());
+  LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), nb_off, nb_csr, (const int32_t*)nullptr, c.mom.as<VMom>(),
          c.nrm.as<float>());
 
   // --- seeds ---
@@ -984,7 +992,7 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   int32_t* own_b = c.owner2.as<int32_t>();
   auto expand = [&]() -> vgs_status {
     for (int it = 1; it < depth; it++) {
-      LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, c.nb.as<int32_t>(), own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
+      LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, nb_off, nb_csr, own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
              c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
              spatial_importance, normal_importance);
       std::swap(own_a, own_b);
@@ -1000,8 +1008,8 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   if (s) return s;
   // --- refineSupervoxels(k): normals inside each supervoxel, reseed at the voxel nearest to the centroid, expand ---
   for (int it = 0; it < refine_iterations; it++) {
-    LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.mom.as<VMom>());
-    LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), c.nb.as<int32_t>(), (const int32_t*)own_a, c.mom.as<VMom>(),
+    LAUNCH(k_vccs_moments, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), nb_off, nb_csr, (const int32_t*)own_a, c.mom.as<VMom>());
+    LAUNCH(k_vccs_normals, (unsigned)cdiv(V, 128), 128, 0, V, c.xyz.as<float>(), nb_off, nb_csr, (const int32_t*)own_a, c.mom.as<VMom>(),
            c.nrm.as<float>());
     LAUNCH(k_vccs_reseed, (unsigned)cdiv(H * 32, 128), 128, 0, H, c.hc.as<float>(), c.alive.as<uint8_t>(), h->box.mn[0], h->box.mn[1], h->box.mn[2],
            (double)voxel_res, h->depth, c.tk.as<unsigned long long>(), c.tv.as<uint32_t>(), vmask, ob, c.xyz.as<float>(), c.seedv.as<int32_t>());
@@ -1632,14 +1640,17 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     uint32_t* d_changed = h->small.as<uint32_t>() + 128;
     uint32_t* d_scnt = h->small.as<uint32_t>() + 132;
     CK(h->singles.reserve((size_t)nu * 4 + 16));
-    CK(cudaMemsetAsync(d_scnt, 0, 8, h->stream));
+    CK(h->singles_best.reserve((size_t)nu * 8 + 16));          // start of every single's kept candidate weights
+    CK(cudaMemsetAsync(d_scnt, 0, 16, h->stream));             // [0] eligible, [1] all singles, [2..3] kept weights (u64)
     LAUNCH(k_collect_singles, (unsigned)cdiv(nu, 256), 256, 0, h->adj_off.as<uint32_t>(), h->conn1_cnt.as<uint32_t>(), nu, adjacency_min,
-           h->singles.as<uint32_t>(), d_scnt);
-    uint32_t scnt[2] = {0, 0};
-    CK(cudaMemcpyAsync(scnt, d_scnt, 8, cudaMemcpyDeviceToHost, h->stream));
+           h->singles.as<uint32_t>(), d_scnt, h->singles_best.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(d_scnt + 2));
+    uint32_t scnt[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(scnt, d_scnt, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(stream_wait(h->stream));
-    // The first round visits every eligible single and files the ones whose result can still move (a candidate that is a
-    // smaller-id single) in a sublist; the following rounds visit only that sublist (its length is read on the device).
+    const unsigned long long n_kept = (unsigned long long)scnt[2] | ((unsigned long long)scnt[3] << 32);
+    // The first round visits every eligible single, keeps the candidate weights and files the singles whose result can
+    // still move (a candidate that is a smaller-id single) in a sublist; the following rounds visit only that sublist (its
+    // length is read on the device) and pick from the kept weights.
     // Rounds are launched three at a time with one flag each and read back together (a round costs microseconds, a host
     // round trip more): the fixed point is reached when a round changes nothing.
     int rounds = 0;
@@ -1647,7 +1658,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
     uint32_t* d_dep_cnt = h->small.as<uint32_t>() + 136;
     if (more) {
       CK(h->singles_dep.reserve((size_t)scnt[0] * 4 + 16));
-      CK(h->singles_best.reserve((size_t)scnt[0] * sizeof(ClosestBest) + 16));
+      CK(h->closest_w.reserve((size_t)n_kept * 4 + 16));              // candidate weights of the eligible singles
       CK(cudaMemsetAsync(d_dep_cnt, 0, 4, h->stream));
     }
     while (more) {
@@ -1656,7 +1667,7 @@ static vgs_status segment_finish(vgs_handle h, const vgs_sigmas* sg, float cut_t
       for (int b = 0; b < BATCH; b++)
         LAUNCH(k_closest_round_warp, (unsigned)cdiv((int64_t)scnt[0] * 32, 128), 128, 0, h->singles.as<uint32_t>(), scnt[0],
                h->adj_off.as<uint32_t>(), h->adj_idx.as<int32_t>(), h->conn1_cnt.as<uint32_t>(), h->rec.as<float>(), nu, gp.pp,
-               h->attach.as<int32_t>(), d_changed + b, (rounds == 0 && b == 0) ? 1 : 0, h->singles_best.as<ClosestBest>(),
+               h->attach.as<int32_t>(), d_changed + b, (rounds == 0 && b == 0) ? 1 : 0, h->closest_w.as<float>(), h->singles_best.as<unsigned long long>(),
                h->singles_dep.as<uint32_t>(), d_dep_cnt);
       uint32_t changed[BATCH] = {0, 0, 0};
       CK(cudaMemcpyAsync(changed, d_changed, 4 * BATCH, cudaMemcpyDeviceToHost, h->stream));

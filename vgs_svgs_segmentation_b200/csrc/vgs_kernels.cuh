@@ -839,41 +839,34 @@ __global__ void __launch_bounds__(128) k_mutual(const uint32_t* __restrict__ adj
 //      that already attached.  attach[i] depends only on attach[c], c < i, hence iterating to a
 //      fixed point reproduces the sequential result.  One warp per single unit (k_closest_round_warp). ----
 
-// units whose list is {self} after the mutual filter and that have enough neighbours (VS.h:2199-2201)
+// units whose list is {self} after the mutual filter and that have enough neighbours (VS.h:2199-2201); woff (optional) =
+// start of the single's n + 1 kept candidate weights in a compact buffer, wtotal = its running size
 __global__ void __launch_bounds__(256) k_collect_singles(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ cnt1, int64_t nu,
-                                                       int adjacency_min, uint32_t* __restrict__ list, uint32_t* __restrict__ counts /* [0]=eligible [1]=all singles */) {
+                                                       int adjacency_min, uint32_t* __restrict__ list, uint32_t* __restrict__ counts /* [0]=eligible [1]=all singles */,
+                                                       unsigned long long* __restrict__ woff = nullptr, unsigned long long* __restrict__ wtotal = nullptr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nu || cnt1[i] != 1u) return;
   atomicAdd(&counts[1], 1u);
   const int n = (int)(adj_off[i + 1] - adj_off[i]);
   if (!(n + 1 > adjacency_min)) return;
-  list[atomicAdd(&counts[0], 1u)] = (uint32_t)i;
+  const uint32_t slot = atomicAdd(&counts[0], 1u);
+  list[slot] = (uint32_t)i;
+  if (woff) woff[slot] = atomicAdd(wtotal, (unsigned long long)(n + 1));
 }
 // one warp per single unit: lanes evaluate the candidates; the winner is the LAST candidate with the
 // largest weight (`>=` in VS.h:2281), candidates in the order slot 0 (= the COUNT), then the neighbours.
-// A candidate with a list of more than one unit is always eligible (STATIC); a candidate that is itself a single is
-// eligible only once it has attached, and only for singles with a larger id (DYNAMIC) — the one rule that makes the
-// reference's loop order dependent.  The first round (first != 0) evaluates everything, keeps the best static
-// candidate of every single that has dynamic candidates (best_w / best_j / best_c, indexed like `singles`) and files
-// those singles in dep_list; the later rounds visit only dep_list (length read on the device: no host round trip in
-// between) and evaluate only the dynamic candidates against the kept static best.
-struct ClosestBest { float w; int j; int c; };
-__device__ __forceinline__ void closest_take(float w, int j, int c, float& bw, int& bj, int& bc) {
-  if (w >= bw) { bw = w; bj = j; bc = c; }      // per lane: j ascends, so `>=` keeps the last of equal weights
-}
-__device__ __forceinline__ void closest_reduce(float& bw, int& bj, int& bc) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ow = __shfl_xor_sync(0xffffffffu, bw, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oc = __shfl_xor_sync(0xffffffffu, bc, o);
-    if (oj >= 0 && (bj < 0 || ow > bw || (ow == bw && oj > bj))) { bw = ow; bj = oj; bc = oc; }
-  }
-}
+// A candidate with a list of more than one unit is always eligible; a candidate that is itself a single is eligible only
+// once it has attached, and only for singles with a larger id — the one rule that makes the reference's loop order
+// dependent.  Weights never change between rounds, only that eligibility: the first round (first != 0) evaluates the
+// weight of every candidate that is or can become eligible and keeps it (n + 1 floats per single from woff[slot] in
+// wcache; -1 = never eligible) and files the singles that have such "dynamic" candidates in dep_list; the later rounds
+// visit only dep_list (length read on the device: no host round trip in between) and pick from the kept weights.
 __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __restrict__ singles, uint32_t nsingles, const uint32_t* __restrict__ adj_off,
                                                           const int32_t* __restrict__ adj_idx, const uint32_t* __restrict__ cnt1,
                                                           const float* __restrict__ rec, int64_t nu, PairParams pp, int32_t* attach,
-                                                          uint32_t* __restrict__ changed, int first, ClosestBest* __restrict__ kept,
-                                                          uint32_t* __restrict__ dep_list, uint32_t* __restrict__ dep_count) {
+                                                          uint32_t* __restrict__ changed, int first, float* __restrict__ wcache,
+                                                          const unsigned long long* __restrict__ woff, uint32_t* __restrict__ dep_list,
+                                                          uint32_t* __restrict__ dep_count) {
   const int lane = threadIdx.x & 31;
   uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (first) { if (li >= nsingles) return; }
@@ -881,39 +874,48 @@ __global__ void __launch_bounds__(128) k_closest_round_warp(const uint32_t* __re
   const int64_t i = singles[li];
   const uint32_t off = adj_off[i];
   const int n = (int)(adj_off[i + 1] - off);
+  const unsigned long long wbase = woff[li];
   float ri[REC_FLOATS], rc[REC_FLOATS];
-  for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
-  float sw = 0.f, dw = 0.f;       // best static / dynamic candidate of this lane
-  int sj = -1, sc = -1, dj = -1, dc = -1;
+  if (first)
+    for (int q = 0; q < REC_FLOATS; q++) ri[q] = rec[i * REC_FLOATS + q];
+  float best = 0.f;
+  int bj = -1, bi = -1;
   bool dynamic = false;
   for (int j = lane; j <= n; j += 32) {
     const int64_t c = (j == 0) ? (int64_t)n : (int64_t)adj_idx[off + j - 1];
-    if (c < 0 || c >= nu) continue;
-    const uint32_t cc = cnt1[c];
-    const bool is_static = cc > 1u, is_dynamic = cc == 1u && c < i;
-    if (is_dynamic) dynamic = true;
-    if (is_static ? !first : !(is_dynamic && ((volatile int32_t*)attach)[c] >= 0)) continue;   // later rounds: statics come from `kept`
-    for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
-    float w_ab, w_ba;
-    pair_weights(ri, rc, pp, w_ab, w_ba);
-    if (is_static) closest_take(w_ab, j, (int)c, sw, sj, sc);
-    else closest_take(w_ab, j, (int)c, dw, dj, dc);
-  }
-  closest_reduce(dw, dj, dc);
-  if (first) {
-    closest_reduce(sw, sj, sc);
-    if (__any_sync(0xffffffffu, dynamic) && lane == 0) {
-      kept[li] = ClosestBest{sw, sj, sc};
-      dep_list[atomicAdd(dep_count, 1u)] = li;
+    float* slot = wcache + wbase + j;
+    float w = -1.0f;
+    bool is_dynamic = false;
+    if (c >= 0 && c < nu) {
+      const uint32_t cc = cnt1[c];
+      is_dynamic = cc == 1u && c < i;
+      if (first) {
+        if (cc > 1u || is_dynamic) {
+          for (int t = 0; t < REC_FLOATS; t++) rc[t] = rec[c * REC_FLOATS + t];
+          float w_ab, w_ba;
+          pair_weights(ri, rc, pp, w_ab, w_ba);
+          w = w_ab >= 0.f ? w_ab : -1.0f;            // a NaN weight never wins (`>=` is false)
+        }
+      } else {
+        w = *slot;
+      }
     }
-  } else {
-    const ClosestBest k = kept[li];
-    sw = k.w; sj = k.j; sc = k.c;
+    if (first) *slot = w;
+    if (is_dynamic) dynamic = true;
+    if (w < 0.f || (is_dynamic && ((volatile int32_t*)attach)[c] < 0)) continue;
+    if (w >= best) { best = w; bj = j; bi = (int)c; }
   }
-  // the winner over both kinds: largest weight, the later slot among equals
-  float bw = sw; int bj = sj, bc = sc;
-  if (dj >= 0 && (bj < 0 || dw > bw || (dw == bw && dj > bj))) { bw = dw; bj = dj; bc = dc; }
-  if (lane == 0 && bc != attach[i]) { attach[i] = bc; *changed = 1u; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ow = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oj >= 0 && (bj < 0 || ow > best || (ow == best && oj > bj))) { best = ow; bj = oj; bi = oi; }
+  }
+  const bool any_dynamic = __any_sync(0xffffffffu, dynamic);
+  if (lane == 0) {
+    if (bi != attach[i]) { attach[i] = bi; *changed = 1u; }
+    if (first && any_dynamic) dep_list[atomicAdd(dep_count, 1u)] = li;
+  }
 }
 
 // ---- stage 5d: connected components by lock-free union-find, root = smallest unit id ----

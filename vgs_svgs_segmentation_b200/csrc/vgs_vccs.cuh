@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) k_vccs_voxels(const float* __restrict__ x
 
 // ---- OctreePointCloudAdjacency::computeNeighbors: the 27 lattice cells around a voxel, self included.
 //      Table layout nb[v * 27 + j] (measured against the slot-major layout nb[j * V + v]: expand 95 vs 112 us, plane-fit
-//      moments 131 vs 184 us — a thread walks its own 108 bytes through L1, 27 far-apart streams per warp cost more) ----
+//      moments 131 vs 184 us — a thread walks its own 108 bytes through L1, 27 far-apart streams per warp cost more);
+//      consumed once by k_vccs_nb_count / k_vccs_nb_compact ----
 __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restrict__ key3, int64_t V, int depth,
                                                        const unsigned long long* __restrict__ tk, const uint32_t* __restrict__ tv,
                                                        uint64_t mask, VccsBits ob, int32_t* __restrict__ nb) {
@@ -76,6 +77,27 @@ __global__ void __launch_bounds__(256) k_vccs_neighbours(const uint32_t* __restr
   if (x >= 0 && y >= 0 && z >= 0 && x < lim && y < lim && z < lim && vccs_maybe_occupied(ob, x, y, z))
     id = hash_lookup(tk, tv, mask, vccs_key((uint32_t)x, (uint32_t)y, (uint32_t)z));
   nb[i] = id;
+}
+
+// The rounds below only ever want the EXISTING neighbours (about 10 of the 27 slots on a surface): the table is compacted once
+// into a CSR (slot order kept), which cuts the bytes every expansion round and plane fit streams by ~2.7x.
+__global__ void __launch_bounds__(256) k_vccs_nb_count(const int32_t* __restrict__ nb, int64_t V, uint32_t* __restrict__ cnt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > V) return;
+  int c = 0;
+  if (v < V)
+    for (int j = 0; j < 27; j++) c += nb[v * 27 + j] >= 0 ? 1 : 0;
+  cnt[v] = (uint32_t)c;          // cnt[V] = 0: the scan then yields the end of the last list
+}
+__global__ void __launch_bounds__(256) k_vccs_nb_compact(const int32_t* __restrict__ nb, int64_t V, const uint32_t* __restrict__ off,
+                                                       int32_t* __restrict__ out) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  uint32_t p = off[v];
+  for (int j = 0; j < 27; j++) {
+    const int u = nb[v * 27 + j];
+    if (u >= 0) out[p++] = u;
+  }
 }
 
 __device__ __forceinline__ float vccs_dot3(float ax, float ay, float az, float bx, float by, float bz) { return (ax * bx + ay * by) + az * bz; }
@@ -94,8 +116,8 @@ __device__ __forceinline__ void vccs_q3(const float* __restrict__ vxyz, int64_t 
   q[1] = __double2ll_rn((double)vxyz[3 * w + 1] * 1048576.0);
   q[2] = __double2ll_rn((double)vxyz[3 * w + 2] * 1048576.0);
 }
-__global__ void __launch_bounds__(128) k_vccs_moments(int64_t V, const float* __restrict__ vxyz, const int32_t* __restrict__ nb,
-                                                    const int32_t* __restrict__ owner, VMom* __restrict__ mom) {
+__global__ void __launch_bounds__(128) k_vccs_moments(int64_t V, const float* __restrict__ vxyz, const uint32_t* __restrict__ nb_off,
+                                                    const int32_t* __restrict__ nb, const int32_t* __restrict__ owner, VMom* __restrict__ mom) {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= V) return;
   int f = -2;
@@ -105,9 +127,9 @@ __global__ void __launch_bounds__(128) k_vccs_moments(int64_t V, const float* __
   VMom A;
   A.n = 0; A.s[0] = A.s[1] = A.s[2] = 0;
   for (int i = 0; i < 6; i++) A.m[i] = 0;
-  for (int k = 0; k < 27; k++) {
-    const int w = nb[u * 27 + k];
-    if (w < 0 || (f >= 0 && owner[w] != f)) continue;
+  for (uint32_t k = nb_off[u], ke = nb_off[u + 1]; k < ke; k++) {
+    const int w = nb[k];
+    if (f >= 0 && owner[w] != f) continue;
     long long qw[3];
     vccs_q3(vxyz, w, qw);
     const long long x = qw[0] - qu[0], y = qw[1] - qu[1], z = qw[2] - qu[2];
@@ -118,8 +140,8 @@ __global__ void __launch_bounds__(128) k_vccs_moments(int64_t V, const float* __
   out[0] = make_longlong2(A.n, A.s[0]); out[1] = make_longlong2(A.s[1], A.s[2]); out[2] = make_longlong2(A.m[0], A.m[1]);
   out[3] = make_longlong2(A.m[2], A.m[3]); out[4] = make_longlong2(A.m[4], A.m[5]);
 }
-__global__ void __launch_bounds__(128) k_vccs_normals(int64_t V, const float* __restrict__ vxyz, const int32_t* __restrict__ nb,
-                                                    const int32_t* __restrict__ owner, const VMom* __restrict__ mom,
+__global__ void __launch_bounds__(128) k_vccs_normals(int64_t V, const float* __restrict__ vxyz, const uint32_t* __restrict__ nb_off,
+                                                    const int32_t* __restrict__ nb, const int32_t* __restrict__ owner, const VMom* __restrict__ mom,
                                                     float* __restrict__ nrm) {
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
@@ -129,9 +151,9 @@ __global__ void __launch_bounds__(128) k_vccs_normals(int64_t V, const float* __
   long long qv[3];
   vccs_q3(vxyz, v, qv);
   long long n = filter == -2 ? 1 : 0, S0 = 0, S1 = 0, S2 = 0, M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0;
-  for (int j = 0; j < 27; j++) {
-    const int u = nb[v * 27 + j];
-    if (u < 0 || (filter >= 0 && owner[u] != filter)) continue;
+  for (uint32_t j = nb_off[v], je = nb_off[v + 1]; j < je; j++) {
+    const int u = nb[j];
+    if (filter >= 0 && owner[u] != filter) continue;
     long long qu[3];
     vccs_q3(vxyz, u, qu);
     const long long tx = qu[0] - qv[0], ty = qu[1] - qv[1], tz = qu[2] - qv[2];
@@ -265,7 +287,7 @@ __global__ void __launch_bounds__(256) k_vccs_helpers(const unsigned long long* 
 // ---- expandSupervoxels, one synchronous round: a voxel goes to the supervoxel (among the owners of its 26
 //      neighbours) whose centroid is nearest in voxelDataDistance, if that beats its best distance so far;
 //      ties to the smaller label (the sequential reference lets the first, i.e. smaller, label win) ----
-__global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const int32_t* __restrict__ nb, const int32_t* __restrict__ owner_old,
+__global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const uint32_t* __restrict__ nb_off, const int32_t* __restrict__ nb, const int32_t* __restrict__ owner_old,
                                                    int32_t* __restrict__ owner_new, float* __restrict__ dist, const float* __restrict__ vxyz,
                                                    const float* __restrict__ nrm, const float* __restrict__ hc, const float* __restrict__ hn,
                                                    const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn) {
@@ -278,9 +300,8 @@ __global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const int32_t* _
   const float qx = nrm[3 * v], qy = nrm[3 * v + 1], qz = nrm[3 * v + 2];
   // (measured and rejected: fetching the 27 neighbour ids and then their 27 owners into registers first — 104 vs 95 us)
   int last = -1;
-  for (int j = 0; j < 27; j++) {
-    const int u = nb[v * 27 + j];
-    if (u < 0) continue;
+  for (uint32_t j = nb_off[v], je = nb_off[v + 1]; j < je; j++) {
+    const int u = nb[j];
     const int h = owner_old[u];
     if (h < 0 || h == own || h == last || !alive[h]) continue;   // h == last: same candidate again, same distance
     last = h;
