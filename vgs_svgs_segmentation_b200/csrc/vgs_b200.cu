@@ -991,15 +991,17 @@ vgs_status vgs_make_supervoxels_vccs(vgs_handle h, float seed_resolution, float 
   int32_t* own_a = c.owner.as<int32_t>();
   int32_t* own_b = c.owner2.as<int32_t>();
   auto expand = [&]() -> vgs_status {
+    // centroid sums of the phase's starting owners (the seeds), then kept current by the rounds
+    unsigned long long* d_acc = c.acc.as<unsigned long long>();
+    unsigned long long* d_cnt = d_acc + (size_t)H * 6;                  // acc (6 x u64 per helper) and cnt live in one buffer
+    CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 56, h->stream));
+    LAUNCH(k_vccs_accumulate, (unsigned)cdiv(cdiv(V, VCCS_ACC_RUN), 256), 256, 0, V, own_a, c.xyz.as<float>(), c.nrm.as<float>(), d_acc, d_cnt);
     for (int it = 1; it < depth; it++) {
       LAUNCH(k_vccs_expand, (unsigned)cdiv(V, 256), 256, 0, V, nb_off, nb_csr, own_a, own_b, c.dist.as<float>(), c.xyz.as<float>(),
              c.nrm.as<float>(), c.hc.as<float>(), c.hn.as<float>(), c.alive.as<uint8_t>(), seed_resolution, color_importance,
-             spatial_importance, normal_importance);
+             spatial_importance, normal_importance, d_acc, d_cnt);
       std::swap(own_a, own_b);
-      CK(cudaMemsetAsync(c.acc.p, 0, (size_t)H * 56, h->stream));      // acc (6 x u64 per helper) and cnt live in one buffer
-      LAUNCH(k_vccs_accumulate, (unsigned)cdiv(cdiv(V, VCCS_ACC_RUN), 256), 256, 0, V, own_a, c.xyz.as<float>(), c.nrm.as<float>(), c.acc.as<unsigned long long>(),
-             c.acc.as<unsigned long long>() + (size_t)H * 6);
-      LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, c.acc.as<unsigned long long>(), c.acc.as<unsigned long long>() + (size_t)H * 6, c.hc.as<float>(),
+      LAUNCH(k_vccs_centroids, (unsigned)cdiv(H, 256), 256, 0, H, d_acc, d_cnt, c.hc.as<float>(),
              c.hn.as<float>(), c.alive.as<uint8_t>());
     }
     return VGS_OK;

@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) k_vccs_helpers(const unsigned long long* 
 __global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const uint32_t* __restrict__ nb_off, const int32_t* __restrict__ nb, const int32_t* __restrict__ owner_old,
                                                    int32_t* __restrict__ owner_new, float* __restrict__ dist, const float* __restrict__ vxyz,
                                                    const float* __restrict__ nrm, const float* __restrict__ hc, const float* __restrict__ hn,
-                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn) {
+                                                   const uint8_t* __restrict__ alive, float seed_res, float wc, float ws, float wn,
+                                                   unsigned long long* __restrict__ acc, unsigned long long* __restrict__ cnt) {
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   const int own = owner_old[v];
@@ -314,9 +315,32 @@ __global__ void __launch_bounds__(256) k_vccs_expand(int64_t V, const uint32_t* 
   }
   owner_new[v] = bh;
   dist[v] = bd;
+  // SupervoxelHelper::updateCentroid: the fixed-point sums are exact integers, so a voxel that changes hands is simply taken
+  // out of its old supervoxel's sums and put into the new one's (k_vccs_accumulate builds them once per expansion phase)
+  if (bh != own) {
+    const unsigned long long x = (unsigned long long)__double2ll_rn((double)px * 1048576.0), y = (unsigned long long)__double2ll_rn((double)py * 1048576.0),
+                             z = (unsigned long long)__double2ll_rn((double)pz * 1048576.0);
+    const bool hasn = qx == qx;           // NaN normals (isolated voxels) contribute nothing
+    unsigned long long nx = 0, ny = 0, nz = 0;
+    if (hasn) {
+      nx = (unsigned long long)__double2ll_rn((double)qx * 1073741824.0); ny = (unsigned long long)__double2ll_rn((double)qy * 1073741824.0);
+      nz = (unsigned long long)__double2ll_rn((double)qz * 1073741824.0);
+    }
+    if (own >= 0) {
+      unsigned long long* a = acc + (int64_t)own * 6;
+      atomicAdd(a + 0, 0ull - x); atomicAdd(a + 1, 0ull - y); atomicAdd(a + 2, 0ull - z);
+      if (hasn) { atomicAdd(a + 3, 0ull - nx); atomicAdd(a + 4, 0ull - ny); atomicAdd(a + 5, 0ull - nz); }
+      atomicAdd(cnt + own, ~0ull);        // - 1
+    }
+    unsigned long long* a = acc + (int64_t)bh * 6;       // bh >= 0: a voxel never goes back to "no owner"
+    atomicAdd(a + 0, x); atomicAdd(a + 1, y); atomicAdd(a + 2, z);
+    if (hasn) { atomicAdd(a + 3, nx); atomicAdd(a + 4, ny); atomicAdd(a + 5, nz); }
+    atomicAdd(cnt + bh, 1ull);
+  }
 }
 
 // ---- SupervoxelHelper::updateCentroid with order-independent sums: 2^-20 fixed point for xyz, 2^-30 for normals.
+//      Runs ONCE per expansion phase (over the seeds); the rounds keep the sums current with the voxels that change hands.
 //      Consecutive voxels (Morton order) mostly share their supervoxel: a thread walks VCCS_ACC_RUN consecutive voxels and
 //      issues its seven atomics only when the owner changes.  (Measured and rejected: warp-level aggregation with
 //      match_any / REDUX over run masks — 138 us per round against 56 us for one set of atomics per voxel.) ----
