@@ -33,6 +33,10 @@ def test_no_cpu_fallback(built_lib):
     with pytest.raises(capi.VgsError) as e:
         capi.Handle()
     assert e.value.status == 5 and "no CPU path" in str(e.value)
+    with pytest.raises(capi.VgsError) as e:      # the pooled lifecycle of the drop-in classes fails the same way
+        capi.Handle(pooled=True)
+    assert e.value.status == 5 and "no CPU path" in str(e.value)
+    capi.load().vgs_pool_trim()                  # nothing parked: a no-op
 
 
 def test_product_does_not_import_oracle():
