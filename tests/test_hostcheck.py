@@ -84,3 +84,20 @@ def test_morton_roundtrip(hc):
         out = (C.c_uint32 * 3)()
         hc.hc_demorton(C.c_uint64(m), out)
         assert list(out) == k
+
+
+def test_fast_acos_exp_equal_the_library_rounding():
+    """csrc/vgs_math.cuh: the short float-rounded acos / exp evaluations (IEEE operations only: same bits on host and device)
+    against (float)acos((double)x) / (float)exp(y) — every 64th float of [-1, 1], every 64th weight argument, 2e7 random
+    exponents (tools/fastmath_check.cpp without an argument checks EVERY float: 6.5e9 evaluations, 0 differences)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_build", "fastmath_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fopenmp", os.path.join(root, "tools", "fastmath_check.cpp"), "-o", exe]
+    if "fma" in open("/proc/cpuinfo").read():
+        cmd.insert(1, "-mfma")          # hardware fma: the same results as libm's exact software fma, much faster
+    subprocess.run(cmd, check=True)
+    r = subprocess.run([exe, "quick"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr

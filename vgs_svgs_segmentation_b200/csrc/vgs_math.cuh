@@ -30,8 +30,113 @@ VGS_HD double vgs_dacos(double x) { return acos(x); }
 VGS_HD double vgs_dexp(double x) { return exp(x); }
 #endif
 
+// ---- the float-rounded acos / exp of pair_weights: a short evaluation + a rounding-boundary test ----
+// pair_weights needs (float)acos((double)x) four times and (float)exp(y) up to three times per pair; the library double
+// functions behind them are 131 and 60 SASS instructions, a third of the pair kernels.  Only the FLOAT rounding of the result
+// is used, so a polynomial with a relative error below 2^-49 suffices whenever the value is not within VGS_FM_REL of a
+// float rounding boundary — in that case (about one call in 2^19) the library function decides, as before.  The fast
+// path uses IEEE operations only (fma, +, *, sqrt, rint, conversions), so this header computes the same bits on the host:
+// tools/fastmath_check.cpp compares vgs_acosf_cr with (float)acos((double)x) for EVERY float in [-1, 1] (and the pi - acos
+// pair, and exp over 4e9 arguments of the pair kernels' range): no difference, i.e. results are unchanged.
+constexpr double VGS_FM_REL = 1.1368683772161603e-13;   // 2^-43: > 30x the error bound of the evaluations below
+constexpr double VGS_FM_ABS = 2.2737367544323206e-13;   // 2^-42, absolute margin for pi - acos (the error of acos is < 2^-48)
+// Polynomial coefficients, highest degree first.  On the device they live in constant memory: an FP64 instruction takes a
+// constant-bank operand directly, an immediate double costs two extra (uniform-datapath) instructions per coefficient.
+#if defined(__CUDA_ARCH__)
+#define VGS_COEF_TABLE static __constant__ double
+#else
+#define VGS_COEF_TABLE static const double
+#endif
+// (asin(sqrt t) / sqrt t - 1) / t on [0, 1/4], degree 10 (interpolation at Chebyshev nodes; relative error of asin 2^-50)
+VGS_COEF_TABLE vgs_c_asin[11] = {0x1.c8a4a8d5d7026p-6, -0x1.bf16e7c9f283cp-8, 0x1.fa1b2b4831188p-7, 0x1.512bc40e88a9ep-7,
+                                 0x1.cf5ed14c7cb7ep-7, 0x1.1c0d74beb3610p-6,  0x1.6e8f34a32a3ecp-6, 0x1.f1c6ff7f5507fp-6,
+                                 0x1.6db6dba99e56dp-5, 0x1.33333333030cfp-4,  0x1.55555555555bbp-3};
+// exp(r) on |r| <= ln2 / 2, degree 10 (relative error 2^-51); the constant term 1 is added by the last fma
+VGS_COEF_TABLE vgs_c_exp[10] = {0x1.28a2ca617b969p-22, 0x1.72fafebdaf273p-19, 0x1.a019a6611cad5p-16, 0x1.a01978b8b3d18p-13,
+                                0x1.6c16c17f46982p-10, 0x1.1111112ddae8bp-7,  0x1.55555555520a4p-5,  0x1.555555554b736p-3,
+                                0x1.0000000000005p-1,  0x1.000000000001ep+0};
+VGS_HD double vgs_asin_poly(double t) {
+  double p = vgs_c_asin[0];
+#pragma unroll
+  for (int i = 1; i < 11; i++) p = fma(p, t, vgs_c_asin[i]);
+  return p;
+}
+// acos(x), |x| <= 1, relative error < 2^-49 (fdlibm's case split, without its division)
+VGS_HD double vgs_acos_poly(double x) {
+  const double a = fabs(x);
+  if (a <= 0.5) {
+    const double t = x * x;
+    const double r = fma(x * t, vgs_asin_poly(t), x);                      // asin(x)
+    return 0x1.921fb54442d18p+0 - (r - 0x1.1a62633145c07p-54);              // pi/2 - asin(x)
+  }
+  const double z = (1.0 - a) * 0.5, sq = sqrt(z);
+  const double r = fma(sq * z, vgs_asin_poly(z), sq);                       // asin(sqrt((1 - |x|) / 2))
+  return x > 0 ? 2.0 * r : 0x1.921fb54442d18p+1 - (2.0 * r - 0x1.1a62633145c07p-53);
+}
+// exp(y), -60 <= y <= 2, relative error < 2^-46: y = k ln2 + r, degree-10 polynomial on |r| <= ln2 / 2, scaled by 2^k
+VGS_HD double vgs_exp_poly(double y) {
+  const double k = rint(y * 0x1.71547652b82fep+0);
+  double r = fma(-k, 6.93147180369123816490e-01, y);
+  r = fma(-k, 1.90821492927058770002e-10, r);
+  double p = vgs_c_exp[0];
+#pragma unroll
+  for (int i = 1; i < 10; i++) p = fma(p, r, vgs_c_exp[i]);
+  p = fma(p, r, 1.0);
+  union { long long i; double d; } sc;
+  sc.i = (long long)(1023 + (int)k) << 52;
+  return p * sc.d;
+}
+// the float both v (1 - rel) and v (1 + rel) round to, if they agree (v >= 0)
+VGS_HD bool vgs_float_if_sure(double v, double rel, float& out) {
+  const float lo = (float)(v * (1.0 - rel)), hi = (float)(v * (1.0 + rel));
+  out = lo;
+  return lo == hi;
+}
+#if defined(__CUDA_ARCH__)
+#define VGS_MATH_FN static __device__ __noinline__
+#else
+#define VGS_MATH_FN VGS_HD
+#endif
+// (float)acos((double)x)
+VGS_MATH_FN float vgs_acosf_cr(float x) {
+  const double xd = (double)x;
+  if (fabs(xd) <= 1.0) {
+    float f;
+    if (vgs_float_if_sure(vgs_acos_poly(xd), VGS_FM_REL, f)) return f;
+  }
+  return (float)vgs_dacos(xd);
+}
+// a = (float)acos((double)x) and pia = (float)(pi - acos((double)x)) (the subtraction in double, as pair_weights has it)
+VGS_MATH_FN void vgs_acosf_pair_cr(float x, float& a, float& pia) {
+  const double xd = (double)x, PI_D = 3.14159265358979323846;
+  if (fabs(xd) <= 1.0) {
+    const double v = vgs_acos_poly(xd), w = PI_D - v;
+    const float wlo = (float)(w - VGS_FM_ABS), whi = (float)(w + VGS_FM_ABS);
+    pia = wlo;
+    if (vgs_float_if_sure(v, VGS_FM_REL, a) && wlo == whi) return;
+  }
+  const double ad = vgs_dacos(xd);
+  a = (float)ad; pia = (float)(PI_D - ad);
+}
+// (float)exp(y)
+VGS_MATH_FN float vgs_expf_cr(double y) {
+  if (y >= -60.0 && y <= 2.0) {
+    float f;
+    if (vgs_float_if_sure(vgs_exp_poly(y), VGS_FM_REL, f)) return f;
+  }
+  return (float)vgs_dexp(y);
+}
+// (float)(c / (1 + exp(u))), c > 0
+VGS_MATH_FN float vgs_logistic_cr(double c, double u) {
+  if (u >= -60.0 && u <= 2.0) {
+    float f;
+    if (vgs_float_if_sure(c / (1 + vgs_exp_poly(u)), VGS_FM_REL, f)) return f;
+  }
+  return (float)(c / (1 + vgs_dexp(u)));
+}
+
 // ---- correctly rounded float libm (double evaluation, one rounding) ----
-VGS_HD float cr_acosf(float x) { return (float)vgs_dacos((double)x); }
+VGS_HD float cr_acosf(float x) { return vgs_acosf_cr(x); }
 VGS_HD float cr_sinf(float x) { return (float)sin((double)x); }
 VGS_HD float cr_cosf(float x) { return (float)cos((double)x); }
 VGS_HD float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
@@ -261,16 +366,17 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
         // acos(-x) = pi - acos(x) is evaluated in double and rounded once, i.e. the same correctly
         // rounded float as (float)acos(-(double)x) (the 1-ulp double error of the subtraction moves a float
         // with probability ~2^-28) — two double acos per pair instead of four.
-        const double ad1 = vgs_dacos((double)c1d), ad2 = vgs_dacos((double)c2d);
-        a1 = (double)(float)ad1; a2 = (double)(float)ad2;
-        b1 = (double)(float)(3.14159265358979323846 - ad2); b2 = (double)(float)(3.14159265358979323846 - ad1);
+        float a1f, a2f, b1f, b2f;
+        vgs_acosf_pair_cr(c1d, a1f, b2f);      // a1 = (float)acos(c1d), b2 = (float)(pi - acos(c1d))
+        vgs_acosf_pair_cr(c2d, a2f, b1f);
+        a1 = (double)a1f; a2 = (double)a2f; b1 = (double)b1f; b2 = (double)b2f;
         ads1 = (double)cr_acosf(cds);
         ads2 = PI - ads1;
       }
     }
     if (!P.svgs) {
       double max_singular = PI / 2;
-      float thr = (float)((double)(float)max_singular / (1 + vgs_dexp(-1 * 0.5 * (a12 - PI / 6))));
+      float thr = vgs_logistic_cr((double)(float)max_singular, -1 * 0.5 * (a12 - PI / 6));   // (float)(c / (1 + exp(u)))
       double ads = ads1;
       if (ads1 > ads2) ads = ads2;
       if (ads > (double)thr) { C_ab = (float)fabs(a1 - a2); C_ba = (float)fabs(b1 - b2); }
@@ -293,17 +399,17 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
     double ee = (double)qe * (double)qe;
     float qc = C_ab / P.sig_c;
     float sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-    w_ab = (float)vgs_dexp(-0.5 * (double)sd / w2);
+    w_ab = vgs_expf_cr(-0.5 * (double)sd / w2);
     if (f2u(C_ba) == f2u(C_ab)) { w_ba = w_ab; }
     else {
       qc = C_ba / P.sig_c;
       sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-      w_ba = (float)vgs_dexp(-0.5 * (double)sd / w2);
+      w_ba = vgs_expf_cr(-0.5 * (double)sd / w2);
     }
   } else {
     float sd = (float)sqrt((double)S * (double)S / (double)P.sig_p + (double)A * (double)A / (double)P.sig_n +
                            (double)E * (double)E / (double)P.sig_e + (double)T * (double)T / (double)P.sig_o);
-    w_ab = (float)vgs_dexp(-0.5 * (double)sd / w2);
+    w_ab = vgs_expf_cr(-0.5 * (double)sd / w2);
     w_ba = w_ab;
   }
 }
