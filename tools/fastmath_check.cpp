@@ -1,4 +1,5 @@
-// fastmath_check.cpp — dev tool / proof harness for the short float-rounded acos / exp of csrc/vgs_math.cuh.
+// fastmath_check.cpp — dev tool / proof harness for the short float-rounded acos / exp of csrc/vgs_math.cuh (the
+// VGS_FAST_ROUNDED_MATH option; off in the product build: measured slower in the instruction-cache-bound pair kernels).
 // The fast paths use IEEE operations only (fma, +, *, /, sqrt, rint, conversions), so this host build computes the bits
 // the device computes.  Checked here:
 //   1. vgs_acosf_cr(x) == (float)acos((double)x) and vgs_acosf_pair_cr(x) == ((float)acos, (float)(pi - acos)) for EVERY
@@ -16,6 +17,7 @@
 #include <omp.h>
 #endif
 
+#define VGS_FAST_ROUNDED_MATH 1
 #include "../vgs_svgs_segmentation_b200/csrc/vgs_math.cuh"
 
 static float f_of(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }

@@ -30,7 +30,12 @@ VGS_HD double vgs_dacos(double x) { return acos(x); }
 VGS_HD double vgs_dexp(double x) { return exp(x); }
 #endif
 
+#ifdef VGS_FAST_ROUNDED_MATH
 // ---- the float-rounded acos / exp of pair_weights: a short evaluation + a rounding-boundary test ----
+// OFF by default (VGS_FAST_ROUNDED_MATH): measured on the 10 M-point site, k_rows_fill 2.29 -> 2.43 ms and k_local_graph2
+// 2.76 -> 2.90 ms WITH it — the two-branch evaluation + boundary test + the library fallback that has to stay make the pair
+// kernels longer (2 784 -> 3 184 SASS instructions against a 32 KB instruction cache) and the saved fp64 work does not pay for
+// it.  Kept, with its proof harness, for kernels that are not instruction-cache bound.
 // pair_weights needs (float)acos((double)x) four times and (float)exp(y) up to three times per pair; the library double
 // functions behind them are 131 and 60 SASS instructions, a third of the pair kernels.  Only the FLOAT rounding of the result
 // is used, so a polynomial with a relative error below 2^-49 suffices whenever the value is not within VGS_FM_REL of a
@@ -135,8 +140,14 @@ VGS_MATH_FN float vgs_logistic_cr(double c, double u) {
   return (float)(c / (1 + vgs_dexp(u)));
 }
 
+#endif   // VGS_FAST_ROUNDED_MATH
+
 // ---- correctly rounded float libm (double evaluation, one rounding) ----
+#ifdef VGS_FAST_ROUNDED_MATH
 VGS_HD float cr_acosf(float x) { return vgs_acosf_cr(x); }
+#else
+VGS_HD float cr_acosf(float x) { return (float)vgs_dacos((double)x); }
+#endif
 VGS_HD float cr_sinf(float x) { return (float)sin((double)x); }
 VGS_HD float cr_cosf(float x) { return (float)cos((double)x); }
 VGS_HD float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
@@ -320,6 +331,12 @@ VGS_HD int attr_flags(const float* rec, bool used) {
   return fl;
 }
 
+#ifdef VGS_FAST_ROUNDED_MATH
+VGS_HD float pw_expf(double y) { return vgs_expf_cr(y); }
+#else
+VGS_HD float pw_expf(double y) { return (float)vgs_dexp(y); }
+#endif
+
 // ---- perceptual-grouping weight of the UNORDERED pair {a,b}: returns w(a->b) and w(b->a) ----
 // measuringDistance VS.h:1597-1720 / SV.h:1756-1878 ; distanceWeight VS.h:1722-1740 / SV.h:1880-1905.
 // The two orders share S, A, T, E; only the convexity cue C differs (acosf(-x) != pi - acosf(x)
@@ -366,17 +383,27 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
         // acos(-x) = pi - acos(x) is evaluated in double and rounded once, i.e. the same correctly
         // rounded float as (float)acos(-(double)x) (the 1-ulp double error of the subtraction moves a float
         // with probability ~2^-28) — two double acos per pair instead of four.
+#ifdef VGS_FAST_ROUNDED_MATH
         float a1f, a2f, b1f, b2f;
         vgs_acosf_pair_cr(c1d, a1f, b2f);      // a1 = (float)acos(c1d), b2 = (float)(pi - acos(c1d))
         vgs_acosf_pair_cr(c2d, a2f, b1f);
         a1 = (double)a1f; a2 = (double)a2f; b1 = (double)b1f; b2 = (double)b2f;
+#else
+        const double ad1 = vgs_dacos((double)c1d), ad2 = vgs_dacos((double)c2d);
+        a1 = (double)(float)ad1; a2 = (double)(float)ad2;
+        b1 = (double)(float)(3.14159265358979323846 - ad2); b2 = (double)(float)(3.14159265358979323846 - ad1);
+#endif
         ads1 = (double)cr_acosf(cds);
         ads2 = PI - ads1;
       }
     }
     if (!P.svgs) {
       double max_singular = PI / 2;
+#ifdef VGS_FAST_ROUNDED_MATH
       float thr = vgs_logistic_cr((double)(float)max_singular, -1 * 0.5 * (a12 - PI / 6));   // (float)(c / (1 + exp(u)))
+#else
+      float thr = (float)((double)(float)max_singular / (1 + vgs_dexp(-1 * 0.5 * (a12 - PI / 6))));
+#endif
       double ads = ads1;
       if (ads1 > ads2) ads = ads2;
       if (ads > (double)thr) { C_ab = (float)fabs(a1 - a2); C_ba = (float)fabs(b1 - b2); }
@@ -399,17 +426,17 @@ VGS_HD void pair_weights(const float* A_, const float* B_, const PairParams& P, 
     double ee = (double)qe * (double)qe;
     float qc = C_ab / P.sig_c;
     float sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-    w_ab = vgs_expf_cr(-0.5 * (double)sd / w2);
+    w_ab = pw_expf(-0.5 * (double)sd / w2);
     if (f2u(C_ba) == f2u(C_ab)) { w_ba = w_ab; }
     else {
       qc = C_ba / P.sig_c;
       sd = (float)sqrt(base + (double)qc * (double)qc + ee);
-      w_ba = vgs_expf_cr(-0.5 * (double)sd / w2);
+      w_ba = pw_expf(-0.5 * (double)sd / w2);
     }
   } else {
     float sd = (float)sqrt((double)S * (double)S / (double)P.sig_p + (double)A * (double)A / (double)P.sig_n +
                            (double)E * (double)E / (double)P.sig_e + (double)T * (double)T / (double)P.sig_o);
-    w_ab = vgs_expf_cr(-0.5 * (double)sd / w2);
+    w_ab = pw_expf(-0.5 * (double)sd / w2);
     w_ba = w_ab;
   }
 }
