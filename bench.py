@@ -99,7 +99,7 @@ class ClockSampler:
                 except Exception:
                     rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
                 self.rows.append((float(sm), float(mx), int(rs)))
-                self.stop.wait(0.02)
+                self.stop.wait(0.005)
             return
         except Exception:
             pass
