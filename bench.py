@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--points", type=int, default=0, help="override the number of points of the config's scene (density kept)")
     ap.add_argument("--ref-points", type=int, default=0, help="--impl reference: 0 = the full scene of the config")
-    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--cpu-sample", type=int, default=600_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin figure (the C++ drop-in class driven like the reference's test)")
     ap.add_argument("--no-verify", action="store_true", help="N>1 slabs: skip the comparison with one single-GPU run of the whole scene")
