@@ -93,9 +93,12 @@ inline cudaError_t to_device(void* dst, const void* src, size_t bytes, int devic
     if (cudaEventRecord(e.ev_end[t], e.st[t]) != cudaSuccess) err = 1;
   };
   std::thread th[kThreads];
-  for (int t = 1; t < kThreads; t++) th[t] = std::thread(worker, t);
+  for (int t = 1; t < kThreads; t++) {
+    try { th[t] = std::thread(worker, t); }
+    catch (...) { worker(t); }          // no thread to be had (no exception may cross the C ABI): this share runs inline
+  }
   worker(0);
-  for (int t = 1; t < kThreads; t++) th[t].join();
+  for (int t = 1; t < kThreads; t++) if (th[t].joinable()) th[t].join();
   if (err) { cudaGetLastError(); return cudaErrorUnknown; }
   for (int t = 0; t < kThreads; t++)
     if ((r = cudaStreamWaitEvent(stream, e.ev_end[t], 0)) != cudaSuccess) return r;
@@ -138,9 +141,12 @@ inline cudaError_t to_host(void* dst, const void* src, size_t bytes, int device,
     }
   };
   std::thread th[kThreads];
-  for (int t = 1; t < kThreads; t++) th[t] = std::thread(worker, t);
+  for (int t = 1; t < kThreads; t++) {
+    try { th[t] = std::thread(worker, t); }
+    catch (...) { worker(t); }          // no thread to be had (no exception may cross the C ABI): this share runs inline
+  }
   worker(0);
-  for (int t = 1; t < kThreads; t++) th[t].join();
+  for (int t = 1; t < kThreads; t++) if (th[t].joinable()) th[t].join();
   if (err) { cudaGetLastError(); return cudaErrorUnknown; }
   return cudaSuccess;
 }
