@@ -85,6 +85,21 @@ def test_oracle_vccs_normals_on_a_plane():
     np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
 
 
+def test_oracle_vccs_integer_moment_normals_equal_the_float_walk():
+    """schedule 1 fits its planes from exact integer moments of the 2^-20 fixed-point voxel centroids, factorised over the two
+    rings (27 + 27 gathers); schedule 0 walks the 27 x 27 multiset in float like PCL.  Same multiset, so the two initial
+    normal fields agree to float accuracy wherever the fit is well conditioned (quantisation: 1 um)"""
+    from oracle import oracle
+    xyz, _ = _scene("site")
+    a = oracle.vccs(xyz, schedule=0, refine_iterations=0).vox_normal
+    b = oracle.vccs(xyz, schedule=1, refine_iterations=0).vox_normal
+    ok = ~np.isnan(a[:, 0])
+    assert np.array_equal(ok, ~np.isnan(b[:, 0]))           # the same voxels have too few neighbours for a fit
+    cosang = np.abs(np.sum(a[ok] * b[ok], axis=1))
+    assert (cosang > 1 - 1e-6).mean() > 0.999               # (nearly) all agree to ~1e-3 rad
+    assert np.median(1 - cosang) < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["planes", "site"])
 def test_gpu_vccs_equals_oracle_synchronous_schedule(built_lib, kind):
